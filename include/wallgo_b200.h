@@ -1,0 +1,118 @@
+/*
+ * wallgo_b200 -- C ABI of the B200-native Boltzmann hot path.
+ *
+ * The reference (Wall-Go/WallGo v1.1.2) is pure Python and has no FFI; the seam this
+ * library plugs into is the class WallGo.BoltzmannSolver (src/WallGo/boltzmann.py:37-886,
+ * constructed at src/WallGo/manager.py:605-619, consumed at
+ * src/WallGo/equationOfMotion.py:1349-1355).  Each entry point below replaces one piece of
+ * that class; the ctypes binding a maintainer adds is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - return value: 0 = ok, <0 = error (WG_ERR_*; text via wg_last_error()).  A singular pivot is
+ *     reported LAPACK-style through wg_info() (>0 = 1-based column), mirroring numpy.linalg.LinAlgError
+ *     raised from boltzmann.py:283.
+ *   - "host" pointers are read synchronously during the call; "dev" pointers are CUDA device memory
+ *     owned by the caller (e.g. torch tensors) and are used stream-ordered on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - all arrays are C-ordered float64.  n = P*(M-1)*(N-1)^2, q = (N-1)^2.
+ *     row r = ((a*(M-1)+alpha)*(N-1)+beta)*(N-1)+gamma, col c = ((b*(M-1)+i)*(N-1)+j)*(N-1)+k
+ *     (boltzmann.py:813-817, :286-292).
+ *   - handles are not thread-safe; one solver per process per GPU (the reference is single-threaded).
+ *   - there is no CPU path: every call fails with WG_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef WALLGO_B200_H
+#define WALLGO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WG_OK 0
+#define WG_ERR_ARG (-1)
+#define WG_ERR_CUDA (-2)
+#define WG_ERR_STATE (-3)
+#define WG_ERR_UNSUPPORTED (-4)
+
+typedef struct wg_solver wg_solver;
+typedef struct wg_lu wg_lu;
+
+int wg_version(void);
+const char* wg_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process (graph replays included) */
+long long wg_launch_count(void);
+/* nb: top-level LU panel width (multiple of 16, 32..256); use_graph: replay the factorisation as a CUDA graph */
+int wg_set_tuning(int nb, int use_graph);
+
+/* ---- lifecycle : BoltzmannSolver.__init__ + updateParticleList (boltzmann.py:52-139) */
+int wg_create(int P, int M, int N, int device, wg_solver** out);
+int wg_destroy(wg_solver* s);
+int wg_dims(const wg_solver* s, int* n, int* q);
+
+/* ---- static data (host pointers)
+ * grid: Grid.getCompactCoordinates / getCoordinates / getCompactificationDerivatives (grid.py:116-122, 219-274);
+ *       chi[M-1], rz[N-1], rp[N-1], pz[N-1], pp[N-1], dpzdrz[N-1], dppdrp[N-1]                           */
+int wg_set_grid(wg_solver* s, const double* chi, const double* rz, const double* rp, const double* pz,
+                const double* pp, const double* dpzdrz, const double* dppdrp);
+/* statistics[P]: +1 boson, -1 fermion (boltzmann.py:668-670) */
+int wg_set_statistics(wg_solver* s, const double* statistics);
+/* Evaluate the default-basis tables ON THE DEVICE (Cardinal in z, restricted Chebyshev in p_z,p_par,
+ * spectral derivatives): Polynomial.matrix / derivMatrix (polynomial.py:635-862) and the two Kronecker
+ * products T_rz(x)T_rp, D_rz(x)T_rp consumed by the assembly. */
+int wg_build_basis(wg_solver* s);
+/* Explicit tables for the other basis / derivative choices (boltzmann.py:673-726):
+ * Tchi,Dchi [(M-1)^2], DchiFull [(M+1)^2], Trz,Drz,Trp [(N-1)^2] */
+int wg_set_tables(wg_solver* s, const double* Tchi, const double* Dchi, const double* DchiFull,
+                  const double* Trz, const double* Drz, const double* Trp);
+int wg_get_tables(wg_solver* s, double* Tchi, double* Dchi, double* DchiFull, double* Trz, double* Drz,
+                  double* Trp);
+/* Basis-change matrices used by getDeltas: mats[3*stage+axis], stage 0 = solver basis -> Chebyshev,
+ * 1 = Chebyshev -> solver basis, 2 = solver basis -> Cardinal; axis 0 = z [(M-1)^2], 1 = pz, 2 = pp
+ * [(N-1)^2].  NULL = identity (Polynomial.changeBasis, polynomial.py:222-298). */
+int wg_set_transforms(wg_solver* s, const double* const mats[9]);
+/* Collision tensor C[a,beta,gamma,b,j,k] in the solver's momentum basis, P^2 q^2 doubles
+ * (BoltzmannSolver.setCollisionArray, boltzmann.py:125-129).  on_device: pointer is device memory. */
+int wg_set_collision(wg_solver* s, const double* C, int on_device);
+
+/* ---- per solve (device pointers, stream ordered)
+ * profiles_dev = [ T(M+1) | v(M+1) plasma frame | msq(P x (M+1)) | dxi/dchi(M-1) ]
+ * (BoltzmannSolver.setBackground + buildLinearEquations, boltzmann.py:116-123, 628-820).
+ * Writes the dense operator A (n x n, leading dimension lda >= n, even) and the source S (n).
+ * parts: bit 0 = Liouville term, bit 1 = collision term (3 = the operator; 1 and 2 give the
+ * `liouville` and `collision` arrays that buildLinearEquations also returns, boltzmann.py:820). */
+int wg_assemble(wg_solver* s, const double* profiles_dev, double vw, double collisionMultiplier, int parts,
+                double* A_dev, long long lda, double* S_dev, void* stream);
+/* np.linalg.solve(operator, source) (boltzmann.py:283): LU in place with row partial pivoting ... */
+int wg_factor(wg_solver* s, double* A_dev, long long lda, void* stream);
+/* ... and the triangular solves; b_dev (n) is overwritten by the solution.  May be called again with
+ * another right-hand side (checkLinearization re-uses the factors, boltzmann.py:541-550). */
+int wg_solve(wg_solver* s, const double* LU_dev, long long lda, double* b_dev, void* stream);
+/* synchronises `stream` and returns LAPACK-style info of the last wg_factor */
+int wg_info(wg_solver* s, void* stream, int* info_host);
+/* checkSpectralConvergence, first half (boltzmann.py:376-397): Chebyshev coefficients (kept inside the
+ * solver) and spectra_dev[(M-1)+2(N-1)] = sum|c| along (chi | pz | pp). */
+int wg_spectra(wg_solver* s, const double* deltaF_dev, double* spectra_dev, void* stream);
+/* second half + estimateTruncationError + getDeltas quadrature (boltzmann.py:296-351, 431-491, 182-238):
+ * keep* = number of coefficients kept per axis; roundtrip = 0 returns the input deltaF unchanged
+ * (ETruncationOption.NONE).  Outputs: deltaF_out_dev[n], deltas_dev[4*P*(M-1)] (Delta00,02,20,11),
+ * err_dev[4*P] (sum|c| kept, and on the last kept chi/pz/pp slice, per species). */
+int wg_moments(wg_solver* s, const double* deltaF_dev, const double* profiles_dev, int keepM, int keepPz,
+               int keepPp, int roundtrip, double* deltaF_out_dev, double* deltas_dev, double* err_dev,
+               void* stream);
+/* y = (collision part of the last assembled operator) * x   (boltzmann.py:541-545) */
+int wg_collision_apply(wg_solver* s, const double* x_dev, double* y_dev, void* stream);
+/* in-place basis change of a (P, M-1, N-1, N-1) array with the matrices of wg_set_transforms */
+int wg_change_basis(wg_solver* s, int stage, const double* in_dev, double* out_dev, void* stream);
+
+/* ---- generic dense pieces (used by the solver; exported for tests and other callers) */
+int wg_lu_create(int n, int device, wg_lu** out);
+int wg_lu_destroy(wg_lu* p);
+int wg_lu_factor(wg_lu* p, double* A_dev, long long lda, int* ipiv_dev, int* info_dev, void* stream);
+int wg_lu_solve(wg_lu* p, const double* LU_dev, long long lda, double* b_dev, void* stream);
+/* C[MxN] -= A[MxK] * B[KxN], row-major, FP64 tensor cores */
+int wg_dgemm_sub(double* C_dev, const double* A_dev, const double* B_dev, int M, int N, int K,
+                 long long ldc, long long lda, long long ldb, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,271 @@
+"""CPU-only tests: the oracle against the reference golden vectors, the host-side logic, and the
+C-ABI surface (library loads and exports every symbol of include/wallgo_b200.h; no compute)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden_names, load_golden, oracle_problem_from_golden, relmax
+
+
+# ----------------------------------------------------------------------------- oracle vs golden
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_reproduces_reference_golden(name):
+    from oracle import boltzmann_oracle as bo
+
+    g = load_golden(name)
+    pb = oracle_problem_from_golden(g)
+    for k, ref in (("Tchi", "ref_Tchi"), ("Dchi", "ref_Dchi"), ("Trz", "ref_Trz"), ("Trp", "ref_Trp"),
+                   ("Drz", "ref_Drz")):
+        assert relmax(getattr(pb.tab, k), g[ref]) < 1e-12, (name, k)
+    op, src = bo.assemble(pb)
+    assert relmax(src, g["ref_source"]) < 1e-11
+    assert relmax(op[g["ref_op_probe_rows"]], g["ref_op_probe"]) < 1e-13
+    assert relmax(op @ np.ones(op.shape[0]), g["ref_op_rowsum"]) < 1e-12
+    dF = np.linalg.solve(op, src).reshape(g["ref_deltaF"].shape)
+    assert relmax(dF, g["ref_deltaF"]) < 1e-10
+    out = bo.get_deltas(pb, g["ref_deltaF"], str(g["option"]))
+    assert tuple(out["truncatedTail"]) == tuple(bool(x) for x in g["ref_truncatedTail"])
+    assert tuple(out["spectralPeaks"]) == tuple(int(x) for x in g["ref_spectralPeaks"])
+    assert relmax(out["Deltas"], g["ref_Deltas"]) < 1e-12
+    assert relmax(out["deltaF"], g["ref_deltaF_trunc"]) < 1e-12
+    assert abs(out["truncationError"] - float(g["ref_truncationError"])) < 1e-9 * float(g["ref_truncationError"])
+    if "ref_linearization" in g:
+        c1, c2 = bo.check_linearization(pb, g["ref_deltaF"])
+        assert abs(c1 - g["ref_linearization"][0]) < 1e-9 * abs(g["ref_linearization"][0])
+        assert abs(c2 - g["ref_linearization"][1]) < 1e-8 * abs(g["ref_linearization"][1])
+
+
+def test_oracle_delta00_known_answer():
+    """Reference known-answer test tests/test_Boltzmann.py:14-85 through the oracle."""
+    from oracle import boltzmann_oracle as bo
+
+    for (M, N, a, b, c, d, e, f) in [(25, 19, 1, 2, 3, 4, 5, 6), (5, 5, 1, 1, 2, 3, 5, 8)]:
+        tab = bo.build_tables(M, N, "Cardinal", "Cardinal", "Spectral")
+        pz, pp, dpzdrz, dppdrp = bo.momentum_maps(tab.rz, tab.rp, 100.0)
+        fieldv = np.ones(M + 1)
+        fieldv[M // 2:] = 0
+        fieldv += 0.1 * np.sin(7 * 2 * np.pi * np.arange(M + 1) + 6)
+        msq = 0.5 * fieldv**2
+        T = 100 * np.ones(M + 1)
+        rz, rp = tab.rz[None, :, None], tab.rp[None, None, :]
+        E = np.sqrt(msq[1:-1, None, None] + pz[None, :, None] ** 2 + pp[None, None, :] ** 2)
+        eps = 2e-16
+        integrand = (2 * E * (1 - rz**2) * (1 - rp**2)
+                     * np.sqrt((1 - rz**2) * (1 - rp) ** 2 / (1 - rp**2 + eps)) / (np.log(2 / (1 - rp)) + eps))
+        integrand = integrand * (a + b * rz + c * rz**2) * (d + e * rp + f * rp**2)
+        pb = bo.Problem(tab=tab, xi_dxidchi=np.ones(M - 1), pz=pz, pp=pp, dpzdrz=dpzdrz, dppdrp=dppdrp, T=T,
+                        v=np.zeros(M + 1), msq=msq[None, :], vw=0.0, statistics=np.array([-1.0]),
+                        collision=np.zeros((1, N - 1, N - 1, 1, N - 1, N - 1)))
+        D = bo.moments(integrand[None, ...], pb)
+        exact = (4 * a + c) * (4 * d + f) * T[1:-1] ** 3 / 64
+        np.testing.assert_allclose(D[0, 0], exact, rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize("M,N,slope", [(7, 9, -0.1), (9, 9, -0.1), (11, 9, 0.1)])
+def test_oracle_truncation_decisions(M, N, slope):
+    """Reference test tests/test_Boltzmann.py:128-174 (Chebyshev/Chebyshev, AUTO) through the oracle."""
+    from oracle import boltzmann_oracle as bo
+
+    tab = bo.build_tables(M, N, "Chebyshev", "Chebyshev", "Spectral")
+    z, pz, pp = np.meshgrid(np.arange(M - 1), np.arange(N - 1), np.arange(N - 1), indexing="ij")
+    dF = (np.exp(slope * z - 1e-2 * pz - 1e-3 * pp) / (1 + pz) / (1 + pp) ** 2)[None, ...]
+    out, shape, _ = bo.check_spectral_convergence(dF, tab, "AUTO")
+    nT = (M - 1) // 3
+    if slope > 0:
+        assert shape == (1, M - 1 - nT, N - 1, N - 1)
+        assert np.allclose(out[:, -nT:], 0, atol=1e-2)
+    else:
+        assert shape == (1, M - 1, N - 1, N - 1)
+        assert not np.allclose(out[:, -nT:], 0)
+
+
+def test_lu_c_oracle_against_lapack():
+    so = os.path.join(ROOT, "oracle", "_build", "liblu_oracle.so")
+    if not os.path.exists(so):
+        import subprocess
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
+    lib = C.CDLL(so)
+    import scipy.linalg as sl
+    rng = np.random.default_rng(0)
+    for n in (1, 7, 64, 301):
+        A = rng.standard_normal((n, n))
+        b = rng.standard_normal(n)
+        LU = A.copy()
+        piv = np.zeros(n, dtype=np.int32)
+        assert lib.wgo_lu_factor(LU.ctypes.data_as(C.c_void_p), n, n, piv.ctypes.data_as(C.c_void_p)) == 0
+        lu_ref, piv_ref = sl.lu_factor(A)
+        assert np.array_equal(piv, piv_ref)
+        assert relmax(LU, lu_ref) < 1e-11
+        x = b.copy()
+        lib.wgo_lu_solve(LU.ctypes.data_as(C.c_void_p), n, n, piv.ctypes.data_as(C.c_void_p),
+                         x.ctypes.data_as(C.c_void_p))
+        assert relmax(x, np.linalg.solve(A, b)) < 1e-10
+    Z = np.zeros((3, 3))
+    assert lib.wgo_lu_factor(Z.ctypes.data_as(C.c_void_p), 3, 3, np.zeros(3, np.int32).ctypes.data_as(C.c_void_p)) == 1
+
+
+# ----------------------------------------------------------------------------- host logic
+@pytest.mark.parametrize("name", golden_names())
+def test_host_tables_match_reference(name):
+    from wallgo_b200 import spectral
+
+    g = load_golden(name)
+    Tchi, Dchi, DchiFull, Trz, Drz, Trp = spectral.buildTables(int(g["M"]), int(g["N"]), str(g["basisM"]),
+                                                               str(g["basisN"]), str(g["derivatives"]))
+    for mine, ref in ((Tchi, "ref_Tchi"), (Dchi, "ref_Dchi"), (Trz, "ref_Trz"), (Trp, "ref_Trp"), (Drz, "ref_Drz")):
+        assert relmax(mine, g[ref]) < 2e-13, (name, ref)
+    if str(g["basisM"]) == "Cardinal":
+        assert relmax(DchiFull[1:-1, 1:-1], Dchi) == 0.0
+
+
+@pytest.mark.parametrize("name", ["cfg1_P1_M20_N11", "small_P2_M12_N7", "simplegrid_P3_M9_N5"])
+def test_host_grid_matches_reference(name):
+    import wallgo_b200 as wb
+
+    g = load_golden(name)
+    M, N = int(g["M"]), int(g["N"])
+    grid = wb.Grid3Scales(M, N, 0.2, 0.2, 0.05, 100.0, 0.5, 0.1) if bool(g["grid3"]) else wb.Grid(M, N, 0.05, 100.0)
+    chi, rz, rp = grid.getCompactCoordinates()
+    assert relmax(chi, g["chi"]) < 1e-15 and relmax(rz, g["rz"]) < 1e-15 and relmax(rp, g["rp"]) < 1e-15
+    dxidchi, dpzdrz, dppdrp = grid.getCompactificationDerivatives()
+    assert relmax(dxidchi, g["dxidchi"]) < 1e-14
+    assert relmax(dpzdrz, g["dpzdrz"]) < 1e-15 and relmax(dppdrp, g["dppdrp"]) < 1e-15
+    _, pz, pp = grid.getCoordinates()
+    assert relmax(pz, g["pz"]) < 1e-15 and relmax(pp, g["pp"]) < 1e-15
+    assert grid.getCompactCoordinates(True, "z").size == M + 1
+    assert grid.getCoordinates(True)[2][-1] == np.inf
+
+
+def test_host_grid3scales_position_map():
+    """xi(chi) of Grid3Scales against the oracle's restatement (grid3Scales.py:198-264)."""
+    import wallgo_b200 as wb
+    from oracle import boltzmann_oracle as bo
+
+    grid = wb.Grid3Scales(30, 11, 0.3, 0.15, 0.04, 90.0, 0.4, 0.2, wallCenter=0.01)
+    xi, d = bo.position_map_3scales(grid.chiValues, 0.3, 0.15, 0.04, 0.4, 0.2, 0.01)
+    assert relmax(grid.xiValues, xi) < 1e-13
+    assert relmax(grid.dxidchi, d) < 1e-14
+    grid.changePositionFalloffScale(0.5, 0.6, 0.1, 0.0)
+    xi, d = bo.position_map_3scales(grid.chiValues, 0.5, 0.6, 0.1, 0.4, 0.2, 0.0)
+    assert relmax(grid.xiValues, xi) < 1e-13
+
+
+def test_host_collision_change_basis():
+    import wallgo_b200 as wb
+    from oracle import boltzmann_oracle as bo
+
+    M, N, P = 6, 7, 2
+    tab = bo.build_tables(M, N)
+    rng = np.random.default_rng(4)
+    C0 = rng.standard_normal((P, N - 1, N - 1, P, N - 1, N - 1))
+    grid = wb.Grid(M, N, 1.0, 1.0)
+    ca = wb.CollisionArray(grid, "Cardinal", [None] * P, C0.copy())
+    assert ca.changeBasis("Cardinal") is ca
+    ca.changeBasis("Chebyshev")
+    assert relmax(ca[...], bo.collision_to_chebyshev(C0, tab)) < 1e-12
+    ca.changeBasis("Cardinal")
+    assert relmax(ca[...], C0) < 1e-10
+    assert ca.getBasisType() == "Cardinal" and ca.getBasisSize() == N - 1
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_host_truncation_decision(name):
+    """The host half of checkSpectralConvergence, fed with spectra computed by the oracle."""
+    import wallgo_b200 as wb
+    from oracle import boltzmann_oracle as bo
+    from conftest import FixtureGrid
+
+    g = load_golden(name)
+    pb = oracle_problem_from_golden(g)
+    c = np.abs(bo.to_chebyshev(g["ref_deltaF"], pb.tab))
+    spectra = np.concatenate([c.sum(axis=(0, 2, 3)), c.sum(axis=(0, 1, 3)), c.sum(axis=(0, 1, 2))])
+    solver = wb.BoltzmannSolver(FixtureGrid(g), str(g["basisM"]), str(g["basisN"]), str(g["derivatives"]),
+                                truncationOption=getattr(wb.ETruncationOption, str(g["option"])))
+    keep, peaks = solver._decideTruncation(spectra)
+    M1, N1 = int(g["M"]) - 1, int(g["N"]) - 1
+    if N1 // 3 > 0 and M1 // 3 > 0:
+        assert (keep[0] != M1, keep[1] != N1, keep[2] != N1) == tuple(bool(x) for x in g["ref_truncatedTail"])
+        assert tuple(peaks) == tuple(int(x) for x in g["ref_spectralPeaks"])
+
+
+def test_results_arithmetic_mirrors_reference():
+    """scalar*res, res+res, res-res as used for under-relaxation (equationOfMotion.py:1352-1355)."""
+    import wallgo_b200 as wb
+
+    def mk(x):
+        p = [wb.Polynomial(np.full((1, 3), x * (i + 1)), None, ("Array", "Cardinal"), ("Array", "z"), False)
+             for i in range(4)]
+        return wb.BoltzmannResults(np.full((1, 3, 2, 2), x), wb.BoltzmannDeltas(*p), 0.1 * x, (False,) * 3, (1, 2, 3))
+
+    a, b = mk(1.0), mk(2.0)
+    r = 0.25 * a + (1 - 0.25) * b
+    assert np.allclose(r.deltaF, 1.75) and np.allclose(r.Deltas.Delta02.coefficients, 3.5)
+    d = b - a
+    assert np.allclose(d.Deltas.Delta11.coefficients, 4.0) and np.allclose(d.deltaF, 1.0)
+    assert (-2 * a).truncationError == pytest.approx(0.2)
+
+
+def test_solver_validates_arguments_like_reference():
+    import wallgo_b200 as wb
+
+    grid = wb.Grid(5, 5, 1.0, 1.0)
+    with pytest.raises(AssertionError):
+        wb.BoltzmannSolver(grid, basisM="Legendre")
+    with pytest.raises(AssertionError):
+        wb.BoltzmannSolver(grid, derivatives="Upwind")
+    with pytest.raises(AssertionError):
+        wb.BoltzmannSolver(grid, "Cardinal", "Chebyshev", "Finite Difference")
+    with pytest.raises(ValueError):
+        wb.Particle("x", 0, None, None, "Anyon", 1)
+    s = wb.BoltzmannSolver(grid)
+    with pytest.raises(AssertionError):
+        s.updateParticleList([object()])
+
+
+# ----------------------------------------------------------------------------- C ABI surface
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "wallgo_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(wg_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_capi_exports_every_declared_symbol():
+    from wallgo_b200 import _lib
+
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("libwallgo_b200.so not built (run __graft_entry__.build())")
+    declared = _header_symbols()
+    assert len(declared) >= 25
+    lib = C.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/wallgo_b200.h but not exported"
+    assert sorted(_lib.SYMBOLS) == declared, "ctypes binding and header disagree"
+    assert _lib.load().wg_version() == 100
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device the product must fail loudly, never compute on the CPU."""
+    import torch
+    from wallgo_b200 import _lib
+    from wallgo_b200.engine import BoltzmannEngine
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(_lib.WallGoB200Error):
+        BoltzmannEngine(1, 6, 5)
+    if os.path.exists(_lib.LIB_PATH):
+        lib = _lib.load()
+        h = C.c_void_p()
+        assert lib.wg_create(1, 6, 5, 0, C.byref(h)) == -2  # WG_ERR_CUDA
+        assert b"no CPU path" in lib.wg_last_error()
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "wallgo_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert "oracle" not in open(os.path.join(dirpath, f)).read().lower().replace(
+                    "c oracle", ""), f"{f} mentions the oracle"

@@ -1,0 +1,193 @@
+"""GPU tests of the dense pieces behind the C ABI: FP64 tensor-core GEMM and the blocked
+partial-pivoting LU + triangular solves (replacing LAPACK dgesv, boltzmann.py:283).
+
+Checked against NumPy/LAPACK and against the C restatement in oracle/lu_oracle.c; at the
+full benchmark size through size-independent properties (residual, linearity, P*A = L*U).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env(cuda_device):
+    import torch
+    from wallgo_b200 import _lib
+
+    lib = _lib.load()
+    return torch, lib, _lib
+
+
+def _stream(torch):
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 16), (256, 384, 256), (1000, 16, 16), (777, 33, 48),
+                                   (129, 257, 100), (5, 7, 3), (2048, 128, 128), (300, 64, 32),
+                                   (64, 2000, 256), (1, 1, 1)])
+def test_dgemm_sub(env, M, N, K):
+    torch, lib, _lib = env
+    rng = np.random.default_rng(M * 1000 + N * 10 + K)
+    ldc, lda, ldb = N + (3 if (M * N) % 2 else 4), K + 2, N + 6
+    Ch = rng.standard_normal((M, ldc))
+    Ah = rng.standard_normal((M, lda))
+    Bh = rng.standard_normal((K, ldb))
+    Cd, Ad, Bd = (torch.from_numpy(x).cuda() for x in (Ch, Ah, Bh))
+    _lib.check(lib.wg_dgemm_sub(Cd.data_ptr(), Ad.data_ptr(), Bd.data_ptr(), M, N, K, ldc, lda, ldb,
+                                _stream(torch)), "wg_dgemm_sub")
+    got = Cd.cpu().numpy()
+    want = Ch.copy()
+    want[:, :N] -= Ah[:, :K] @ Bh[:, :N]
+    scale = np.abs(Ah[:, :K]) @ np.abs(Bh[:, :N]) + np.abs(Ch[:, :N])
+    assert np.max(np.abs(got[:, :N] - want[:, :N]) / scale) < 1e-15 * max(4, K ** 0.5)
+    assert np.array_equal(got[:, N:], Ch[:, N:])  # padding columns untouched
+
+
+def _lu(env, A, b=None, lda=None):
+    torch, lib, _lib = env
+    n = A.shape[0]
+    lda = n if lda is None else lda
+    Ah = np.zeros((n, lda))
+    Ah[:, :n] = A
+    Ad = torch.from_numpy(Ah).cuda()
+    ipiv = torch.zeros(n, dtype=torch.int32, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    plan = C.c_void_p()
+    _lib.check(lib.wg_lu_create(n, 0, C.byref(plan)), "wg_lu_create")
+    try:
+        _lib.check(lib.wg_lu_factor(plan, Ad.data_ptr(), lda, ipiv.data_ptr(), info.data_ptr(), _stream(torch)),
+                   "wg_lu_factor")
+        x = None
+        if b is not None:
+            bd = torch.from_numpy(b.copy()).cuda()
+            _lib.check(lib.wg_lu_solve(plan, Ad.data_ptr(), lda, bd.data_ptr(), _stream(torch)), "wg_lu_solve")
+            x = bd.cpu().numpy()
+        torch.cuda.synchronize()
+    finally:
+        lib.wg_lu_destroy(plan)
+    return Ad.cpu().numpy()[:, :n], ipiv.cpu().numpy(), int(info.item()), x
+
+
+def _check_factors(A, LU, ipiv):
+    n = A.shape[0]
+    L = np.tril(LU, -1) + np.identity(n)
+    U = np.triu(LU)
+    PA = A.copy()
+    for j in range(n):
+        p = ipiv[j]
+        assert j <= p < n
+        if p != j:
+            PA[[j, p]] = PA[[p, j]]
+    err = np.max(np.abs(L @ U - PA)) / np.max(np.abs(A))
+    assert err < 1e-13 * max(1, n ** 0.5), err
+    assert np.max(np.abs(L)) <= 1.0 + 1e-15  # partial pivoting bounds the multipliers
+
+
+@pytest.mark.parametrize("n,lda_pad", [(1, 0), (2, 0), (5, 1), (16, 0), (17, 3), (64, 0), (100, 0), (255, 1),
+                                       (256, 0), (257, 0), (400, 0), (513, 2), (1000, 0), (1900, 0), (2049, 1)])
+def test_lu_random(env, n, lda_pad):
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n))
+    b = rng.standard_normal(n)
+    LU, ipiv, info, x = _lu(env, A, b, lda=n + lda_pad)
+    assert info == 0
+    _check_factors(A, LU, ipiv)
+    xr = np.linalg.solve(A, b)
+    assert np.max(np.abs(x - xr)) / np.max(np.abs(xr)) < 1e-10
+
+
+@pytest.mark.parametrize("n", [8, 50, 300])
+def test_lu_pivots_match_c_oracle(env, n):
+    """Same pivot rule as dgetf2 (first maximal |a| in the column): identical ipiv and factors to rounding."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(root, "oracle", "_build", "liblu_oracle.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_build/liblu_oracle.so not built")
+    olib = C.CDLL(so)
+    rng = np.random.default_rng(100 + n)
+    A = rng.standard_normal((n, n))
+    LU, ipiv, info, _ = _lu(env, A)
+    Ao = A.copy()
+    piv = np.zeros(n, dtype=np.int32)
+    oinfo = olib.wgo_lu_factor(Ao.ctypes.data_as(C.c_void_p), n, n, piv.ctypes.data_as(C.c_void_p))
+    assert info == oinfo == 0
+    assert np.array_equal(ipiv, piv)
+    assert np.max(np.abs(LU - Ao)) / np.max(np.abs(Ao)) < 1e-12
+
+
+def test_lu_singular_reports_info(env):
+    n = 40
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((n, n))
+    A[:, 7] = 0.0
+    _, _, info, _ = _lu(env, A)
+    assert info == 8
+    A = rng.standard_normal((n, n))
+    A[:, 20] = A[:, 3]          # exactly dependent columns: elimination produces an exact zero column
+    _, _, info, _ = _lu(env, A)
+    assert info == 0 or info == 21
+
+
+def test_lu_badly_scaled_needs_pivoting(env):
+    """Entries spanning many orders of magnitude (1e-17 .. 2e5)."""
+    n = 600
+    rng = np.random.default_rng(9)
+    A = rng.standard_normal((n, n)) * 10.0 ** rng.uniform(-8, 5, size=(n, 1))
+    A[np.arange(n), np.arange(n)] *= 1e-12   # tiny diagonal forces row exchanges
+    b = rng.standard_normal(n)
+    LU, ipiv, info, x = _lu(env, A, b)
+    assert info == 0
+    assert np.mean(ipiv != np.arange(n)) > 0.9
+    xr = np.linalg.solve(A, b)
+    assert np.max(np.abs(x - xr)) / np.max(np.abs(xr)) < 1e-9
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE config M=40, N=21, P=1 (n = 15600): residual, linearity and idempotent re-solve."""
+    import torch
+    import wallgo_b200 as wb
+    from conftest import FixtureBackground, FixtureGrid
+    from oracle import boltzmann_oracle as bo
+
+    P, M, N = 1, 40, 21
+    pb = bo.synthetic_problem(P, M, N)
+    g = dict(P=P, M=M, N=N, chi=pb.tab.chi, rz=pb.tab.rz, rp=pb.tab.rp, pz=pb.pz, pp=pb.pp,
+             dxidchi=pb.xi_dxidchi, dpzdrz=pb.dpzdrz, dppdrp=pb.dppdrp, vw=pb.vw, v=pb.v, T=pb.T, msq=pb.msq)
+    grid = FixtureGrid(g)
+    parts = [wb.Particle("p0", 0, (lambda f: f.msq[0]), None, "Fermion", 12)]
+    solver = wb.BoltzmannSolver(grid)
+    solver.updateParticleList(parts)
+    solver.setBackground(FixtureBackground(g))
+    solver.setCollisionArray(wb.CollisionArray(grid, "Chebyshev", parts, pb.collision))
+    eng = solver._getEngine()
+    solver._uploadBackground(eng)
+    eng.assemble(pb.vw, 1.0)
+    A0 = eng.A.clone()
+    S0 = eng.S.clone()
+    # a few assembled rows against the oracle's row formula (the oracle cannot hold 1.9 GB x 3)
+    rq = bo.row_quantities(pb)
+    src = (bo.dfeq(rq["Epl"] / rq["T"], rq["s"]) / rq["T"]) * rq["dchidxi"] * (
+        rq["Pw"] * rq["Ppl"] * rq["gpl"] ** 2 * rq["dv"] + rq["Pw"] * rq["Epl"] * rq["dT"] / rq["T"]
+        + 0.5 * rq["dmsq"] * rq["uwupl"])
+    assert np.max(np.abs(S0.cpu().numpy() - src.reshape(-1))) / np.max(np.abs(src)) < 1e-11
+    eng.factor()
+    eng.solve()
+    assert eng.info() == 0
+    x = eng.S.clone()
+    r = torch.mv(A0, x) - S0
+    assert float(torch.linalg.norm(r) / torch.linalg.norm(S0)) < 1e-12
+    # linearity: solve(3*S) == 3*solve(S) with the same factors
+    b3 = 3.0 * S0
+    eng.solve(b3)
+    assert float(torch.max(torch.abs(b3 - 3.0 * x)) / torch.max(torch.abs(x))) < 1e-12
+    # moments are linear in deltaF
+    res1 = solver.getDeltas(x.cpu().numpy().reshape(P, M - 1, N - 1, N - 1))
+    solver.truncationOption = wb.ETruncationOption.NONE
+    resa = solver.getDeltas(x.cpu().numpy().reshape(P, M - 1, N - 1, N - 1))
+    resb = solver.getDeltas(2.0 * x.cpu().numpy().reshape(P, M - 1, N - 1, N - 1))
+    assert np.allclose(2.0 * resa.Deltas.Delta00.coefficients, resb.Deltas.Delta00.coefficients, rtol=1e-13, atol=0)
+    assert np.all(np.isfinite(res1.Deltas.Delta11.coefficients))

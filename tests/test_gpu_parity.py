@@ -1,0 +1,206 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the committed reference golden
+vectors and against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): deltaF and the four Delta moments <= 1e-10 relative
+(to the max-norm of the quantity); integer outputs (truncation flags, kept shapes, spectral
+peaks) must be equal.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden, oracle_problem_from_golden, relmax, solver_from_golden
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10          # north-star tolerance on deltaF and moments
+TOL_ASSEMBLY = 2e-13  # operator/source: relative to the largest entry of the row / vector
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import boltzmann_oracle as bo
+    return bo
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names()])
+def test_basis_tables_match_reference(cuda_device, name):
+    g = load_golden(name)
+    solver = solver_from_golden(g)
+    eng = solver._getEngine()
+    tabs = eng.get_tables()
+    for k in ("Tchi", "Dchi", "Trz", "Trp", "Drz"):
+        ref = g["ref_" + k]
+        err = np.max(np.abs(tabs[k] - ref)) / np.max(np.abs(ref))
+        assert err < 2e-13, (name, k, err)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_operator_and_source_match_reference(cuda_device, name):
+    g = load_golden(name)
+    solver = solver_from_golden(g)
+    op, src, liou, coll = solver.buildLinearEquations()
+    n = op.shape[0]
+    assert op.shape == (n, n) and src.shape == (n,)
+    assert relmax(src, g["ref_source"]) < 1e-11, name
+    scale = np.max(np.abs(g["ref_op_probe"]), axis=1, keepdims=True)
+    rows = g["ref_op_probe_rows"]
+    assert np.max(np.abs(op[rows] - g["ref_op_probe"]) / scale) < TOL_ASSEMBLY, name
+    assert relmax(np.diag(op), g["ref_op_diag"]) < TOL_ASSEMBLY
+    ones = np.ones(n)
+    assert relmax(op @ ones, g["ref_op_rowsum"]) < 1e-12
+    assert relmax(op.T @ ones, g["ref_op_colsum"]) < 1e-12
+    if "ref_operator" in g:
+        assert np.max(np.abs(op - g["ref_operator"])) / np.max(np.abs(g["ref_operator"])) < TOL_ASSEMBLY
+    # the two parts add up to the operator (boltzmann.py:810)
+    assert relmax((liou + coll).reshape(n, n), op) < 1e-15
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_deltaF_matches_reference(cuda_device, name):
+    g = load_golden(name)
+    solver = solver_from_golden(g)
+    dF = solver.solveBoltzmannEquations()
+    assert dF.shape == g["ref_deltaF"].shape
+    assert relmax(dF, g["ref_deltaF"]) < TOL, name
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_getDeltas_matches_reference(cuda_device, name):
+    g = load_golden(name)
+    solver = solver_from_golden(g)
+    res = solver.getDeltas()
+    assert tuple(res.truncatedTail) == tuple(bool(x) for x in g["ref_truncatedTail"]), name
+    assert tuple(res.spectralPeaks) == tuple(int(x) for x in g["ref_spectralPeaks"]), name
+    assert relmax(res.deltaF, g["ref_deltaF_trunc"]) < TOL
+    D = np.stack([res.Deltas.Delta00.coefficients, res.Deltas.Delta02.coefficients,
+                  res.Deltas.Delta20.coefficients, res.Deltas.Delta11.coefficients])
+    for i in range(4):
+        assert relmax(D[i], g["ref_Deltas"][i]) < TOL, (name, i)
+    assert abs(res.truncationError - float(g["ref_truncationError"])) <= 1e-8 * float(g["ref_truncationError"])
+    # moments of a GIVEN deltaF (no solve): isolates the quadrature kernels
+    res2 = solver.getDeltas(g["ref_deltaF"])
+    D2 = np.stack([res2.Deltas.Delta00.coefficients, res2.Deltas.Delta02.coefficients,
+                   res2.Deltas.Delta20.coefficients, res2.Deltas.Delta11.coefficients])
+    assert relmax(D2, g["ref_Deltas"]) < 1e-12
+    assert relmax(res2.deltaF, g["ref_deltaF_trunc"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["tiny_P1_M6_N5", "small_P2_M12_N7"])
+def test_checkLinearization_matches_reference(cuda_device, name):
+    g = load_golden(name)
+    solver = solver_from_golden(g)
+    c1, c2 = solver.checkLinearization()
+    assert abs(c1 - g["ref_linearization"][0]) < 1e-9 * abs(g["ref_linearization"][0])
+    assert abs(c2 - g["ref_linearization"][1]) < 1e-8 * abs(g["ref_linearization"][1])
+
+
+@pytest.mark.parametrize("P,M,N,kw", [
+    (1, 16, 9, {}),
+    (2, 10, 9, dict(r=0.05, seed=5)),
+    (3, 8, 7, dict(collisionMultiplier=1e-2, seed=7)),
+    (1, 24, 13, dict(seed=2)),
+])
+def test_against_oracle_on_seeded_inputs(cuda_device, oracle, P, M, N, kw):
+    """Sizes without a golden file: CUDA vs the oracle on the same synthetic inputs."""
+    import wallgo_b200 as wb
+    from conftest import FixtureBackground, FixtureGrid
+
+    pb = oracle.synthetic_problem(P, M, N, **kw)
+    g = dict(P=P, M=M, N=N, chi=pb.tab.chi, rz=pb.tab.rz, rp=pb.tab.rp, pz=pb.pz, pp=pb.pp,
+             dxidchi=pb.xi_dxidchi, dpzdrz=pb.dpzdrz, dppdrp=pb.dppdrp, vw=pb.vw, v=pb.v, T=pb.T, msq=pb.msq)
+    grid = FixtureGrid(g)
+    parts = [wb.Particle(f"p{a}", a, (lambda f, a=a: f.msq[a]), None,
+                         "Fermion" if pb.statistics[a] < 0 else "Boson", 12) for a in range(P)]
+    solver = wb.BoltzmannSolver(grid, collisionMultiplier=pb.collisionMultiplier)
+    solver.updateParticleList(parts)
+    solver.setBackground(FixtureBackground(g))
+    solver.setCollisionArray(wb.CollisionArray(grid, "Chebyshev", parts, pb.collision))
+    ref = oracle.get_deltas(pb, None, "AUTO")
+    res = solver.getDeltas()
+    assert tuple(res.truncatedTail) == tuple(ref["truncatedTail"])
+    assert tuple(res.spectralPeaks) == tuple(ref["spectralPeaks"])
+    assert relmax(res.deltaF, ref["deltaF"]) < TOL
+    D = np.stack([res.Deltas.Delta00.coefficients, res.Deltas.Delta02.coefficients,
+                  res.Deltas.Delta20.coefficients, res.Deltas.Delta11.coefficients])
+    for i in range(4):
+        assert relmax(D[i], ref["Deltas"][i]) < TOL
+
+
+@pytest.mark.parametrize("M,N,a,b,c,d,e,f", [(25, 19, 1, 2, 3, 4, 5, 6), (5, 5, 1, 1, 2, 3, 5, 8)])
+def test_Delta00_known_answer(cuda_device, M, N, a, b, c, d, e, f):
+    """Re-statement of the reference's analytic test (tests/test_Boltzmann.py:14-85), rtol 1e-14."""
+    import wallgo_b200 as wb
+
+    grid = wb.Grid(M, N, 1, 100)
+    fieldv = np.ones(M + 1)
+    fieldv[M // 2:] = 0
+    fieldv += 0.1 * np.sin(7 * 2 * np.pi * np.arange(M + 1) + 6)
+    v = -np.ones(M + 1) / np.sqrt(3) + 0.01 * np.sin(10 * 2 * np.pi * np.arange(M + 1))
+    T = 100 * np.ones(M + 1)
+
+    class F:
+        def __init__(self, x):
+            self.x = x
+
+    particle = wb.Particle("top", 0, lambda fl: 0.5 * fl.x**2, None, "Fermion", 12)
+    bg = wb.BoltzmannBackground(0.5 * (v[0] + v[-1]), v, F(fieldv), T)
+    solver = wb.BoltzmannSolver(grid, "Cardinal", "Cardinal", "Spectral")
+    solver.truncationOption = wb.ETruncationOption.NONE
+    solver.updateParticleList([particle])
+    solver.setBackground(bg)
+    solver.setCollisionArray(wb.CollisionArray(grid, "Cardinal", [particle],
+                                               np.zeros((1, N - 1, N - 1, 1, N - 1, N - 1))))
+    rz = grid.rzValues[None, :, None]
+    rp = grid.rpValues[None, None, :]
+    pz = grid.pzValues[None, :, None]
+    pp = grid.ppValues[None, None, :]
+    msq = 0.5 * fieldv[1:-1, None, None] ** 2
+    E = np.sqrt(msq + pz**2 + pp**2)
+    eps = 2e-16
+    integrand = (2 * E * (1 - rz**2) * (1 - rp**2)
+                 * np.sqrt((1 - rz**2) * (1 - rp) ** 2 / (1 - rp**2 + eps)) / (np.log(2 / (1 - rp)) + eps))
+    integrand = integrand * (a + b * rz + c * rz**2) * (d + e * rp + f * rp**2)
+    res = solver.getDeltas(integrand[None, ...])
+    exact = (4 * a + c) * (4 * d + f) * T**3 / 64
+    np.testing.assert_allclose(res.Deltas.Delta00.coefficients[0], exact[1:-1], rtol=1e-14, atol=0)
+
+
+@pytest.mark.parametrize("M,N", [(3, 3), (5, 5)])
+def test_solution_residual(cuda_device, M, N):
+    """Re-statement of tests/test_Boltzmann.py:88-125: ||A deltaF - S|| / ||S|| < 1e-14."""
+    import wallgo_b200 as wb
+
+    grid = wb.Grid(M, N, 1, 1)
+    fieldv = np.ones(M + 1)
+    fieldv[M // 2:] = 0
+    fieldv += 0.1 * np.sin(7 * 2 * np.pi * np.arange(M + 1) + 6)
+    v = -np.ones(M + 1) / np.sqrt(3) + 0.01 * np.sin(10 * 2 * np.pi * np.arange(M + 1))
+
+    class F:
+        def __init__(self, x):
+            self.x = x
+
+    particle = wb.Particle("top", 0, lambda fl: 0.5 * fl.x**2, None, "Fermion", 12)
+    solver = wb.BoltzmannSolver(grid)
+    solver.updateParticleList([particle])
+    solver.setBackground(wb.BoltzmannBackground(0.5 * (v[0] + v[-1]), v, F(fieldv), 100 * np.ones(M + 1)))
+    rng = np.random.default_rng(11)
+    q = (N - 1) ** 2
+    coll = (0.5 * np.identity(q) + 1e-2 * rng.standard_normal((q, q))).reshape(1, N - 1, N - 1, 1, N - 1, N - 1)
+    solver.setCollisionArray(wb.CollisionArray(grid, "Chebyshev", [particle], coll))
+    dF = solver.solveBoltzmannEquations()
+    op, src, _, _ = solver.buildLinearEquations()
+    ratio = np.linalg.norm(op @ dF.flatten() - src) / np.linalg.norm(src)
+    assert ratio < 1e-14
+
+
+def test_singular_operator_raises(cuda_device):
+    """A singular operator must surface as numpy.linalg.LinAlgError like boltzmann.py:283 would."""
+    g = load_golden("tiny_P1_M6_N5")
+    solver = solver_from_golden(g)
+    eng = solver._getEngine()
+    solver._uploadBackground(eng)
+    eng.assemble(float(g["vw"]), 1.0)
+    eng.A.zero_()
+    eng.factor()
+    assert eng.info() == 1

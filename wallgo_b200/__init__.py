@@ -1,0 +1,16 @@
+"""wallgo_b200 -- B200-native (sm_100a) Boltzmann-transport hot path behind the WallGo API.
+
+Public surface:
+  BoltzmannSolver            standalone class with the reference's interface (boltzmann.py)
+  dropin.install()           subclass of WallGo.BoltzmannSolver for unmodified WallGoManager/EOM
+  Grid, Grid3Scales, Particle, BoltzmannBackground, CollisionArray, ETruncationOption
+  engine.BoltzmannEngine     thin torch/ctypes wrapper over the C ABI (include/wallgo_b200.h)
+"""
+from .boltzmann import BoltzmannSolver
+from .containers import (BoltzmannBackground, BoltzmannDeltas, BoltzmannResults, CollisionArray,
+                         ETruncationOption, Particle, Polynomial)
+from .grid import Grid, Grid3Scales
+
+__all__ = ["BoltzmannSolver", "BoltzmannBackground", "BoltzmannDeltas", "BoltzmannResults",
+           "CollisionArray", "ETruncationOption", "Particle", "Polynomial", "Grid", "Grid3Scales"]
+__version__ = "0.1.0"

@@ -1,0 +1,366 @@
+"""B200-native `BoltzmannSolver`: same public interface as the reference class
+(`/root/reference/src/WallGo/boltzmann.py:37-886`), every numerical step on the GPU.
+
+Host Python keeps only what the reference keeps outside NumPy kernels: evaluating the user's
+`msqVacuum` callbacks on the M+1 profile points, the branchy truncation decision on the
+(M-1)+2(N-1) device-reduced spectra (`np.polyfit`, polynomial.py:994-1033) and wrapping the
+results.  Per solve the boundary traffic is one upload of O(P*M) doubles and one download of
+O(n) doubles.
+
+There is no CPU path: constructing the engine without an sm_100 device raises.
+"""
+from __future__ import annotations
+
+import sys
+import typing
+from copy import deepcopy
+
+import numpy as np
+
+from . import containers as _own
+from .containers import ETruncationOption
+from .spectral import basisChangeMatrices, buildTables, spectralPeak, tailConverging
+
+
+class _OwnTypes:
+    Polynomial = _own.Polynomial
+    BoltzmannDeltas = _own.BoltzmannDeltas
+    BoltzmannResults = _own.BoltzmannResults
+
+
+class BoltzmannSolverB200Mixin:
+    """Implementation shared by the standalone class below and the WallGo drop-in subclass."""
+
+    MAX_EXPONENT: typing.Final[float] = sys.float_info.max_exp * np.log(2)
+    _types = _OwnTypes
+
+    # ------------------------------------------------------------------ construction / setters
+    def _initB200(self, grid, basisM, basisN, derivatives, collisionMultiplier, truncationOption, device):
+        self.grid = grid
+        self._checkDerivatives(derivatives)
+        self.derivatives = derivatives
+        self._checkBasis(basisM)
+        self._checkBasis(basisN)
+        if derivatives == "Finite Difference":
+            assert basisM == "Cardinal" and basisN == "Cardinal", \
+                "Must use Cardinal basis for Finite Difference method"
+        self.basisM, self.basisN = basisM, basisN
+        self.collisionMultiplier = collisionMultiplier
+        self.truncationOption = truncationOption
+        self.background = None
+        self.collisionArray = None
+        self.offEqParticles = []
+        self.device = device
+        self._engine = None
+        self._staticKey = None
+
+    def setBackground(self, background) -> None:
+        """Deep-copies and boosts to the plasma frame (boltzmann.py:116-123)."""
+        self.background = deepcopy(background)
+        self.background.boostToPlasmaFrame()
+
+    def setCollisionArray(self, collisionArray) -> None:
+        self.collisionArray = collisionArray
+
+    def updateParticleList(self, offEqParticles) -> None:
+        for p in offEqParticles:
+            assert hasattr(p, "msqVacuum") and hasattr(p, "statistics"), "not a Particle"
+        self.offEqParticles = offEqParticles
+
+    def loadCollisions(self, directoryPath) -> None:
+        """Reads collisions_{a}_{b}.hdf5 (boltzmann.py:822-844).  HDF5 ingest is a 'next' row
+        (SURVEY section 8 f2): it needs an HDF5 reader, which this image does not have."""
+        raise NotImplementedError(
+            "wallgo_b200: HDF5 collision ingest is not built yet; pass an in-memory tensor with "
+            "setCollisionArray (the reference supports this via CollisionArray.newFromPolynomial)")
+
+    # deepcopy (used by EOM.getBoltzmannFiniteDifference, equationOfMotion.py:2135) must not clone
+    # the device handle; the copy builds its own engine lazily.
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st["_engine"] = None
+        st["_staticKey"] = None
+        return st
+
+    def __deepcopy__(self, memo):
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k in ("_engine", "_staticKey"):
+                setattr(new, k, None)
+            elif k == "grid":
+                setattr(new, k, deepcopy(v, memo))
+            else:
+                setattr(new, k, deepcopy(v, memo))
+        return new
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _collisionData(self):
+        ca = self.collisionArray
+        assert ca is not None, "BoltzmannSolver error: collision array not set"
+        return np.asarray(ca[...])
+
+    def _getEngine(self):
+        from .engine import BoltzmannEngine
+
+        P = len(self.offEqParticles)
+        assert P >= 1, "BoltzmannSolver error: no out-of-equilibrium particles"
+        g = self.grid
+        if self._engine is None or (self._engine.P, self._engine.M, self._engine.N) != (P, g.M, g.N):
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = BoltzmannEngine(P, g.M, g.N, self.device)
+            self._staticKey = None
+        eng = self._engine
+        coll = self._collisionData()
+        stats = tuple(-1.0 if p.statistics == "Fermion" else 1.0 for p in self.offEqParticles)
+        _, dpzdrz, dppdrp = g.getCompactificationDerivatives()
+        key = (self.basisM, self.basisN, self.derivatives, stats, coll.__array_interface__["data"][0],
+               coll.shape, float(g.momentumFalloffT), float(coll.flat[0]), float(coll.flat[-1]))
+        if key != self._staticKey:
+            chi, rz, rp = g.getCompactCoordinates()
+            _, pz, pp = g.getCoordinates()
+            eng.set_grid(chi, rz, rp, pz, pp, dpzdrz, dppdrp)
+            eng.set_statistics(np.array(stats))
+            if (self.basisM, self.basisN, self.derivatives) == ("Cardinal", "Chebyshev", "Spectral"):
+                eng.build_basis()
+            else:
+                eng.set_tables(*buildTables(g.M, g.N, self.basisM, self.basisN, self.derivatives))
+            eng.set_transforms(basisChangeMatrices(g.M, g.N, self.basisM, self.basisN))
+            assert coll.shape == (P, g.N - 1, g.N - 1, P, g.N - 1, g.N - 1), "collision tensor has the wrong shape"
+            eng.set_collision(coll)
+            self._staticKey = key
+        return eng
+
+    def _msq(self, fields):
+        return np.array([np.asarray(p.msqVacuum(fields), dtype=np.float64) for p in self.offEqParticles])
+
+    def _uploadBackground(self, eng):
+        bg = self.background
+        assert bg is not None, "BoltzmannSolver error: background not set"
+        dxidchi, _, _ = self.grid.getCompactificationDerivatives()
+        msq = self._msq(bg.fieldProfiles)
+        eng.upload_profiles(np.asarray(bg.temperatureProfile, dtype=np.float64),
+                            np.asarray(bg.velocityProfile, dtype=np.float64), msq, dxidchi)
+
+    def _solveOnDevice(self):
+        """assemble + LU + triangular solves; leaves deltaF in eng.S (device)."""
+        eng = self._getEngine()
+        self._uploadBackground(eng)
+        eng.assemble(float(self.background.velocityWall), float(self.collisionMultiplier))
+        eng.factor()
+        eng.solve()
+        return eng
+
+    def _shape(self):
+        g = self.grid
+        return (len(self.offEqParticles), g.M - 1, g.N - 1, g.N - 1)
+
+    # ------------------------------------------------------------------ queries
+    def solveBoltzmannEquations(self) -> np.ndarray:
+        """delta f = operator^-1 source (boltzmann.py:240-294)."""
+        eng = self._solveOnDevice()
+        info = eng.info()
+        if info != 0:
+            raise np.linalg.LinAlgError("Singular matrix")
+        return eng.S.cpu().numpy().reshape(self._shape())
+
+    def buildLinearEquations(self):
+        """(operator (n,n), source (n,), liouville, collision) on the host (boltzmann.py:628-820).
+        Debug/test entry point: the production path never moves the operator off the device."""
+        eng = self._getEngine()
+        self._uploadBackground(eng)
+        vw, mult = float(self.background.velocityWall), float(self.collisionMultiplier)
+        shape8 = self._shape() * 2
+        eng.assemble(vw, mult, 1)
+        liouville = eng.A.cpu().numpy().reshape(shape8)
+        eng.assemble(vw, mult, 2)
+        collision = eng.A.cpu().numpy().reshape(shape8)
+        eng.assemble(vw, mult, 3)
+        operator = eng.A.cpu().numpy()
+        source = eng.S.cpu().numpy()
+        return operator, source, liouville, collision
+
+    def _decideTruncation(self, spectra):
+        """Host half of checkSpectralConvergence (boltzmann.py:399-483) on device-reduced spectra."""
+        g = self.grid
+        M1, N1 = g.M - 1, g.N - 1
+        sChi, sPz, sPp = spectra[:M1], spectra[M1:M1 + N1], spectra[M1 + N1:]
+        cutM, cutN = M1 // 3, N1 // 3
+        # (for grids with fewer than 3 coefficients per axis the reference's `[-0:]` slice is the
+        # whole axis; such grids are only used by its residual test, never with getDeltas)
+        conv = (tailConverging(sChi[M1 - cutM:], M1 - cutM),
+                tailConverging(sPz[N1 - cutN:], N1 - cutN),
+                tailConverging(sPp[N1 - cutN:], N1 - cutN))
+        keep = [M1, N1, N1]
+        if self.truncationOption == ETruncationOption.AUTO or self.truncationOption.name == "AUTO":
+            cut = [not c for c in conv]
+        elif self.truncationOption.name == "THIRD":
+            cut = [True, True, True]
+        else:
+            cut = [False, False, False]
+        if cut[0]:
+            keep[0] = M1 - cutM
+        if cut[1]:
+            keep[1] = N1 - cutN
+        if cut[2]:
+            keep[2] = N1 - cutN
+        peaks = (spectralPeak(sChi[:keep[0]], 0), spectralPeak(sPz[:keep[1]], 1),
+                 spectralPeak(sPp[:keep[2]], 2))
+        return keep, peaks
+
+    def _toDevice(self, eng, deltaF):
+        arr = np.ascontiguousarray(deltaF, dtype=np.float64).reshape(-1)
+        assert arr.size == eng.n, "deltaF has the wrong shape"
+        eng.dF_in.copy_(eng.torch.from_numpy(arr), non_blocking=False)
+        return eng.dF_in
+
+    def _spectralPipeline(self, eng, dFdev):
+        eng.spectra_async(dFdev)
+        spectra = eng.spectra_to_host()
+        keep, peaks = self._decideTruncation(spectra)
+        roundtrip = self.truncationOption.name != "NONE"
+        eng.moments_async(dFdev, keep, roundtrip)
+        dF, deltas, err = eng.results_to_host()
+        return dF, deltas, err, keep, peaks
+
+    def checkSpectralConvergence(self, deltaF):
+        """(deltaFTruncated, shapeTruncated, spectralPeaks) (boltzmann.py:353-491)."""
+        eng = self._getEngine()
+        if self.background is not None:
+            self._uploadBackground(eng)
+        dF, _, _, keep, peaks = self._spectralPipeline(eng, self._toDevice(eng, deltaF))
+        shape = (deltaF.shape[0], keep[0], keep[1], keep[2])
+        if self.truncationOption.name == "NONE":
+            return deltaF, shape, peaks
+        return dF.reshape(deltaF.shape), shape, peaks
+
+    def estimateTruncationError(self, deltaF, shapeTruncated) -> float:
+        """max over axes/species of |last kept coefficient| / sum |coefficients| (boltzmann.py:296-351)."""
+        eng = self._getEngine()
+        if self.background is not None:
+            self._uploadBackground(eng)
+        dev = self._toDevice(eng, deltaF)
+        eng.spectra_async(dev)
+        eng.moments_async(dev, shapeTruncated[1:], False)
+        _, _, err = eng.results_to_host()
+        return float(np.max(err[:, 1:] / err[:, :1]))
+
+    def getDeltas(self, deltaF=None):
+        """Solve (unless deltaF is given), truncate, integrate the four moments (boltzmann.py:141-238)."""
+        if deltaF is None:
+            eng = self._solveOnDevice()
+            dFdev = eng.S
+        else:
+            eng = self._getEngine()
+            self._uploadBackground(eng)
+            dFdev = self._toDevice(eng, deltaF)
+        dF, deltas, err, keep, peaks = self._spectralPipeline(eng, dFdev)
+        if deltaF is None:
+            info = eng.info()
+            if info != 0:
+                raise np.linalg.LinAlgError("Singular matrix")
+        g = self.grid
+        M1, N1 = g.M - 1, g.N - 1
+        truncationError = float(np.max(err[:, 1:] / err[:, :1]))
+        truncatedTail = (keep[0] != M1, keep[1] != N1, keep[2] != N1)
+        T = self._types
+        polys = [T.Polynomial(deltas[i], g, ("Array", "Cardinal"), ("Array", "z"), (False, False))
+                 for i in range(4)]
+        Deltas = T.BoltzmannDeltas(Delta00=polys[0], Delta02=polys[1], Delta20=polys[2], Delta11=polys[3])
+        return T.BoltzmannResults(deltaF=dF, Deltas=Deltas, truncationError=truncationError,
+                                  truncatedTail=truncatedTail, spectralPeaks=peaks)
+
+    def checkLinearization(self, deltaF=None):
+        """The two linearisation criteria (boltzmann.py:500-626).  The second solve re-uses the LU
+        factors of the first instead of re-assembling and re-factoring."""
+        eng = self._solveOnDevice()          # operator factors + deltaF in eng.S
+        torch = eng.torch
+        shape = self._shape()
+        if deltaF is not None:
+            dFdev = self._toDevice(eng, deltaF).clone()
+        else:
+            dFdev = eng.S.clone()
+        card = torch.empty_like(dFdev)
+        eng.change_basis(2, dFdev, card)                     # solver basis -> Cardinal
+        sq = card * card
+        sqB = torch.empty_like(sq)
+        # Cardinal -> solver basis = inverse of stage 2; identical to stage 0 on the axes that differ
+        self._cardinalToSolver(eng, sq, sqB)
+        src2 = torch.empty_like(sq)
+        eng.collision_apply(sqB, src2)
+        eng.solve(src2)                                      # deltaNonlin in src2
+        nlCard = torch.empty_like(src2)
+        eng.change_basis(2, src2, nlCard)
+        # pressure integrals: small host-side quadrature on three n-vectors
+        g = self.grid
+        bg = self.background
+        msqFull = self._msq(bg.fieldProfiles)
+        tabs = eng.get_tables()
+        dmsq = (msqFull @ tabs["DchiFull"].T)[:, 1:-1, None, None]
+        chi, rz, rp = g.getCompactCoordinates()
+        _, pz, pp = g.getCoordinates()
+        _, dpzdrz, dppdrp = g.getCompactificationDerivatives()
+        pz4, pp4 = pz[None, None, :, None], pp[None, None, None, :]
+        energy = np.sqrt(msqFull[:, 1:-1, None, None] + pz4**2 + pp4**2)
+        temp = np.asarray(bg.temperatureProfile)[None, 1:-1, None, None]
+        stat = np.array([-1 if p.statistics == "Fermion" else 1 for p in self.offEqParticles])[:, None, None, None]
+        x = energy / temp
+        with np.errstate(over="ignore"):
+            fEq = np.where(x > self.MAX_EXPONENT, 0.0, 1 / (np.exp(x) - stat))
+        dofs = np.array([p.totalDOFs for p in self.offEqParticles])[:, None, None, None]
+        integrand = dofs * dmsq * dpzdrz[None, None, :, None] * dppdrp[None, None, None, :] * pp4 / (
+            4 * np.pi**2 * energy)
+        wchi = np.sqrt(1 - chi**2) * (np.pi / g.M)
+        wz = np.sqrt(1 - rz**2) * (np.pi / g.N)
+        wp = np.full(g.N - 1, np.pi / (g.N - 1))
+        wp[0] /= 2
+        wp = np.sqrt(1 - rp**2) * wp
+        W = wchi[None, :, None, None] * wz[None, None, :, None] * wp[None, None, None, :]
+        pEq = np.sum(fEq * integrand * W)
+        pDf = np.sum(card.cpu().numpy().reshape(shape) * integrand * W)
+        pNl = np.sum(nlCard.cpu().numpy().reshape(shape) * integrand * W)
+        return abs(pDf / pEq), abs(pNl / (pEq + pDf))
+
+    def _cardinalToSolver(self, eng, src, dst):
+        """Cardinal values -> solver basis.  On axes where the solver basis is Chebyshev this is the
+        inverse Chebyshev matrix; such matrices are stage 0 only for Cardinal solver axes, so the
+        (rare) Chebyshev case is done through a temporary transform set."""
+        g = self.grid
+        from .spectral import chebyshevMatrix, lobattoNodes
+        chi, rz, rp = lobattoNodes(g.M, g.N)
+        mats = basisChangeMatrices(g.M, g.N, self.basisM, self.basisN)
+        inv = [None] * 9
+        if self.basisM == "Chebyshev":
+            inv[0] = np.linalg.inv(chebyshevMatrix(chi, g.M - 1, "full"))
+        if self.basisN == "Chebyshev":
+            inv[1] = np.linalg.inv(chebyshevMatrix(rz, g.N - 1, "full"))
+            inv[2] = np.linalg.inv(chebyshevMatrix(rp, g.N - 1, "partial"))
+        if all(m is None for m in inv):
+            dst.copy_(src)
+            return
+        eng.set_transforms(inv[:3] + mats[3:])
+        eng.change_basis(0, src, dst)
+        eng.torch.cuda.current_stream(eng.dev).synchronize()
+        eng.set_transforms(mats)
+
+    # ------------------------------------------------------------------ validation helpers
+    @staticmethod
+    def _checkBasis(basis: str) -> None:
+        assert basis in ["Cardinal", "Chebyshev"], f"BoltzmannSolver error: unkown basis {basis}"
+
+    @staticmethod
+    def _checkDerivatives(derivatives: str) -> None:
+        assert derivatives in ["Spectral", "Finite Difference"], \
+            f"BoltzmannSolver error: unkown derivatives option {derivatives}"
+
+
+class BoltzmannSolver(BoltzmannSolverB200Mixin):
+    """Standalone class (no WallGo import needed).  Constructor signature follows
+    boltzmann.py:52-60 plus an optional CUDA device index."""
+
+    def __init__(self, grid, basisM: str = "Cardinal", basisN: str = "Chebyshev",
+                 derivatives: str = "Spectral", collisionMultiplier: float = 1.0,
+                 truncationOption=ETruncationOption.AUTO, device: int | None = None):
+        self._initB200(grid, basisM, basisN, derivatives, collisionMultiplier, truncationOption, device)

@@ -1,0 +1,179 @@
+"""Host-side mirror of the reference's boundary types for the Boltzmann path.
+
+When WallGo itself is importable the drop-in (wallgo_b200/dropin.py) returns WallGo's own
+`Polynomial`, `BoltzmannDeltas`, `BoltzmannResults`; these stand-ins are what the standalone
+class returns on a machine without WallGo (e.g. the benchmark box).  They keep the same field
+names and the same `scalar*res`, `res+res`, `res-res` arithmetic the EOM loop relies on
+(reference containers.py:167-227, results.py:13-85, equationOfMotion.py:1352-1355).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from enum import Enum, auto
+
+import numpy as np
+
+
+class ETruncationOption(Enum):
+    """Mirror of WallGo.boltzmann.ETruncationOption (boltzmann.py:24-34)."""
+    NONE = auto()
+    AUTO = auto()
+    THIRD = auto()
+
+
+class Polynomial:
+    """Minimal stand-in: coefficient array + basis/direction/endpoints labels (polynomial.py:24-85)."""
+
+    def __init__(self, coefficients, grid, basis="Cardinal", direction="z", endpoints=False):
+        self.coefficients = np.asanyarray(coefficients)
+        self.rank = self.coefficients.ndim
+        self.grid = grid
+        self.basis = (basis,) * self.rank if isinstance(basis, str) else tuple(basis)
+        self.direction = (direction,) * self.rank if isinstance(direction, str) else tuple(direction)
+        self.endpoints = (endpoints,) * self.rank if isinstance(endpoints, bool) else tuple(endpoints)
+
+    def _like(self, coeffs):
+        return Polynomial(coeffs, self.grid, self.basis, self.direction, self.endpoints)
+
+    def __mul__(self, other):
+        if isinstance(other, Polynomial):
+            return self._like(self.coefficients * other.coefficients)
+        return self._like(other * self.coefficients)
+
+    __rmul__ = __mul__
+
+    def __add__(self, other):
+        if isinstance(other, Polynomial):
+            return self._like(self.coefficients + other.coefficients)
+        return self._like(other + self.coefficients)
+
+    __radd__ = __add__
+
+    def __sub__(self, other):
+        return self.__add__((-1.0) * other)
+
+
+@dataclass
+class BoltzmannDeltas:
+    Delta00: Polynomial  # pylint: disable=invalid-name
+    Delta02: Polynomial  # pylint: disable=invalid-name
+    Delta20: Polynomial  # pylint: disable=invalid-name
+    Delta11: Polynomial  # pylint: disable=invalid-name
+
+    def __mul__(self, number):
+        return BoltzmannDeltas(number * self.Delta00, number * self.Delta02, number * self.Delta20,
+                               number * self.Delta11)
+
+    __rmul__ = __mul__
+
+    def __add__(self, other):
+        return BoltzmannDeltas(other.Delta00 + self.Delta00, other.Delta02 + self.Delta02,
+                               other.Delta20 + self.Delta20, other.Delta11 + self.Delta11)
+
+    def __sub__(self, other):
+        return self.__add__((-1) * other)
+
+
+@dataclass
+class BoltzmannResults:
+    deltaF: np.ndarray
+    Deltas: BoltzmannDeltas  # pylint: disable=invalid-name
+    truncationError: float
+    truncatedTail: tuple
+    spectralPeaks: tuple
+    linearizationCriterion1: float = 0
+    linearizationCriterion2: float = 0
+
+    def __mul__(self, number):
+        return BoltzmannResults(
+            deltaF=number * self.deltaF, Deltas=number * self.Deltas,
+            truncationError=abs(number) * self.truncationError, truncatedTail=self.truncatedTail,
+            spectralPeaks=self.spectralPeaks,
+            linearizationCriterion1=abs(number) * self.linearizationCriterion1,
+            linearizationCriterion2=self.linearizationCriterion2)
+
+    __rmul__ = __mul__
+
+    def __add__(self, other):
+        return BoltzmannResults(
+            deltaF=other.deltaF + self.deltaF, Deltas=other.Deltas + self.Deltas,
+            truncationError=other.truncationError + self.truncationError,
+            truncatedTail=self.truncatedTail, spectralPeaks=self.spectralPeaks,
+            linearizationCriterion1=other.linearizationCriterion1 + self.linearizationCriterion1,
+            linearizationCriterion2=other.linearizationCriterion2 + self.linearizationCriterion2)
+
+    def __sub__(self, other):
+        return self.__add__((-1) * other)
+
+
+class Particle:
+    """Off-equilibrium species (reference particle.py:19-67); msqVacuum is a host callback."""
+
+    def __init__(self, name, index, msqVacuum, msqDerivative, statistics, totalDOFs):
+        if statistics not in ("Fermion", "Boson"):
+            raise ValueError(f"{statistics=} not in ['Fermion', 'Boson']")
+        self.name, self.index = name, index
+        self.msqVacuum, self.msqDerivative = msqVacuum, msqDerivative
+        self.statistics, self.totalDOFs = statistics, totalDOFs
+
+
+class BoltzmannBackground:
+    """Wall-frame background profiles on the M+1 Lobatto nodes (reference containers.py:112-164)."""
+
+    def __init__(self, velocityMid, velocityProfile, fieldProfiles, temperatureProfile,
+                 polynomialBasis="Cardinal"):
+        self.velocityWall = 0
+        self.velocityProfile = np.asarray(velocityProfile)
+        self.fieldProfiles = fieldProfiles
+        self.temperatureProfile = np.asarray(temperatureProfile)
+        self.polynomialBasis = polynomialBasis
+        self.velocityMid = velocityMid
+
+    def boostToPlasmaFrame(self):
+        vm = self.velocityMid
+        self.velocityProfile = (self.velocityProfile - vm) / (1.0 - self.velocityProfile * vm)
+        self.velocityWall = (self.velocityWall - vm) / (1.0 - self.velocityWall * vm)
+
+    def boostToWallFrame(self):
+        vw = self.velocityWall
+        self.velocityProfile = (self.velocityProfile - vw) / (1.0 - self.velocityProfile * vw)
+        self.velocityWall = 0
+
+
+class CollisionArray:
+    """In-memory collision tensor (P,N-1,N-1,P,N-1,N-1) with its momentum-polynomial basis
+    (reference collisionArray.py:95-174, 356-388)."""
+
+    def __init__(self, grid, basisType, particles, data):
+        n1 = grid.N - 1
+        data = np.asarray(data, dtype=np.float64)
+        assert data.shape == (len(particles), n1, n1, len(particles), n1, n1)
+        assert basisType in ("Cardinal", "Chebyshev")
+        self.grid, self.basisType, self.particles = grid, basisType, particles
+        self.size = n1
+        self.data = data
+
+    def __getitem__(self, key):
+        return self.data[key]
+
+    def getBasisSize(self):
+        return self.size
+
+    def getBasisType(self):
+        return self.basisType
+
+    def changeBasis(self, newBasisType):
+        """Inverse-transpose transform of the two polynomial axes (polynomial.py:282-297)."""
+        from .spectral import chebyshevMatrix, lobattoNodes
+
+        if newBasisType == self.basisType:
+            return self
+        assert newBasisType in ("Cardinal", "Chebyshev"), f"collisionarray error: unknown basis {newBasisType}"
+        _, rz, rp = lobattoNodes(self.grid.M, self.grid.N)
+        out = self.data
+        for axis, T in ((4, chebyshevMatrix(rz, self.size, "full")), (5, chebyshevMatrix(rp, self.size, "partial"))):
+            mat = T.T if newBasisType == "Chebyshev" else np.linalg.inv(T).T
+            out = np.moveaxis(np.tensordot(mat, out, axes=([1], [axis])), 0, axis)
+        self.data = np.ascontiguousarray(out)
+        self.basisType = newBasisType
+        return self

@@ -1,0 +1,463 @@
+// Device side of the Boltzmann hot path (everything except the LU):
+//   * basis / derivative tables on the Gauss-Lobatto grid        (polynomial.py:445-490, 691-862)
+//   * per-row kinematics + source term                            (boltzmann.py:651-759)
+//   * dense operator assembly, HBM-write bound                    (boltzmann.py:761-817)
+//   * basis changes, spectra, truncation, moment quadrature       (boltzmann.py:141-238, 296-491;
+//                                                                  polynomial.py:222-298, 539-567)
+// Compiled with -fmad=false so that the element formulas round like the NumPy reference
+// (separate multiply/add); the kernels here are bandwidth bound, not FLOP bound.
+#include <math.h>
+
+#include "wg_boltzmann.h"
+#include "wg_common.cuh"
+
+namespace wg {
+
+// ============================================================================ basis tables
+// Default WallGo bases: Cardinal in z, restricted Chebyshev in (p_z, p_par), spectral derivatives.
+// Nodes: chi_a=-cos(a pi/M), rz_b=-cos(b pi/N), rp_g=-cos(g pi/(N-1)); on these nodes
+// T_n(-cos t) = (-1)^n cos(n t) and U_{n-1}(-cos t) = (-1)^{n+1} sin(n t)/sin(t), evaluated with
+// cospi/sinpi on an exactly reduced integer argument.
+__device__ __forceinline__ double cospi_ratio(long long num, long long den) {
+  num %= 2 * den;
+  return cospi((double)num / (double)den);
+}
+__device__ __forceinline__ double sinpi_ratio(long long num, long long den) {
+  num %= 2 * den;
+  return sinpi((double)num / (double)den);
+}
+
+__global__ void wg_basis_kernel(int M, int N, const double* __restrict__ rz, double* __restrict__ Tchi,
+                                double* __restrict__ Dchi, double* __restrict__ DchiFull,
+                                double* __restrict__ Trz, double* __restrict__ Drz,
+                                double* __restrict__ Trp) {
+  const int M1 = M - 1, N1 = N - 1;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  // Lagrange-cardinal differentiation matrix on the M+1 Lobatto nodes: DchiFull[j][i] = C_i'(x_j)
+  for (int e = tid; e < (M + 1) * (M + 1); e += nth) {
+    const int j = e / (M + 1), i = e % (M + 1);
+    double v;
+    if (i != j) {
+      const double dx = 2.0 * sinpi_ratio(i + j, 2 * M) * sinpi_ratio(j - i + 4LL * M, 2 * M);  // x_j - x_i
+      const double cj = (j == 0 || j == M) ? 2.0 : 1.0, ci = (i == 0 || i == M) ? 2.0 : 1.0;
+      v = (cj / ci) * (((i + j) & 1) ? -1.0 : 1.0) / dx;
+    } else if (j == 0) {
+      v = -(2.0 * M * M + 1.0) / 6.0;
+    } else if (j == M) {
+      v = (2.0 * M * M + 1.0) / 6.0;
+    } else {
+      const double x = -cospi_ratio(j, M), s = sinpi_ratio(j, M);
+      v = -x / (2.0 * s * s);
+    }
+    DchiFull[e] = v;
+    if (j >= 1 && j < M && i >= 1 && i < M) {
+      Dchi[(j - 1) * M1 + (i - 1)] = v;
+      Tchi[(j - 1) * M1 + (i - 1)] = (i == j) ? 1.0 : 0.0;
+    }
+  }
+  for (int e = tid; e < N1 * N1; e += nth) {
+    const int b = e / N1 + 1, n = e % N1 + 2;  // rz node b = 1..N-1, order n = 2..N
+    const double sgn = (n & 1) ? -1.0 : 1.0;
+    const double Tn = sgn * cospi_ratio((long long)n * b, N);
+    const double x = rz[b - 1];
+    Trz[e] = Tn - ((n & 1) ? x : 1.0);
+    const double Un1 = -sgn * sinpi_ratio((long long)n * b, N) / sinpi_ratio(b, N);
+    Drz[e] = (double)n * Un1 - ((n & 1) ? 1.0 : 0.0);
+    const int g = e / N1, k = e % N1 + 1;  // rp node g = 0..N-2, order k = 1..N-1
+    const double Tk = ((k & 1) ? -1.0 : 1.0) * cospi_ratio((long long)k * g, N - 1);
+    Trp[e] = Tk - 1.0;
+  }
+}
+
+// K = X (kron) Y for (N-1)x(N-1) factors: K[(b*N1+g)*q + (j*N1+k)] = X[b][j] * Y[g][k]
+__global__ void wg_kron_kernel(int N1, const double* __restrict__ X, const double* __restrict__ Y,
+                               double* __restrict__ K) {
+  const int q = N1 * N1;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < (long long)q * q;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(e / q), c = (int)(e % q);
+    K[e] = X[(r / N1) * N1 + c / N1] * Y[(r % N1) * N1 + c % N1];
+  }
+}
+
+// ============================================================================ per-solve prologue
+// profiles = [ T(M+1) | v(M+1) | msq(P x (M+1)) | dxidchi(M-1) ]; derivs = [ dT | dv | dmsq ] on M+1 nodes
+__global__ void wg_profile_deriv_kernel(int M, int P, const double* __restrict__ DchiFull,
+                                        const double* __restrict__ prof, double* __restrict__ derivs) {
+  const int L = M + 1;
+  for (int e = threadIdx.x; e < (2 + P) * L; e += blockDim.x) {
+    const int f = e / L, j = e % L;
+    const double* fv = prof + f * L;
+    const double* drow = DchiFull + j * L;
+    double s = 0.0;
+    for (int i = 0; i < L; ++i) s += drow[i] * fv[i];
+    derivs[e] = s;
+  }
+}
+
+__global__ void wg_rows_kernel(BzDims d, const double* __restrict__ prof, const double* __restrict__ derivs,
+                               const double* __restrict__ pz, const double* __restrict__ pp,
+                               const double* __restrict__ dpzdrz, const double* __restrict__ stat, double vw,
+                               double collMult, double liouScale, double* __restrict__ w1, double* __restrict__ w2,
+                               double* __restrict__ cT2, double* __restrict__ S) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= d.n) return;
+  const int L = d.M + 1;
+  const int gmm = r % d.N1, bt = (r / d.N1) % d.N1, al = (r / d.q) % d.M1, a = r / (d.q * d.M1);
+  const double T = prof[al + 1], v = prof[L + al + 1], msq = prof[(2 + a) * L + al + 1];
+  const double dxidchi = prof[(2 + d.P) * L + al];
+  const double dT = derivs[al + 1], dv = derivs[L + al + 1], dmsq = derivs[(2 + a) * L + al + 1];
+  const double pzv = pz[bt], ppv = pp[gmm];
+  const double E = sqrt(msq + pzv * pzv + ppv * ppv);
+  const double gw = 1.0 / sqrt(1.0 - vw * vw);
+  const double Pw = gw * (pzv - vw * E);
+  const double gpl = 1.0 / sqrt(1.0 - v * v);
+  const double Epl = gpl * (E - v * pzv);
+  const double Ppl = gpl * (pzv - v * E);
+  const double uwupl = gw * gpl * (vw - v);
+  const double dchidxi = 1.0 / dxidchi;
+  const double drzdpz = 1.0 / dpzdrz[bt];
+  const double x = Epl / T;
+  const double s = stat[a];
+  // boltzmann.py:876-886 ; MAX_EXPONENT = 1024 ln 2
+  const double dfeq = (x > 709.782712893384) ? -0.0 : -1.0 / (exp(x) - 2.0 * s + exp(-x));
+  S[r] = (dfeq / T) * dchidxi * (Pw * Ppl * (gpl * gpl) * dv + Pw * Epl * dT / T + 0.5 * dmsq * uwupl);
+  w1[r] = liouScale * (dchidxi * Pw);
+  w2[r] = liouScale * (dchidxi * drzdpz * (gw / 2.0) * dmsq);
+  if (r < d.M1) {
+    const double Ta = prof[r + 1];
+    cT2[r] = collMult * (Ta * Ta);
+  }
+}
+
+// ============================================================================ operator assembly
+// One CTA = R consecutive (beta,gamma) rows at fixed (species a, position alpha); it writes R complete
+// rows of the n x n operator.  The R-row tiles of K1 = Trz(x)Trp, K2 = Drz(x)Trp and of the collision
+// tensor are staged in shared memory with TMA bulk copies; the K1 tile (scaled by the Liouville row
+// weight) then lives in registers and is re-used for all (M-1) z-blocks of the row.
+template <int R>
+__global__ void __launch_bounds__(512) wg_assemble_kernel(BzDims d, const double* __restrict__ K1,
+                                                          const double* __restrict__ K2,
+                                                          const double* __restrict__ Coll,
+                                                          const double* __restrict__ Tchi,
+                                                          const double* __restrict__ Dchi,
+                                                          const double* __restrict__ w1,
+                                                          const double* __restrict__ w2,
+                                                          const double* __restrict__ cT2,
+                                                          double* __restrict__ A, long long lda) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int q = d.q, M1 = d.M1, P = d.P;
+  double* K1s = reinterpret_cast<double*>(smraw);  // [R][q]
+  double* K2s = K1s + R * q;                       // [R][q]
+  double* Cs = K2s + R * q;                        // [R][P*q]
+  double* dch = Cs + (size_t)R * P * q;            // [M1]
+  double* tch = dch + M1;                          // [M1]
+  __shared__ __align__(8) uint64_t bar;
+
+  const int a = blockIdx.y / M1, al = blockIdx.y % M1;
+  const int bg0 = blockIdx.x * R;
+  const long long r0 = ((long long)a * M1 + al) * q + bg0;
+  const int tid = threadIdx.x;
+
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t kb = (uint32_t)(R * q * sizeof(double));
+    const uint32_t cb = (uint32_t)((size_t)R * P * q * sizeof(double));
+    mbar_expect_tx(&bar, 2 * kb + cb);
+    tma_load_1d(K1s, K1 + (size_t)bg0 * q, kb, &bar);
+    tma_load_1d(K2s, K2 + (size_t)bg0 * q, kb, &bar);
+    tma_load_1d(Cs, Coll + ((size_t)a * q + bg0) * ((size_t)P * q), cb, &bar);
+  }
+  for (int i = tid; i < M1; i += blockDim.x) {
+    dch[i] = Dchi[al * M1 + i];
+    tch[i] = Tchi[al * M1 + i];
+  }
+  double rw1[R], rw2[R];
+#pragma unroll
+  for (int rr = 0; rr < R; ++rr) {
+    rw1[rr] = w1[r0 + rr];
+    rw2[rr] = w2[r0 + rr];
+  }
+  const double ct2 = cT2[al];
+  __syncthreads();
+  mbar_wait(&bar, 0);
+
+  for (int cp = tid; cp < q / 2; cp += blockDim.x) {
+    double2 wk[R];
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+      const double2 kv = *reinterpret_cast<const double2*>(K1s + rr * q + 2 * cp);
+      wk[rr] = make_double2(rw1[rr] * kv.x, rw1[rr] * kv.y);
+    }
+    for (int b = 0; b < P; ++b) {
+      const bool same = (b == a);
+      double* out = A + r0 * lda + (long long)b * M1 * q + 2 * cp;
+      for (int i = 0; i < M1; ++i, out += q) {
+        const double dv = same ? dch[i] : 0.0;
+        const double tx = tch[i];
+        if (tx == 0.0) {
+#pragma unroll
+          for (int rr = 0; rr < R; ++rr)
+            *reinterpret_cast<double2*>(out + rr * lda) = make_double2(wk[rr].x * dv, wk[rr].y * dv);
+        } else {
+          const double ctx = ct2 * tx;
+#pragma unroll
+          for (int rr = 0; rr < R; ++rr) {
+            const double2 cv = *reinterpret_cast<const double2*>(Cs + ((size_t)rr * P + b) * q + 2 * cp);
+            double vx = wk[rr].x * dv, vy = wk[rr].y * dv;
+            if (same) {
+              const double2 k2 = *reinterpret_cast<const double2*>(K2s + rr * q + 2 * cp);
+              const double c2 = rw2[rr] * tx;
+              vx -= c2 * k2.x;
+              vy -= c2 * k2.y;
+            }
+            vx += ctx * cv.x;
+            vy += ctx * cv.y;
+            *reinterpret_cast<double2*>(out + rr * lda) = make_double2(vx, vy);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ============================================================================ basis changes / moments
+// in viewed as [outer][len][inner];  out[o][x][s] = sum_x' Mat[x][x'] * in[o][x'][s]
+__global__ void wg_apply_axis_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                     const double* __restrict__ Mat, int outer, int len, int inner) {
+  const long long total = (long long)outer * len * inner;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(e % inner), x = (int)((e / inner) % len);
+    const long long o = e / ((long long)inner * len);
+    const double* src = in + o * len * inner + s;
+    const double* m = Mat + (long long)x * len;
+    double acc = 0.0;
+    for (int xp = 0; xp < len; ++xp) acc += m[xp] * src[(long long)xp * inner];
+    out[e] = acc;
+  }
+}
+
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (warp == 0) {
+    t = lane < nw ? red[lane] : 0.0;
+    t = warp_sum(t);
+  }
+  return t;  // valid in warp 0
+}
+
+// spectra[0..M1) = sum_{a,j,k}|c| ; [M1..M1+N1) = sum_{a,i,k}|c| ; [M1+N1..M1+2N1) = sum_{a,i,j}|c|
+__global__ void wg_spectra_kernel(BzDims d, const double* __restrict__ c, double* __restrict__ spectra) {
+  __shared__ double red[32];
+  const int bin = blockIdx.x;
+  const int M1 = d.M1, N1 = d.N1, q = d.q;
+  double s = 0.0;
+  if (bin < M1) {
+    for (int e = threadIdx.x; e < d.P * q; e += blockDim.x)
+      s += fabs(c[((long long)(e / q) * M1 + bin) * q + e % q]);
+  } else if (bin < M1 + N1) {
+    const int j = bin - M1;
+    for (int e = threadIdx.x; e < d.P * M1 * N1; e += blockDim.x)
+      s += fabs(c[((long long)(e / N1)) * q + j * N1 + e % N1]);
+  } else {
+    const int k = bin - M1 - N1;
+    for (int e = threadIdx.x; e < d.P * M1 * N1; e += blockDim.x) s += fabs(c[(long long)e * N1 + k]);
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) spectra[bin] = s;
+}
+
+// zero the truncated tails in place and reduce the truncation-error sums:
+//   err[a*4+0] = sum |c| over the kept box, err[a*4+1..3] = sum |c| on the last kept chi / pz / pp slice
+__global__ void wg_truncate_kernel(BzDims d, double* __restrict__ c, int keepM, int keepN1, int keepN2,
+                                   double* __restrict__ err) {
+  __shared__ double red[32];
+  const int a = blockIdx.x;
+  const int M1 = d.M1, N1 = d.N1, q = d.q;
+  double tot = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+  for (int e = threadIdx.x; e < M1 * q; e += blockDim.x) {
+    const int i = e / q, j = (e / N1) % N1, k = e % N1;
+    double* p = c + (long long)a * M1 * q + e;
+    if (i >= keepM || j >= keepN1 || k >= keepN2) {
+      *p = 0.0;
+    } else {
+      const double v = fabs(*p);
+      tot += v;
+      if (i == keepM - 1) e1 += v;
+      if (j == keepN1 - 1) e2 += v;
+      if (k == keepN2 - 1) e3 += v;
+    }
+  }
+  tot = block_sum(tot, red);
+  e1 = block_sum(e1, red);
+  e2 = block_sum(e2, red);
+  e3 = block_sum(e3, red);
+  if (threadIdx.x == 0) {
+    err[a * 4 + 0] = tot;
+    err[a * 4 + 1] = e1;
+    err[a * 4 + 2] = e2;
+    err[a * 4 + 3] = e3;
+  }
+}
+
+// Delta_{00,02,20,11}[a][alpha] : Gauss-Chebyshev-Lobatto quadrature of the cardinal-basis deltaF
+// (boltzmann.py:199-225, polynomial.py:546-561).  deltas layout [4][P][M1].
+__global__ void wg_moments_kernel(BzDims d, const double* __restrict__ card, const double* __restrict__ prof,
+                                  const double* __restrict__ rz, const double* __restrict__ rp,
+                                  const double* __restrict__ pz, const double* __restrict__ pp,
+                                  const double* __restrict__ dpzdrz, const double* __restrict__ dppdrp,
+                                  double* __restrict__ deltas) {
+  __shared__ double red[32];
+  const int a = blockIdx.x / d.M1, al = blockIdx.x % d.M1;
+  const int N1 = d.N1, q = d.q, L = d.M + 1;
+  const double msq = prof[(2 + a) * L + al + 1];
+  const double* f = card + ((long long)a * d.M1 + al) * q;
+  const double PI = 3.141592653589793;
+  double s00 = 0.0, s02 = 0.0, s20 = 0.0, s11 = 0.0;
+  for (int e = threadIdx.x; e < q; e += blockDim.x) {
+    const int b = e / N1, g = e % N1;
+    const double pzv = pz[b], ppv = pp[g];
+    const double E = sqrt(msq + pzv * pzv + ppv * ppv);
+    const double base = dpzdrz[b] * dppdrp[g] * ppv / (4.0 * (PI * PI) * E);
+    double wz = PI / (double)d.N;
+    double wp = PI / (double)(d.N - 1);
+    if (g == 0) wp = wp / 2.0;
+    wz = sqrt(1.0 - rz[b] * rz[b]) * wz;
+    wp = sqrt(1.0 - rp[g] * rp[g]) * wp;
+    const double fv = f[e];
+    s00 += ((base * fv) * wz) * wp;
+    s02 += (((pzv * pzv) * base * fv) * wz) * wp;
+    s20 += (((E * E) * base * fv) * wz) * wp;
+    s11 += (((E * pzv) * base * fv) * wz) * wp;
+  }
+  s00 = block_sum(s00, red);
+  s02 = block_sum(s02, red);
+  s20 = block_sum(s20, red);
+  s11 = block_sum(s11, red);
+  if (threadIdx.x == 0) {
+    const int PM = d.P * d.M1, o = a * d.M1 + al;
+    deltas[0 * PM + o] = s00;
+    deltas[1 * PM + o] = s02;
+    deltas[2 * PM + o] = s20;
+    deltas[3 * PM + o] = s11;
+  }
+}
+
+// y = Coll-operator * x : y[a,al,bg] = cT2[al] * sum_{b,i,jk} Tchi[al][i] C[a,bg,b,jk] x[b,i,jk]
+// (the collision part of the operator applied to a vector; boltzmann.py:541-545)
+__global__ void wg_collision_matvec_kernel(BzDims d, const double* __restrict__ Coll,
+                                           const double* __restrict__ Tchi, const double* __restrict__ cT2,
+                                           const double* __restrict__ x, double* __restrict__ y) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= d.n) return;
+  const int q = d.q, M1 = d.M1, P = d.P;
+  const int bg = warp % q, al = (warp / q) % M1, a = warp / (q * M1);
+  const double* crow = Coll + ((long long)a * q + bg) * ((long long)P * q);
+  double s = 0.0;
+  for (int i = 0; i < M1; ++i) {
+    const double tx = Tchi[al * M1 + i];
+    if (tx == 0.0) continue;
+    for (int b = 0; b < P; ++b) {
+      const double* xv = x + ((long long)b * M1 + i) * q;
+      double t = 0.0;
+      for (int jk = lane; jk < q; jk += 32) t += crow[b * q + jk] * xv[jk];
+      s += tx * t;
+    }
+  }
+  s = warp_sum(s);
+  if (lane == 0) y[warp] = cT2[al] * s;
+}
+
+// ============================================================================ host launchers
+int bz_build_basis(const BzDims& d, const double* rz, double* Tchi, double* Dchi, double* DchiFull,
+                   double* Trz, double* Drz, double* Trp, cudaStream_t st) {
+  wg_basis_kernel<<<8, 256, 0, st>>>(d.M, d.N, rz, Tchi, Dchi, DchiFull, Trz, Drz, Trp);
+  WG_LAUNCH_CHECK();
+  return WG_OK;
+}
+
+int bz_build_kron(const BzDims& d, const double* Trz, const double* Drz, const double* Trp, double* K1,
+                  double* K2, cudaStream_t st) {
+  const int blocks = wg_cdiv((long long)d.q * d.q, 256);
+  wg_kron_kernel<<<blocks < 1184 ? blocks : 1184, 256, 0, st>>>(d.N1, Trz, Trp, K1);
+  WG_LAUNCH_CHECK();
+  wg_kron_kernel<<<blocks < 1184 ? blocks : 1184, 256, 0, st>>>(d.N1, Drz, Trp, K2);
+  WG_LAUNCH_CHECK();
+  return WG_OK;
+}
+
+int bz_assemble(const BzDims& d, const BzStatic& s, const double* prof, double vw, double collMult, int parts,
+                double* derivs, double* w1, double* w2, double* cT2, double* A, long long lda, double* S,
+                cudaStream_t st) {
+  WG_REQUIRE(d.q % 4 == 0, "assemble: (N-1)^2 must be a multiple of 4 (N odd)");
+  WG_REQUIRE(lda % 2 == 0 && reinterpret_cast<uintptr_t>(A) % 16 == 0, "assemble: A must be 16B aligned, lda even");
+  wg_profile_deriv_kernel<<<1, 256, 0, st>>>(d.M, d.P, s.DchiFull, prof, derivs);
+  WG_LAUNCH_CHECK();
+  wg_rows_kernel<<<wg_cdiv(d.n, 256), 256, 0, st>>>(d, prof, derivs, s.pz, s.pp, s.dpzdrz, s.stat, vw,
+                                                   (parts & 2) ? collMult : 0.0, (parts & 1) ? 1.0 : 0.0, w1, w2,
+                                                   cT2, S);
+  WG_LAUNCH_CHECK();
+  constexpr int R = 4;
+  const size_t smem = ((size_t)R * d.q * (2 + d.P) + 2 * d.M1) * sizeof(double);
+  WG_REQUIRE(smem <= 200 * 1024, "assemble: basis tile does not fit in shared memory");
+  static size_t configured = 0;
+  if (smem > configured) {
+    WG_CUDA(cudaFuncSetAttribute(wg_assemble_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  int threads = ((d.q / 2 + 31) / 32) * 32;
+  if (threads > 512) threads = 512;
+  if (threads < 64) threads = 64;
+  dim3 grid(d.q / R, d.P * d.M1);
+  wg_assemble_kernel<R><<<grid, threads, smem, st>>>(d, s.K1, s.K2, s.Coll, s.Tchi, s.Dchi, w1, w2, cT2, A, lda);
+  WG_LAUNCH_CHECK();
+  return WG_OK;
+}
+
+int bz_apply_axis(const double* in, double* out, const double* Mat, int outer, int len, int inner,
+                  cudaStream_t st) {
+  const long long total = (long long)outer * len * inner;
+  int blocks = wg_cdiv(total, 256);
+  if (blocks > 2368) blocks = 2368;
+  wg_apply_axis_kernel<<<blocks, 256, 0, st>>>(in, out, Mat, outer, len, inner);
+  WG_LAUNCH_CHECK();
+  return WG_OK;
+}
+
+int bz_spectra(const BzDims& d, const double* c, double* spectra, cudaStream_t st) {
+  wg_spectra_kernel<<<d.M1 + 2 * d.N1, 256, 0, st>>>(d, c, spectra);
+  WG_LAUNCH_CHECK();
+  return WG_OK;
+}
+
+int bz_truncate(const BzDims& d, double* c, int keepM, int keepN1, int keepN2, double* err, cudaStream_t st) {
+  wg_truncate_kernel<<<d.P, 256, 0, st>>>(d, c, keepM, keepN1, keepN2, err);
+  WG_LAUNCH_CHECK();
+  return WG_OK;
+}
+
+int bz_moments(const BzDims& d, const BzStatic& s, const double* card, const double* prof, double* deltas,
+               cudaStream_t st) {
+  wg_moments_kernel<<<d.P * d.M1, 128, 0, st>>>(d, card, prof, s.rz, s.rp, s.pz, s.pp, s.dpzdrz, s.dppdrp, deltas);
+  WG_LAUNCH_CHECK();
+  return WG_OK;
+}
+
+int bz_collision_matvec(const BzDims& d, const BzStatic& s, const double* cT2, const double* x, double* y,
+                        cudaStream_t st) {
+  wg_collision_matvec_kernel<<<wg_cdiv((long long)d.n * 32, 256), 256, 0, st>>>(d, s.Coll, s.Tchi, cT2, x, y);
+  WG_LAUNCH_CHECK();
+  return WG_OK;
+}
+
+}  // namespace wg

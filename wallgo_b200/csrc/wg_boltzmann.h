@@ -1,0 +1,41 @@
+// Internal declarations for the Boltzmann device path (wg_boltzmann.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace wg {
+
+struct BzDims {
+  int P, M, N;   // species, spatial, momentum basis sizes (N odd)
+  int M1, N1;    // M-1, N-1
+  int q;         // (N-1)^2
+  int n;         // P*(M-1)*q
+};
+
+// device pointers to everything that is constant for one grid / basis / collision tensor
+struct BzStatic {
+  double *chi, *rz, *rp, *pz, *pp, *dpzdrz, *dppdrp;  // grid (momentum maps fixed per run)
+  double* stat;                                       // [P]  +1 boson, -1 fermion
+  double *Tchi, *Dchi;                                // [M1*M1]
+  double* DchiFull;                                   // [(M+1)^2]
+  double *Trz, *Drz, *Trp;                            // [N1*N1]
+  double *K1, *K2;                                    // [q*q]  Trz(x)Trp, Drz(x)Trp
+  double* Coll;                                       // [(P q)^2]  C[a,bg,b,jk], solver basis
+};
+
+int bz_build_basis(const BzDims& d, const double* rz, double* Tchi, double* Dchi, double* DchiFull,
+                   double* Trz, double* Drz, double* Trp, cudaStream_t st);
+int bz_build_kron(const BzDims& d, const double* Trz, const double* Drz, const double* Trp, double* K1,
+                  double* K2, cudaStream_t st);
+int bz_assemble(const BzDims& d, const BzStatic& s, const double* prof, double vw, double collMult, int parts,
+                double* derivs, double* w1, double* w2, double* cT2, double* A, long long lda, double* S,
+                cudaStream_t st);
+int bz_apply_axis(const double* in, double* out, const double* Mat, int outer, int len, int inner,
+                  cudaStream_t st);
+int bz_spectra(const BzDims& d, const double* c, double* spectra, cudaStream_t st);
+int bz_truncate(const BzDims& d, double* c, int keepM, int keepN1, int keepN2, double* err, cudaStream_t st);
+int bz_moments(const BzDims& d, const BzStatic& s, const double* card, const double* prof, double* deltas,
+               cudaStream_t st);
+int bz_collision_matvec(const BzDims& d, const BzStatic& s, const double* cT2, const double* x, double* y,
+                        cudaStream_t st);
+
+}  // namespace wg

@@ -1,0 +1,392 @@
+// extern "C" boundary of libwallgo_b200.so (see include/wallgo_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/wallgo_b200.h"
+#include "wg_boltzmann.h"
+#include "wg_common.cuh"
+#include "wg_kernels.h"
+
+static thread_local char g_err[512] = "";
+long long g_wg_launches = 0;
+void wg_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+struct wg_lu {
+  wg::LuPlan* plan = nullptr;
+  int device = 0;
+};
+
+struct wg_solver {
+  wg::BzDims d;
+  int device = 0;
+  wg::BzStatic st = {};
+  std::vector<void*> allocs;
+  double* mats[9] = {};  // transforms (device) or nullptr
+  // per-solve scratch
+  double *derivs = nullptr, *w1 = nullptr, *w2 = nullptr, *cT2 = nullptr;
+  double *cheb = nullptr, *bufA = nullptr, *bufB = nullptr;
+  int *ipiv = nullptr, *info = nullptr;
+  wg::LuPlan* plan = nullptr;
+  bool haveGrid = false, haveTables = false, haveColl = false, haveStat = false, assembled = false;
+};
+
+template <typename T>
+static int dev_alloc(wg_solver* s, T** p, size_t count) {
+  WG_CUDA(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+  s->allocs.push_back(*p);
+  return WG_OK;
+}
+
+static int require_device(int device) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    wg_set_error("no CUDA device available (%s); wallgo_b200 has no CPU path",
+                 e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return WG_ERR_CUDA;
+  }
+  WG_REQUIRE(device >= 0 && device < count, "device index out of range");
+  WG_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  WG_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    wg_set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major,
+                 prop.minor);
+    return WG_ERR_UNSUPPORTED;
+  }
+  return WG_OK;
+}
+
+extern "C" {
+
+int wg_version(void) { return 100; }
+long long wg_launch_count(void) { return g_wg_launches; }
+const char* wg_last_error(void) { return g_err; }
+int wg_set_tuning(int nb, int use_graph) {
+  wg::lu_set_tuning(nb, use_graph);
+  return WG_OK;
+}
+
+int wg_create(int P, int M, int N, int device, wg_solver** out) {
+  WG_REQUIRE(out != nullptr, "wg_create: out is NULL");
+  WG_REQUIRE(P >= 1 && M >= 3 && N >= 3 && (N % 2 == 1), "wg_create: need P>=1, M>=3, N>=3 and N odd");
+  int rc = require_device(device);
+  if (rc) return rc;
+  wg_solver* s = new wg_solver();
+  s->device = device;
+  wg::BzDims& d = s->d;
+  d.P = P;
+  d.M = M;
+  d.N = N;
+  d.M1 = M - 1;
+  d.N1 = N - 1;
+  d.q = d.N1 * d.N1;
+  d.n = P * d.M1 * d.q;
+  const size_t M1 = d.M1, N1 = d.N1, q = d.q, n = d.n;
+#define A_(ptr, cnt)                      \
+  rc = dev_alloc(s, &(ptr), (cnt));       \
+  if (rc) {                               \
+    wg_destroy(s);                        \
+    return rc;                            \
+  }
+  A_(s->st.chi, M1) A_(s->st.rz, N1) A_(s->st.rp, N1) A_(s->st.pz, N1) A_(s->st.pp, N1)
+  A_(s->st.dpzdrz, N1) A_(s->st.dppdrp, N1) A_(s->st.stat, (size_t)P)
+  A_(s->st.Tchi, M1 * M1) A_(s->st.Dchi, M1 * M1) A_(s->st.DchiFull, (size_t)(M + 1) * (M + 1))
+  A_(s->st.Trz, N1 * N1) A_(s->st.Drz, N1 * N1) A_(s->st.Trp, N1 * N1)
+  A_(s->st.K1, q * q) A_(s->st.K2, q * q) A_(s->st.Coll, (size_t)P * q * P * q)
+  A_(s->derivs, (size_t)(2 + P) * (M + 1)) A_(s->w1, n) A_(s->w2, n) A_(s->cT2, M1)
+  A_(s->cheb, n) A_(s->bufA, n) A_(s->bufB, n) A_(s->ipiv, n) A_(s->info, (size_t)1)
+#undef A_
+  WG_CUDA(cudaMemset(s->info, 0, sizeof(int)));
+  rc = wg::lu_plan_create(d.n, &s->plan);
+  if (rc) {
+    wg_destroy(s);
+    return rc;
+  }
+  *out = s;
+  return WG_OK;
+}
+
+int wg_destroy(wg_solver* s) {
+  if (!s) return WG_OK;
+  cudaSetDevice(s->device);
+  for (void* p : s->allocs) cudaFree(p);
+  for (int i = 0; i < 9; ++i)
+    if (s->mats[i]) cudaFree(s->mats[i]);
+  wg::lu_plan_destroy(s->plan);
+  delete s;
+  return WG_OK;
+}
+
+int wg_dims(const wg_solver* s, int* n, int* q) {
+  WG_REQUIRE(s, "wg_dims: NULL solver");
+  if (n) *n = s->d.n;
+  if (q) *q = s->d.q;
+  return WG_OK;
+}
+
+static int h2d(double* dst, const double* src, size_t count) {
+  WG_REQUIRE(src != nullptr, "NULL host pointer");
+  WG_CUDA(cudaMemcpy(dst, src, count * sizeof(double), cudaMemcpyHostToDevice));
+  return WG_OK;
+}
+
+int wg_set_grid(wg_solver* s, const double* chi, const double* rz, const double* rp, const double* pz,
+                const double* pp, const double* dpzdrz, const double* dppdrp) {
+  WG_REQUIRE(s, "wg_set_grid: NULL solver");
+  WG_CUDA(cudaSetDevice(s->device));
+  int rc = 0;
+  rc |= h2d(s->st.chi, chi, s->d.M1);
+  rc |= h2d(s->st.rz, rz, s->d.N1);
+  rc |= h2d(s->st.rp, rp, s->d.N1);
+  rc |= h2d(s->st.pz, pz, s->d.N1);
+  rc |= h2d(s->st.pp, pp, s->d.N1);
+  rc |= h2d(s->st.dpzdrz, dpzdrz, s->d.N1);
+  rc |= h2d(s->st.dppdrp, dppdrp, s->d.N1);
+  if (rc) return rc < 0 ? rc : WG_ERR_CUDA;
+  s->haveGrid = true;
+  return WG_OK;
+}
+
+int wg_set_statistics(wg_solver* s, const double* statistics) {
+  WG_REQUIRE(s, "wg_set_statistics: NULL solver");
+  WG_CUDA(cudaSetDevice(s->device));
+  int rc = h2d(s->st.stat, statistics, s->d.P);
+  if (rc) return rc;
+  s->haveStat = true;
+  return WG_OK;
+}
+
+int wg_build_basis(wg_solver* s) {
+  WG_REQUIRE(s && s->haveGrid, "wg_build_basis: call wg_set_grid first");
+  WG_CUDA(cudaSetDevice(s->device));
+  int rc = wg::bz_build_basis(s->d, s->st.rz, s->st.Tchi, s->st.Dchi, s->st.DchiFull, s->st.Trz, s->st.Drz,
+                              s->st.Trp, 0);
+  if (rc) return rc;
+  rc = wg::bz_build_kron(s->d, s->st.Trz, s->st.Drz, s->st.Trp, s->st.K1, s->st.K2, 0);
+  if (rc) return rc;
+  WG_CUDA(cudaDeviceSynchronize());
+  s->haveTables = true;
+  return WG_OK;
+}
+
+int wg_set_tables(wg_solver* s, const double* Tchi, const double* Dchi, const double* DchiFull,
+                  const double* Trz, const double* Drz, const double* Trp) {
+  WG_REQUIRE(s, "wg_set_tables: NULL solver");
+  WG_CUDA(cudaSetDevice(s->device));
+  const size_t M1 = s->d.M1, N1 = s->d.N1, L = s->d.M + 1;
+  int rc = 0;
+  rc |= h2d(s->st.Tchi, Tchi, M1 * M1);
+  rc |= h2d(s->st.Dchi, Dchi, M1 * M1);
+  rc |= h2d(s->st.DchiFull, DchiFull, L * L);
+  rc |= h2d(s->st.Trz, Trz, N1 * N1);
+  rc |= h2d(s->st.Drz, Drz, N1 * N1);
+  rc |= h2d(s->st.Trp, Trp, N1 * N1);
+  if (rc) return rc < 0 ? rc : WG_ERR_CUDA;
+  rc = wg::bz_build_kron(s->d, s->st.Trz, s->st.Drz, s->st.Trp, s->st.K1, s->st.K2, 0);
+  if (rc) return rc;
+  WG_CUDA(cudaDeviceSynchronize());
+  s->haveTables = true;
+  return WG_OK;
+}
+
+int wg_get_tables(wg_solver* s, double* Tchi, double* Dchi, double* DchiFull, double* Trz, double* Drz,
+                  double* Trp) {
+  WG_REQUIRE(s && s->haveTables, "wg_get_tables: no tables yet");
+  WG_CUDA(cudaSetDevice(s->device));
+  const size_t M1 = s->d.M1, N1 = s->d.N1, L = s->d.M + 1;
+  if (Tchi) WG_CUDA(cudaMemcpy(Tchi, s->st.Tchi, M1 * M1 * 8, cudaMemcpyDeviceToHost));
+  if (Dchi) WG_CUDA(cudaMemcpy(Dchi, s->st.Dchi, M1 * M1 * 8, cudaMemcpyDeviceToHost));
+  if (DchiFull) WG_CUDA(cudaMemcpy(DchiFull, s->st.DchiFull, L * L * 8, cudaMemcpyDeviceToHost));
+  if (Trz) WG_CUDA(cudaMemcpy(Trz, s->st.Trz, N1 * N1 * 8, cudaMemcpyDeviceToHost));
+  if (Drz) WG_CUDA(cudaMemcpy(Drz, s->st.Drz, N1 * N1 * 8, cudaMemcpyDeviceToHost));
+  if (Trp) WG_CUDA(cudaMemcpy(Trp, s->st.Trp, N1 * N1 * 8, cudaMemcpyDeviceToHost));
+  return WG_OK;
+}
+
+int wg_set_transforms(wg_solver* s, const double* const mats[9]) {
+  WG_REQUIRE(s && mats, "wg_set_transforms: NULL argument");
+  WG_CUDA(cudaSetDevice(s->device));
+  for (int i = 0; i < 9; ++i) {
+    if (s->mats[i]) {
+      cudaFree(s->mats[i]);
+      s->mats[i] = nullptr;
+    }
+    if (!mats[i]) continue;
+    const size_t len = (i % 3 == 0) ? s->d.M1 : s->d.N1;
+    WG_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->mats[i]), len * len * sizeof(double)));
+    WG_CUDA(cudaMemcpy(s->mats[i], mats[i], len * len * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  return WG_OK;
+}
+
+int wg_set_collision(wg_solver* s, const double* C, int on_device) {
+  WG_REQUIRE(s && C, "wg_set_collision: NULL argument");
+  WG_CUDA(cudaSetDevice(s->device));
+  const size_t cnt = (size_t)s->d.P * s->d.q * s->d.P * s->d.q;
+  WG_CUDA(cudaMemcpy(s->st.Coll, C, cnt * sizeof(double),
+                     on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  s->haveColl = true;
+  return WG_OK;
+}
+
+int wg_assemble(wg_solver* s, const double* profiles_dev, double vw, double collisionMultiplier, int parts,
+                double* A_dev, long long lda, double* S_dev, void* stream) {
+  WG_REQUIRE(s && profiles_dev && A_dev && S_dev, "wg_assemble: NULL argument");
+  if (!(s->haveGrid && s->haveTables && s->haveColl && s->haveStat)) {
+    wg_set_error("wg_assemble: grid, statistics, tables and collision tensor must be set first");
+    return WG_ERR_STATE;
+  }
+  WG_REQUIRE(lda >= s->d.n, "wg_assemble: lda < n");
+  int rc = wg::bz_assemble(s->d, s->st, profiles_dev, vw, collisionMultiplier, parts, s->derivs, s->w1, s->w2,
+                           s->cT2, A_dev, lda, S_dev, (cudaStream_t)stream);
+  if (rc == WG_OK && (parts & 2)) s->assembled = true;
+  return rc;
+}
+
+int wg_factor(wg_solver* s, double* A_dev, long long lda, void* stream) {
+  WG_REQUIRE(s && A_dev, "wg_factor: NULL argument");
+  return wg::lu_factor(s->plan, A_dev, lda, s->ipiv, s->info, (cudaStream_t)stream);
+}
+
+int wg_solve(wg_solver* s, const double* LU_dev, long long lda, double* b_dev, void* stream) {
+  WG_REQUIRE(s && LU_dev && b_dev, "wg_solve: NULL argument");
+  return wg::lu_solve(s->plan, LU_dev, lda, b_dev, (cudaStream_t)stream);
+}
+
+int wg_info(wg_solver* s, void* stream, int* info_host) {
+  WG_REQUIRE(s && info_host, "wg_info: NULL argument");
+  WG_CUDA(cudaMemcpyAsync(info_host, s->info, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  WG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return WG_OK;
+}
+
+// apply the (up to three) axis matrices of one stage; result always lands in `out`
+static int apply_stage(wg_solver* s, int stage, const double* in, double* out, cudaStream_t st) {
+  const wg::BzDims& d = s->d;
+  const double* const* m = s->mats + 3 * stage;
+  int cnt = (m[0] != nullptr) + (m[1] != nullptr) + (m[2] != nullptr);
+  if (cnt == 0) {
+    if (in != out) WG_CUDA(cudaMemcpyAsync(out, in, sizeof(double) * d.n, cudaMemcpyDeviceToDevice, st));
+    return WG_OK;
+  }
+  const double* cur = in;
+  double* tmp[2] = {s->bufA, s->bufB};
+  int ti = 0;
+  for (int ax = 0; ax < 3; ++ax) {
+    if (!m[ax]) continue;
+    --cnt;
+    double* dst = (cnt == 0) ? out : tmp[ti];
+    if (dst == cur) {  // never alias (only possible when out == in)
+      wg_set_error("apply_stage: in-place basis change needs distinct buffers");
+      return WG_ERR_ARG;
+    }
+    int rc;
+    if (ax == 0)
+      rc = wg::bz_apply_axis(cur, dst, m[ax], d.P, d.M1, d.q, st);
+    else if (ax == 1)
+      rc = wg::bz_apply_axis(cur, dst, m[ax], d.P * d.M1, d.N1, d.N1, st);
+    else
+      rc = wg::bz_apply_axis(cur, dst, m[ax], d.P * d.M1 * d.N1, d.N1, 1, st);
+    if (rc) return rc;
+    cur = dst;
+    ti ^= 1;
+  }
+  return WG_OK;
+}
+
+int wg_change_basis(wg_solver* s, int stage, const double* in_dev, double* out_dev, void* stream) {
+  WG_REQUIRE(s && in_dev && out_dev && stage >= 0 && stage < 3 && in_dev != out_dev,
+             "wg_change_basis: bad argument");
+  return apply_stage(s, stage, in_dev, out_dev, (cudaStream_t)stream);
+}
+
+int wg_spectra(wg_solver* s, const double* deltaF_dev, double* spectra_dev, void* stream) {
+  WG_REQUIRE(s && deltaF_dev && spectra_dev, "wg_spectra: NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = apply_stage(s, 0, deltaF_dev, s->cheb, st);
+  if (rc) return rc;
+  return wg::bz_spectra(s->d, s->cheb, spectra_dev, st);
+}
+
+int wg_moments(wg_solver* s, const double* deltaF_dev, const double* profiles_dev, int keepM, int keepPz,
+               int keepPp, int roundtrip, double* deltaF_out_dev, double* deltas_dev, double* err_dev,
+               void* stream) {
+  WG_REQUIRE(s && deltaF_dev && profiles_dev && deltaF_out_dev && deltas_dev && err_dev,
+             "wg_moments: NULL argument");
+  WG_REQUIRE(keepM >= 1 && keepM <= s->d.M1 && keepPz >= 1 && keepPz <= s->d.N1 && keepPp >= 1 &&
+                 keepPp <= s->d.N1,
+             "wg_moments: keep counts out of range");
+  WG_REQUIRE(s->haveGrid, "wg_moments: grid not set");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = wg::bz_truncate(s->d, s->cheb, keepM, keepPz, keepPp, err_dev, st);
+  if (rc) return rc;
+  if (roundtrip) {
+    rc = apply_stage(s, 1, s->cheb, deltaF_out_dev, st);
+    if (rc) return rc;
+  } else if (deltaF_out_dev != deltaF_dev) {
+    WG_CUDA(cudaMemcpyAsync(deltaF_out_dev, deltaF_dev, sizeof(double) * s->d.n, cudaMemcpyDeviceToDevice, st));
+  }
+  // cardinal-basis values; s->cheb is free again after the round trip, use it as the target
+  double* card = s->cheb;
+  rc = apply_stage(s, 2, deltaF_out_dev, card, st);
+  if (rc) return rc;
+  return wg::bz_moments(s->d, s->st, card, profiles_dev, deltas_dev, st);
+}
+
+int wg_collision_apply(wg_solver* s, const double* x_dev, double* y_dev, void* stream) {
+  WG_REQUIRE(s && x_dev && y_dev, "wg_collision_apply: NULL argument");
+  if (!s->assembled) {
+    wg_set_error("wg_collision_apply: call wg_assemble first (needs T^2 of the current background)");
+    return WG_ERR_STATE;
+  }
+  return wg::bz_collision_matvec(s->d, s->st, s->cT2, x_dev, y_dev, (cudaStream_t)stream);
+}
+
+int wg_lu_create(int n, int device, wg_lu** out) {
+  WG_REQUIRE(out && n > 0, "wg_lu_create: bad argument");
+  int rc = require_device(device);
+  if (rc) return rc;
+  wg_lu* p = new wg_lu();
+  p->device = device;
+  rc = wg::lu_plan_create(n, &p->plan);
+  if (rc) {
+    delete p;
+    return rc;
+  }
+  *out = p;
+  return WG_OK;
+}
+
+int wg_lu_destroy(wg_lu* p) {
+  if (!p) return WG_OK;
+  cudaSetDevice(p->device);
+  wg::lu_plan_destroy(p->plan);
+  delete p;
+  return WG_OK;
+}
+
+int wg_lu_factor(wg_lu* p, double* A_dev, long long lda, int* ipiv_dev, int* info_dev, void* stream) {
+  WG_REQUIRE(p, "wg_lu_factor: NULL plan");
+  return wg::lu_factor(p->plan, A_dev, lda, ipiv_dev, info_dev, (cudaStream_t)stream);
+}
+
+int wg_lu_solve(wg_lu* p, const double* LU_dev, long long lda, double* b_dev, void* stream) {
+  WG_REQUIRE(p, "wg_lu_solve: NULL plan");
+  return wg::lu_solve(p->plan, LU_dev, lda, b_dev, (cudaStream_t)stream);
+}
+
+int wg_dgemm_sub(double* C_dev, const double* A_dev, const double* B_dev, int M, int N, int K, long long ldc,
+                 long long lda, long long ldb, void* stream) {
+  WG_REQUIRE(C_dev && A_dev && B_dev && M >= 0 && N >= 0 && K >= 0, "wg_dgemm_sub: bad argument");
+  return wg::dgemm_sub(C_dev, A_dev, B_dev, M, N, K, ldc, lda, ldb, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,19 @@
+// Internal (C++) declarations shared by the wallgo_b200 translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace wg {
+
+// C[MxN] -= A[MxK] * B[KxN], row-major, FP64 tensor cores (wg_gemm.cu)
+int dgemm_sub(double* C, const double* A, const double* B, int M, int N, int K, long long ldc,
+              long long lda, long long ldb, cudaStream_t st);
+
+// Blocked LU with partial pivoting (wg_lu.cu)
+struct LuPlan;
+int lu_plan_create(int n, LuPlan** out);
+void lu_plan_destroy(LuPlan* p);
+int lu_factor(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStream_t st);
+int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st);
+void lu_set_tuning(int nb, int use_graph);
+
+}  // namespace wg

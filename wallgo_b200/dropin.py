@@ -1,0 +1,61 @@
+"""Drop-in for `WallGo.BoltzmannSolver` (only importable where WallGo itself is installed).
+
+    import WallGo, wallgo_b200.dropin as b200
+    b200.install()            # WallGoManager.setupWallSolver now builds the B200 solver
+    manager = WallGo.WallGoManager(); ...; manager.solveWall(settings)
+
+`install()` rebinds the name `BoltzmannSolver` in `WallGo` and `WallGo.manager`
+(the single construction site, manager.py:605-611).  The class is a real subclass of the
+reference class, so `isinstance` (equationOfMotion.py:106), the shared-grid assertion (:110-112)
+and `copy.deepcopy` + attribute rewrites in `getBoltzmannFiniteDifference` (:2135-2143) keep working,
+and results are WallGo's own `BoltzmannResults` / `BoltzmannDeltas` / `Polynomial`.
+"""
+from __future__ import annotations
+
+from .boltzmann import BoltzmannSolverB200Mixin
+
+_cached = None
+
+
+def makeDropInClass():
+    """Returns the subclass of WallGo.BoltzmannSolver backed by the B200 engine."""
+    global _cached
+    if _cached is not None:
+        return _cached
+    import WallGo  # pylint: disable=import-outside-toplevel
+    from WallGo.boltzmann import BoltzmannSolver as _RefSolver, ETruncationOption
+    from WallGo.collisionArray import CollisionArray
+
+    class _WallGoTypes:
+        Polynomial = WallGo.Polynomial
+        BoltzmannDeltas = WallGo.BoltzmannDeltas
+        BoltzmannResults = WallGo.BoltzmannResults
+
+    class B200BoltzmannSolver(BoltzmannSolverB200Mixin, _RefSolver):
+        """WallGo.BoltzmannSolver with every numerical step on a B200."""
+
+        _types = _WallGoTypes
+
+        def __init__(self, grid, basisM="Cardinal", basisN="Chebyshev", derivatives="Spectral",
+                     collisionMultiplier=1.0, truncationOption=ETruncationOption.AUTO, device=None):
+            self._initB200(grid, basisM, basisN, derivatives, collisionMultiplier, truncationOption, device)
+
+        def loadCollisions(self, directoryPath):
+            """File ingest stays the reference's own host code (collisionArray.py:178-354); the
+            tensor it returns is uploaded to the GPU at the next solve."""
+            self.collisionArray = CollisionArray.newFromDirectory(
+                directoryPath, self.grid, self.basisN, self.offEqParticles)
+
+    _cached = B200BoltzmannSolver
+    return _cached
+
+
+def install():
+    """Make WallGoManager construct the B200 solver (manager.py:605-611)."""
+    import WallGo  # pylint: disable=import-outside-toplevel
+    import WallGo.manager as _manager
+
+    cls = makeDropInClass()
+    _manager.BoltzmannSolver = cls
+    WallGo.BoltzmannSolver = cls
+    return cls

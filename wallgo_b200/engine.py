@@ -1,0 +1,195 @@
+"""Device engine: owns the torch tensors and drives libwallgo_b200.so through ctypes.
+
+PyTorch is used for device memory, pinned staging buffers and streams only; all
+arithmetic happens in the hand-written CUDA kernels behind the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, host_ptr
+
+
+def default_device() -> int:
+    """One process per GPU: LOCAL_RANK selects the device under torchrun."""
+    return int(os.environ.get("LOCAL_RANK", "0"))
+
+
+class BoltzmannEngine:
+    """One Boltzmann system (P species, M x N grid) resident on one B200."""
+
+    def __init__(self, P: int, M: int, N: int, device: int | None = None):
+        import torch  # imported lazily so that CPU-only tooling can import the package
+
+        if not torch.cuda.is_available():
+            raise _lib.WallGoB200Error(
+                "wallgo_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.torch = torch
+        self.lib = _lib.load()
+        self.P, self.M, self.N = int(P), int(M), int(N)
+        self.device = default_device() if device is None else int(device)
+        self.dev = torch.device("cuda", self.device)
+        h = C.c_void_p()
+        check(self.lib.wg_create(self.P, self.M, self.N, self.device, C.byref(h)), "wg_create")
+        self.h = h
+        n, q = C.c_int(), C.c_int()
+        check(self.lib.wg_dims(self.h, C.byref(n), C.byref(q)), "wg_dims")
+        self.n, self.q = n.value, q.value
+        self.M1, self.N1 = self.M - 1, self.N - 1
+        self.nprof = (2 + self.P) * (self.M + 1) + self.M1
+        f64 = torch.float64
+        self.A = None  # n x n operator / LU factors, allocated on first use
+        self.S = torch.empty(self.n, dtype=f64, device=self.dev)          # source -> deltaF (in place)
+        self.prof = torch.empty(self.nprof, dtype=f64, device=self.dev)
+        self.prof_host = torch.empty(self.nprof, dtype=f64).pin_memory()
+        self.nspec = self.M1 + 2 * self.N1
+        self.spectra = torch.empty(self.nspec, dtype=f64, device=self.dev)
+        self.spectra_host = torch.empty(self.nspec, dtype=f64).pin_memory()
+        # [ deltaF_out (n) | deltas (4 P M1) | err (4 P) ] contiguous so one D2H copy returns everything
+        self.nout = self.n + 4 * self.P * self.M1 + 4 * self.P
+        self.out = torch.empty(self.nout, dtype=f64, device=self.dev)
+        self.out_host = torch.empty(self.nout, dtype=f64).pin_memory()
+        self.dF_in = torch.empty(self.n, dtype=f64, device=self.dev)
+        self.launches = 0  # kernels launched through this engine (rough, for bench accounting)
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.wg_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def _ensure_A(self):
+        if self.A is None:
+            self.A = self.torch.empty((self.n, self.n), dtype=self.torch.float64, device=self.dev)
+        return self.A
+
+    # ------------------------------------------------------------------ static data
+    def set_grid(self, chi, rz, rp, pz, pp, dpzdrz, dppdrp):
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (chi, rz, rp, pz, pp, dpzdrz, dppdrp)]
+        assert arrs[0].size == self.M1 and all(a.size == self.N1 for a in arrs[1:])
+        check(self.lib.wg_set_grid(self.h, *[host_ptr(a) for a in arrs]), "wg_set_grid")
+
+    def set_statistics(self, stat):
+        s = np.ascontiguousarray(stat, dtype=np.float64)
+        assert s.size == self.P
+        check(self.lib.wg_set_statistics(self.h, host_ptr(s)), "wg_set_statistics")
+
+    def build_basis(self):
+        check(self.lib.wg_build_basis(self.h), "wg_build_basis")
+
+    def set_tables(self, Tchi, Dchi, DchiFull, Trz, Drz, Trp):
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (Tchi, Dchi, DchiFull, Trz, Drz, Trp)]
+        check(self.lib.wg_set_tables(self.h, *[host_ptr(a) for a in arrs]), "wg_set_tables")
+
+    def get_tables(self):
+        M1, N1, L = self.M1, self.N1, self.M + 1
+        out = [np.empty((M1, M1)), np.empty((M1, M1)), np.empty((L, L)), np.empty((N1, N1)),
+               np.empty((N1, N1)), np.empty((N1, N1))]
+        check(self.lib.wg_get_tables(self.h, *[host_ptr(a) for a in out]), "wg_get_tables")
+        return dict(zip(("Tchi", "Dchi", "DchiFull", "Trz", "Drz", "Trp"), out))
+
+    def set_transforms(self, mats):
+        """mats: 9 entries (stage-major: toChebyshev, fromChebyshev, toCardinal; axis z, pz, pp) or None."""
+        keep = [None if m is None else np.ascontiguousarray(m, dtype=np.float64) for m in mats]
+        arr = (C.POINTER(C.c_double) * 9)()
+        for i, m in enumerate(keep):
+            if m is not None:
+                size = self.M1 if i % 3 == 0 else self.N1
+                assert m.shape == (size, size)
+                arr[i] = host_ptr(m)
+        check(self.lib.wg_set_transforms(self.h, arr), "wg_set_transforms")
+
+    def set_collision(self, coll):
+        c = np.ascontiguousarray(coll, dtype=np.float64)
+        assert c.size == (self.P * self.q) ** 2, "collision tensor must be (P,N-1,N-1,P,N-1,N-1)"
+        check(self.lib.wg_set_collision(self.h, C.c_void_p(c.ctypes.data), 0), "wg_set_collision")
+
+    # ------------------------------------------------------------------ per solve
+    def upload_profiles(self, T, v, msq, dxidchi):
+        """Host -> device copy of the O(P*M) background numbers (one pinned buffer, one copy)."""
+        L = self.M + 1
+        ph = self.prof_host.numpy()
+        ph[0:L] = T
+        ph[L:2 * L] = v
+        ph[2 * L:(2 + self.P) * L] = np.asarray(msq, dtype=np.float64).reshape(-1)
+        ph[(2 + self.P) * L:] = dxidchi
+        self.prof.copy_(self.prof_host, non_blocking=True)
+
+    def assemble(self, vw: float, collisionMultiplier: float = 1.0, parts: int = 3, A=None):
+        A = self._ensure_A() if A is None else A
+        check(self.lib.wg_assemble(self.h, self.prof.data_ptr(), float(vw), float(collisionMultiplier),
+                                   int(parts), A.data_ptr(), A.stride(0), self.S.data_ptr(), self._stream()),
+              "wg_assemble")
+        return A
+
+    def factor(self):
+        A = self._ensure_A()
+        check(self.lib.wg_factor(self.h, A.data_ptr(), A.stride(0), self._stream()), "wg_factor")
+
+    def solve(self, b=None):
+        """Triangular solves with the current factors; b (device, n) is overwritten by the solution."""
+        b = self.S if b is None else b
+        A = self._ensure_A()
+        check(self.lib.wg_solve(self.h, A.data_ptr(), A.stride(0), b.data_ptr(), self._stream()), "wg_solve")
+        return b
+
+    def info(self) -> int:
+        v = C.c_int(0)
+        check(self.lib.wg_info(self.h, self._stream(), C.byref(v)), "wg_info")
+        return v.value
+
+    def spectra_async(self, dF):
+        check(self.lib.wg_spectra(self.h, dF.data_ptr(), self.spectra.data_ptr(), self._stream()), "wg_spectra")
+
+    def spectra_to_host(self):
+        self.spectra_host.copy_(self.spectra, non_blocking=True)
+        self.torch.cuda.current_stream(self.dev).synchronize()
+        return self.spectra_host.numpy().copy()
+
+    def moments_async(self, dF, keep, roundtrip: bool):
+        n, pm = self.n, 4 * self.P * self.M1
+        o = self.out
+        check(self.lib.wg_moments(self.h, dF.data_ptr(), self.prof.data_ptr(), int(keep[0]), int(keep[1]),
+                                  int(keep[2]), 1 if roundtrip else 0, o.data_ptr(),
+                                  o[n:].data_ptr(), o[n + pm:].data_ptr(), self._stream()), "wg_moments")
+
+    def results_to_host(self):
+        """One device -> host copy: (deltaF (P,M-1,N-1,N-1), Deltas (4,P,M-1), err (P,4))."""
+        self.out_host.copy_(self.out, non_blocking=True)
+        self.torch.cuda.current_stream(self.dev).synchronize()
+        h = self.out_host.numpy()
+        n, pm = self.n, 4 * self.P * self.M1
+        dF = h[:n].reshape(self.P, self.M1, self.N1, self.N1).copy()
+        deltas = h[n:n + pm].reshape(4, self.P, self.M1).copy()
+        err = h[n + pm:].reshape(self.P, 4).copy()
+        return dF, deltas, err
+
+    def collision_apply(self, x, y):
+        check(self.lib.wg_collision_apply(self.h, x.data_ptr(), y.data_ptr(), self._stream()),
+              "wg_collision_apply")
+
+    def change_basis(self, stage: int, src, dst):
+        check(self.lib.wg_change_basis(self.h, int(stage), src.data_ptr(), dst.data_ptr(), self._stream()),
+              "wg_change_basis")
+
+    # ------------------------------------------------------------------ fused device step (bench)
+    def step_device(self, vw: float, collisionMultiplier: float, keep, roundtrip: bool = True):
+        """assemble -> LU -> solve -> spectra -> truncate/moments, inputs already in HBM, no host sync."""
+        self.assemble(vw, collisionMultiplier)
+        self.factor()
+        self.solve()
+        self.spectra_async(self.S)
+        self.moments_async(self.S, keep, roundtrip)
