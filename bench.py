@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""Benchmark of the Boltzmann hot path (BASELINE.json metric: Boltzmann solves/s, assemble+LU+moments).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2a]
+
+One "step" = one full pass of the hot path over one synthetic system: operator assembly, dense LU
+factor-and-solve, spectral truncation and the four moment integrals.  Default workload is
+BASELINE.json configs[1] (single fermion, M=40, N=21, n=15600, operator 1.95 GB >> 126 MB L2, so
+every step streams from HBM; no explicit L2 flush is needed).  Multi-GPU: independent systems
+(scan points) are sharded one process per GPU, weak scaling, one NCCL all_gather of the moments.
+
+Prints ONE JSON line on rank 0 (contract in the task statement).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {  # BASELINE.json configs -> (P, M, N)
+    "cfg1": (1, 20, 11), "cfg2a": (1, 40, 21), "cfg2b": (2, 40, 21), "cfg3": (3, 30, 11), "cfg4": (4, 30, 11),
+}
+METRIC = "Boltzmann solves/sec (assemble+LU+moments)"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.lines = gpu, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], None, [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_inputs(P, M, N, nsys, rank):
+    """Deterministic synthetic systems; every step is a different wall velocity (a scan point)."""
+    from wallgo_b200 import synthetic
+
+    grid = synthetic.makeGrid(M, N)
+    particles = synthetic.makeParticles(P)
+    coll = synthetic.makeCollision(grid, particles)
+    bgs = [synthetic.makeBackground(grid, velocityMid=-0.3 - 0.4 * ((i + rank * nsys) % 97) / 97.0)
+           for i in range(nsys)]
+    return grid, particles, coll, bgs
+
+
+def cpu_port_one_solve(grid, particles, coll, bg):
+    """The oracle (NumPy/LAPACK port of the reference path) on the host cores: one full solve."""
+    from oracle import boltzmann_oracle as bo
+    from copy import deepcopy
+
+    b = deepcopy(bg)
+    b.boostToPlasmaFrame()
+    tab = bo.build_tables(grid.M, grid.N)
+    pb = bo.Problem(tab=tab, xi_dxidchi=grid.dxidchi, pz=grid.pzValues, pp=grid.ppValues, dpzdrz=grid.dpzdrz,
+                    dppdrp=grid.dppdrp, T=b.temperatureProfile, v=b.velocityProfile,
+                    msq=np.array([p.msqVacuum(b.fieldProfiles) for p in particles]), vw=float(b.velocityWall),
+                    statistics=np.array([-1.0 if p.statistics == "Fermion" else 1.0 for p in particles]),
+                    collision=np.asarray(coll[...]), collisionMultiplier=1.0)
+    t0 = time.perf_counter()
+    op, src = bo.assemble(pb)
+    t1 = time.perf_counter()
+    dF = np.linalg.solve(op, src).reshape(len(particles), grid.M - 1, grid.N - 1, grid.N - 1)
+    t2 = time.perf_counter()
+    del op
+    out = bo.get_deltas(pb, dF, "AUTO")
+    t3 = time.perf_counter()
+    return dict(assemble_s=t1 - t0, dgesv_s=t2 - t1, moments_s=t3 - t2, total_s=t3 - t0), out
+
+
+def blas_info():
+    try:
+        from threadpoolctl import threadpool_info
+        return ";".join(f"{d.get('internal_api')} {d.get('version')} threads={d.get('num_threads')}"
+                        for d in threadpool_info())
+    except Exception:
+        return "unknown"
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    P, M, N = WORKLOADS[a.workload]
+    grid, particles, coll, bgs = build_inputs(P, M, N, a.steps + a.warmup, 0)
+    budget = float(a.ref_budget_s)
+    for i in range(min(a.warmup, 1)):
+        cpu_port_one_solve(grid, particles, coll, bgs[i])
+    t0 = time.perf_counter()
+    done, parts = 0, []
+    for i in range(a.steps):
+        t, _ = cpu_port_one_solve(grid, particles, coll, bgs[a.warmup + i])
+        parts.append(t)
+        done += 1
+        if time.perf_counter() - t0 > budget:
+            break
+    el = time.perf_counter() - t0
+    val = done / el
+    n = P * (M - 1) * (N - 1) ** 2
+    sample = (f"{done} of {a.steps} requested full solves (assemble+dgesv+moments) at P={P},M={M},N={N}, "
+              f"time budget {budget:.0f}s; NumPy {np.__version__}, BLAS {blas_info()}; "
+              f"mean assemble {np.mean([p['assemble_s'] for p in parts]):.2f}s dgesv "
+              f"{np.mean([p['dgesv_s'] for p in parts]):.2f}s")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "solves/s", "n_gpus": a.gpus,
+            "steps": done, "warmup": min(a.warmup, 1), "ms_per_step": 1e3 * el / done, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{a.workload}: P={P} M={M} N={N} n={n}, synthetic collision tensor",
+                       "note": "reference is pure Python and cannot travel to the GPU box; this arm runs the "
+                               "oracle port (NumPy broadcasting + LAPACK dgesv) of the same path"},
+            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+
+    import wallgo_b200 as wb
+    from wallgo_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.load()
+    lib.wg_set_tuning(a.nb, a.graph)
+    P, M, N = WORKLOADS[a.workload]
+    K, W = a.steps, a.warmup
+    nsys = K + W
+    grid, particles, coll, bgs = build_inputs(P, M, N, nsys, rank)
+    solver = wb.BoltzmannSolver(grid, device=local)
+    solver.updateParticleList(particles)
+    solver.setCollisionArray(coll)
+    solver.setBackground(bgs[0])
+    eng = solver._getEngine()
+    n, nprof = eng.n, eng.nprof
+    dev = eng.dev
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    # ---- measured FP64 GEMM peak (cuBLAS through torch) = denominator of the LU roofline
+    x = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    y = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    torch.matmul(x, y)
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(x, y)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    fp64_peak = 2 * 8192.0**3 / best / 1e9  # TFLOP/s
+    del x, y
+    torch.cuda.empty_cache()
+
+    # ---- device-resident inputs: every step's background already in HBM
+    profs_h = np.empty((nsys, nprof))
+    vws = []
+    for i, bg in enumerate(bgs):
+        solver.setBackground(bg)
+        b = solver.background
+        L = M + 1
+        profs_h[i, :L] = b.temperatureProfile
+        profs_h[i, L:2 * L] = b.velocityProfile
+        profs_h[i, 2 * L:(2 + P) * L] = solver._msq(b.fieldProfiles).reshape(-1)
+        profs_h[i, (2 + P) * L:] = grid.dxidchi
+        vws.append(float(b.velocityWall))
+    profs = torch.from_numpy(profs_h).to(dev)
+    keep = (M - 1, N - 1, N - 1)
+    own_prof = eng.prof
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(K)]
+
+    def step(i, rec=None):
+        eng.prof = profs[i]
+        if rec:
+            rec[0].record()
+        eng.assemble(vws[i], 1.0)
+        if rec:
+            rec[1].record()
+        eng.factor()
+        if rec:
+            rec[2].record()
+        eng.solve()
+        if rec:
+            rec[3].record()
+        eng.spectra_async(eng.S)
+        eng.moments_async(eng.S, keep, True)
+        if rec:
+            rec[4].record()
+
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+    pm = 4 * P * (M - 1)
+    gathered = torch.empty(world * pm, dtype=torch.float64, device=dev) if world > 1 else None
+    sampler = ClockSampler(local)
+    barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    l0 = lib.wg_launch_count()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(K):
+        step(W + i, evs[i])
+    if world > 1:  # the only collective on the path: gather the moments of the last scan point
+        dist.all_gather_into_tensor(gathered, eng.out[n:n + pm].contiguous())
+    end.record()
+    torch.cuda.synchronize()
+    launches = lib.wg_launch_count() - l0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = start.elapsed_time(end)
+    info = eng.info()
+    assert info == 0, f"singular operator in the benchmark (info={info})"
+    stage = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(4)] for e in evs]).mean(axis=0)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * K / (ms / 1e3)
+
+    # ---- end to end through the public class, host buffers in and out
+    eng.prof = own_prof
+    for i in range(min(W, 2)):
+        solver.setBackground(bgs[i])
+        solver.getDeltas()
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(K):
+        solver.setBackground(bgs[W + i])
+        res = solver.getDeltas()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = world * K / e2e_s
+    assert np.all(np.isfinite(res.Deltas.Delta00.coefficients))
+
+    if rank == 0:
+        hbm_peak, hbm_src = measured_peaks()
+        lu_flops = 2.0 / 3.0 * float(n) ** 3
+        lu_tf = lu_flops / (stage[1] * 1e-3) / 1e12
+        asm_gbs = (8.0 * n * n + 8.0 * n) / (stage[0] * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{a.workload}: P={P} M={M} N={N} n={n} (BASELINE configs[1] when cfg2a), "
+                                   "one independent system (scan point) per step per GPU",
+                       "l2": "operator 8n^2 bytes >> 126 MB L2: inputs larger than L2, no flush needed"
+                             if 8.0 * n * n > 4 * 126e6 else "small operator: L2-resident between stages",
+                       "lu": {"nb": a.nb, "cuda_graph": bool(a.graph)},
+                       "parallelism": f"{world} x independent systems, no collective inside a solve"},
+            "stages_ms": {"assemble": stage[0], "lu_factor": stage[1], "tri_solve": stage[2], "spectra_moments": stage[3]},
+            "roofline": {"kernel": "blocked LU (DMMA GEMM trailing update dominates)", "bound": "tensor",
+                         "achieved": lu_tf, "peak": fp64_peak / 1e3, "unit": "TFLOP/s", "frac": lu_tf / (fp64_peak / 1e3),
+                         "traffic": None,
+                         "peak_source": "measured in this run: torch.matmul (cuBLAS DGEMM) fp64 8192^3 best of 5; "
+                                        "MEASURED_PEAKS.json has no FP64 entry",
+                         "algorithmic": "2/3 n^3 flops per factorisation / mean CUDA-event time of wg_factor"},
+            "roofline_assembly": {"kernel": "wg_assemble_kernel", "bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak,
+                                  "unit": "GB/s", "frac": asm_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                                  "algorithmic": "8n^2+8n bytes written per solve / mean CUDA-event time of wg_assemble"},
+            "e2e": {"value": e2e, "unit": "solves/s", "h2d_bytes_per_step": int(nprof * 8),
+                    "d2h_bytes_per_step": int((eng.nspec + eng.nout) * 8 + 4)},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            try:
+                t, _ = cpu_port_one_solve(grid, particles, coll, bgs[W])
+                line["cpu_baseline"] = {
+                    "value": 1.0 / t["total_s"], "unit": "solves/s", "cores": os.cpu_count(), "kind": "port",
+                    "sample": f"1 full solve of the same workload (assemble {t['assemble_s']:.2f}s + LAPACK dgesv "
+                              f"{t['dgesv_s']:.2f}s + moments {t['moments_s']:.2f}s), NumPy {np.__version__}, "
+                              f"BLAS {blas_info()}"}
+            except MemoryError:
+                line["cpu_baseline"] = {"value": None, "unit": "solves/s", "cores": os.cpu_count(), "kind": "port",
+                                        "sample": "skipped: operator does not fit host RAM"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2a", choices=sorted(WORKLOADS))
+    ap.add_argument("--nb", type=int, default=256)
+    ap.add_argument("--graph", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0)
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()
