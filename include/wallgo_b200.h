@@ -42,6 +42,8 @@ const char* wg_last_error(void);
 long long wg_launch_count(void);
 /* nb: top-level LU panel width (multiple of 16, 32..256); use_graph: replay the factorisation as a CUDA graph */
 int wg_set_tuning(int nb, int use_graph);
+/* on: factor panel k+1 on a high-priority stream while the trailing update of panel k runs (default 1) */
+int wg_set_lookahead(int on);
 
 /* ---- lifecycle : BoltzmannSolver.__init__ + updateParticleList (boltzmann.py:52-139) */
 int wg_create(int P, int M, int N, int device, wg_solver** out);

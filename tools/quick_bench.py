@@ -37,9 +37,11 @@ def main():
     ap.add_argument("--graph", type=int, default=0)
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--dgemm", type=int, default=1)
+    ap.add_argument("--look", type=int, default=1)
     a = ap.parse_args()
     lib = _lib.load()
     lib.wg_set_tuning(a.nb, a.graph)
+    lib.wg_set_lookahead(a.look)
     if a.dgemm:
         x = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
         y = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
@@ -57,7 +59,7 @@ def main():
     eng = s._getEngine()
     s._uploadBackground(eng)
     n = eng.n
-    print(f"P={a.P} M={a.M} N={a.N} n={n} nb={a.nb} graph={a.graph} setup {time.perf_counter() - t0:.2f}s")
+    print(f"P={a.P} M={a.M} N={a.N} n={n} nb={a.nb} graph={a.graph} look={a.look} setup {time.perf_counter() - t0:.2f}s")
     vw = float(s.background.velocityWall)
     eng.assemble(vw, 1.0)
     t_as = time_stage(lambda: eng.assemble(vw, 1.0), a.reps)

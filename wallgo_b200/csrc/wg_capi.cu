@@ -73,6 +73,20 @@ int wg_set_tuning(int nb, int use_graph) {
   wg::lu_set_tuning(nb, use_graph);
   return WG_OK;
 }
+int wg_debug_gemm_variant(int v) {
+  wg::gemm_set_variant(v);
+  return WG_OK;
+}
+int wg_set_lookahead(int on) {
+  wg::lu_set_lookahead(on);
+  return WG_OK;
+}
+
+/* developer probe (not part of the public header): clock64 phase stamps of one leaf panel */
+int wg_debug_leaf(long long* dev_buf, int c0) {
+  wg::lu_set_debug(dev_buf, c0);
+  return WG_OK;
+}
 
 int wg_create(int P, int M, int N, int device, wg_solver** out) {
   WG_REQUIRE(out != nullptr, "wg_create: out is NULL");

@@ -12,8 +12,8 @@
 
 namespace wg {
 
-template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES, bool VEC>
-__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
+template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES, bool VEC, int MINB = 1>
+__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
 dgemm_sub_kernel(double* __restrict__ C, const double* __restrict__ A, const double* __restrict__ B,
                  int M, int N, int K, long long ldc, long long lda, long long ldb) {
   constexpr int NT = WARPS_M * WARPS_N * 32;
@@ -143,14 +143,14 @@ dgemm_sub_kernel(double* __restrict__ C, const double* __restrict__ A, const dou
   }
 }
 
-template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES>
+template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES, int MINB = 1>
 static int launch_cfg(double* C, const double* A, const double* B, int M, int N, int K, long long ldc,
                       long long lda, long long ldb, bool vec, cudaStream_t st) {
   constexpr int NT = WARPS_M * WARPS_N * 32;
   constexpr size_t SMEM = (size_t)STAGES * (BM * (BK + 4) + BK * (BN + 4)) * sizeof(double);
   dim3 grid(wg_cdiv(N, BN), wg_cdiv(M, BM));
   if (vec) {
-    auto kern = dgemm_sub_kernel<BM, BN, BK, WARPS_M, WARPS_N, STAGES, true>;
+    auto kern = dgemm_sub_kernel<BM, BN, BK, WARPS_M, WARPS_N, STAGES, true, MINB>;
     static bool configured = false;
     if (!configured) {
       WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
@@ -158,7 +158,7 @@ static int launch_cfg(double* C, const double* A, const double* B, int M, int N,
     }
     kern<<<grid, NT, SMEM, st>>>(C, A, B, M, N, K, ldc, lda, ldb);
   } else {
-    auto kern = dgemm_sub_kernel<BM, BN, BK, WARPS_M, WARPS_N, STAGES, false>;
+    auto kern = dgemm_sub_kernel<BM, BN, BK, WARPS_M, WARPS_N, STAGES, false, MINB>;
     static bool configured = false;
     if (!configured) {
       WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
@@ -170,12 +170,17 @@ static int launch_cfg(double* C, const double* A, const double* B, int M, int N,
   return WG_OK;
 }
 
+static int g_gemm_variant = 1;  // 1: 128x64 tiles, two CTAs per SM (default); 0: 128x128, one CTA per SM
+void gemm_set_variant(int v) { g_gemm_variant = v; }
+
 int dgemm_sub(double* C, const double* A, const double* B, int M, int N, int K, long long ldc,
               long long lda, long long ldb, cudaStream_t st) {
   if (M <= 0 || N <= 0 || K <= 0) return WG_OK;
   const bool vec = ((ldc | lda | ldb) % 2 == 0) && (N % 2 == 0) && (K % 2 == 0) &&
                    ((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(A) |
                      reinterpret_cast<uintptr_t>(B)) % 16 == 0);
+  if (N > 64 && g_gemm_variant == 1) return launch_cfg<128, 64, 16, 2, 2, 3, 2>(C, A, B, M, N, K, ldc, lda, ldb, vec, st);
+  if (N > 64 && g_gemm_variant == 2) return launch_cfg<128, 128, 32, 2, 4, 3>(C, A, B, M, N, K, ldc, lda, ldb, vec, st);
   if (N > 64) return launch_cfg<128, 128, 16, 2, 4, 4>(C, A, B, M, N, K, ldc, lda, ldb, vec, st);
   if (N > 32) return launch_cfg<128, 64, 16, 4, 2, 4>(C, A, B, M, N, K, ldc, lda, ldb, vec, st);
   return launch_cfg<128, 32, 16, 8, 1, 4>(C, A, B, M, N, K, ldc, lda, ldb, vec, st);

@@ -8,6 +8,8 @@ namespace wg {
 int dgemm_sub(double* C, const double* A, const double* B, int M, int N, int K, long long ldc,
               long long lda, long long ldb, cudaStream_t st);
 
+void gemm_set_variant(int v);
+
 // Blocked LU with partial pivoting (wg_lu.cu)
 struct LuPlan;
 int lu_plan_create(int n, LuPlan** out);
@@ -15,5 +17,7 @@ void lu_plan_destroy(LuPlan* p);
 int lu_factor(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStream_t st);
 int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st);
 void lu_set_tuning(int nb, int use_graph);
+void lu_set_debug(long long* dev_buf, int c0);
+void lu_set_lookahead(int on);
 
 }  // namespace wg

@@ -33,12 +33,20 @@ constexpr int MAXCL = 16;     // largest cluster
 constexpr int MAXEXT = 248;   // widest "rest of the panel" a leaf has to move (NB - 8)
 constexpr int MAXMOVE = 32;   // most rows a leaf can move per CTA (2 * 16)
 
+static long long* g_dbg_buf = nullptr;  // developer probe: timestamps of the leaf starting at column g_dbg_c0
+static int g_dbg_c0 = -1;
+void lu_set_debug(long long* buf, int c0) {
+  g_dbg_buf = buf;
+  g_dbg_c0 = c0;
+}
 static int g_nb = 256;
 static int g_use_graph = 0;
+static int g_lookahead = 1;
 void lu_set_tuning(int nb, int use_graph) {
   if (nb >= 32 && nb <= 256 && nb % 16 == 0) g_nb = nb;
   g_use_graph = use_graph;
 }
+void lu_set_lookahead(int on) { g_lookahead = on; }
 
 struct PanelArgs {
   double* A;
@@ -51,28 +59,60 @@ struct PanelArgs {
   int* grpSrcTop;  // [n] : row (position at leaf start) that ends at position c0+i
   int* grpBDst;    // [n] : final position of the row that started at c0+i, or -1 if it stayed in the top w
   int vec;
+  long long* dbg;  // optional phase timestamps (developer probe), may be nullptr
 };
 
-__device__ __forceinline__ void argmax_redux(long long key, int pos, long long& mkey, int& mpos) {
+// Lane holding the maximum of (key descending, pos ascending) over the lanes with valid != 0.
+// Fast path: one REDUX on the high word of the key (sign, exponent, top mantissa bits) is almost
+// always decisive; exact ties fall back to the full 64-bit key and then to the smallest position
+// (LAPACK idamax picks the first maximal entry).
+__device__ __forceinline__ int argmax_lane(long long key, int pos, bool valid) {
   const unsigned full = 0xffffffffu;
-  const int hi = (int)(key >> 32);
-  const unsigned lo = (unsigned)key;
+  const int hi = valid ? (int)(key >> 32) : INT_MIN;
   const int mhi = __reduce_max_sync(full, hi);
-  const unsigned mlo = __reduce_max_sync(full, hi == mhi ? lo : 0u);
-  const bool cand = (hi == mhi) && (lo == mlo);
-  mpos = __reduce_min_sync(full, cand ? pos : INT_MAX);
-  mkey = ((long long)mhi << 32) | (long long)mlo;
+  unsigned cand = __ballot_sync(full, valid && hi == mhi);
+  if (__popc(cand) <= 1) return cand ? __ffs(cand) - 1 : 0;
+  const unsigned lo = (unsigned)key;
+  const bool c1 = valid && hi == mhi;
+  const unsigned mlo = __reduce_max_sync(full, c1 ? lo : 0u);
+  cand = __ballot_sync(full, c1 && lo == mlo);
+  if (__popc(cand) == 1) return __ffs(cand) - 1;
+  const bool c2 = c1 && lo == mlo;
+  const int mp = __reduce_min_sync(full, c2 ? pos : INT_MAX);
+  cand = __ballot_sync(full, c2 && pos == mp);
+  return __ffs(cand) - 1;
 }
 
+// remote 8-byte store that completes 8 transaction bytes on an mbarrier of the destination CTA
+__device__ __forceinline__ void st_async_u64(uint32_t remote_addr, unsigned long long v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];\n" ::"r"(remote_addr),
+               "l"(v), "r"(remote_bar)
+               : "memory");
+}
+
+template <int W>
+struct LeafSmem {
+  static constexpr int SL = W + 2;   // row values, key bits, position
+  static constexpr int TW = W + 1;   // padded tile row
+  double warpSlot[PNW][SL];          // per-warp pivot candidates of the current column
+  double cluSlot[2][MAXCL][SL];      // per-CTA candidates, double buffered by column parity
+  double moveBuf[MAXMOVE][MAXEXT];   // rest-of-panel data of rows that change position
+  double tile[PNW][32][TW];          // coalescing transposes for the load / store of the leaf block
+  unsigned long long bars[2];
+  int moveDst[MAXMOVE];
+  int moveCount;
+};
+
+// One leaf of the panel recursion: rows [c0, n) x columns [c0, c0+w), w <= W, factored by one cluster.
+// Thread t of CTA r keeps rows c0 + k*CL*PT + r*PT + t (k < R) in registers for the whole kernel.
 template <int W, int R>
 __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  constexpr int SL = W + 2;
-  double* warpSlot = reinterpret_cast<double*>(smraw);     // [PNW][SL]
-  double* cluSlot = warpSlot + PNW * SL;                   // [2][MAXCL][SL]
-  double* moveBuf = cluSlot + 2 * MAXCL * SL;              // [MAXMOVE][MAXEXT]
-  int* moveDst = reinterpret_cast<int*>(moveBuf + MAXMOVE * MAXEXT);  // [MAXMOVE]
-  int* moveCount = moveDst + MAXMOVE;
+  using SM = LeafSmem<W>;
+  SM& sm = *reinterpret_cast<SM*>(smraw);
+  constexpr int SL = SM::SL;
+  constexpr int LPR = W / 2;        // lanes per row when moving double2
+  constexpr int RPI = 32 / LPR;     // rows per warp instruction
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned rank = cluster_ctarank(), CL = cluster_nctarank();
@@ -80,39 +120,74 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
   const int m = p.n - c0;
   const long long lda = p.lda;
   double* __restrict__ A = p.A;
+  const int nLeft = c0 - p.pc0;
+  const int ext = nLeft + (p.pc1 - (c0 + w));
+  const bool dbg = p.dbg != nullptr && rank == 0 && tid == 0;
+  if (dbg) p.dbg[0] = clock64();
+
+  if (tid == 0) {
+    mbar_init(reinterpret_cast<uint64_t*>(&sm.bars[0]), 1);
+    mbar_init(reinterpret_cast<uint64_t*>(&sm.bars[1]), 1);
+    fence_mbar_init();
+    sm.moveCount = 0;
+  }
+  // the top w rows always leave or change position: stage their rest-of-panel columns right away
+  if (rank == 0 && warp < w && warp < m && ext > 0) {
+    const double* srow = A + (long long)(c0 + warp) * lda;
+    for (int e = lane; e < ext; e += 32) {
+      const int col = e < nLeft ? p.pc0 + e : c0 + w + (e - nLeft);
+      cp_async8(&sm.moveBuf[warp][e], srow + col, true);
+    }
+  }
+  cp_async_commit();
 
   double a[R][W];
   int pos[R], spos[R];
 #pragma unroll
   for (int k = 0; k < R; ++k) {
-    const int lr = k * (int)(CL * PT) + (int)rank * PT + tid;
+    const int wbase = k * (int)(CL * PT) + (int)rank * PT + warp * 32;  // first row of this warp's 32
+    const int lr = wbase + lane;
     const bool valid = lr < m;
     pos[k] = valid ? c0 + lr : -1;
     spos[k] = pos[k];
-    const double* src = A + (long long)(c0 + lr) * lda + c0;
     if (p.vec) {
+      __syncwarp();
 #pragma unroll
-      for (int c = 0; c < W; c += 2) {
+      for (int i = 0; i < LPR; ++i) {
+        const int r = i * RPI + lane / LPR, cp = lane % LPR;
         double2 v = make_double2(0.0, 0.0);
-        if (valid && c < w) v = *reinterpret_cast<const double2*>(src + c);
-        a[k][c] = v.x;
-        a[k][c + 1] = v.y;
+        if (wbase + r < m && 2 * cp < w)
+          v = *reinterpret_cast<const double2*>(A + (long long)(c0 + wbase + r) * lda + c0 + 2 * cp);
+        sm.tile[warp][r][2 * cp] = v.x;
+        sm.tile[warp][r][2 * cp + 1] = v.y;
       }
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < W; ++c) a[k][c] = sm.tile[warp][lane][c];
     } else {
+      const double* src = A + (long long)(c0 + lr) * lda + c0;
 #pragma unroll
       for (int c = 0; c < W; ++c) a[k][c] = (valid && c < w) ? src[c] : 0.0;
     }
   }
-  if (tid == 0) *moveCount = 0;
+  cluster_sync_all();  // mbarriers of every CTA initialised before anybody signals them
+  if (dbg) p.dbg[22] = clock64();
+
+  const uint32_t barAddr[2] = {smem_u32(&sm.bars[0]), smem_u32(&sm.bars[1])};
+  constexpr int NPUSH = 0;
+  (void)NPUSH;
 
 #pragma unroll
   for (int j = 0; j < W; ++j) {
     if (j < w) {  // uniform
       const int dj = c0 + j;
       const int par = j & 1;
-      // ---- thread-local and warp-level candidate
+      if (tid == 0) mbar_expect_tx(reinterpret_cast<uint64_t*>(&sm.bars[par]), (uint32_t)(CL * SL * 8));
+      const bool dbc = dbg && j == 8;
+      if (dbc) p.dbg[24] = clock64();
+      // ---- thread-local, then warp-level candidate
       long long bk = -1;
-      int bp = INT_MAX;
+      int bp = INT_MAX, kb = 0;
 #pragma unroll
       for (int k = 0; k < R; ++k) {
         const bool act = pos[k] >= dj;
@@ -121,59 +196,76 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
         if (key > bk || (key == bk && pp < bp)) {
           bk = key;
           bp = pp;
+          kb = k;
         }
       }
-      long long wkey;
-      int wpos;
-      argmax_redux(bk, bp, wkey, wpos);
-      {
-        const bool owner = (wpos == INT_MAX) ? (lane == 0) : (bk == wkey && bp == wpos);
-        if (owner) {
-          double* slot = warpSlot + warp * SL;
+      if (lane == argmax_lane(bk, bp, true)) {
+        double* slot = sm.warpSlot[warp];
 #pragma unroll
-          for (int k = 0; k < R; ++k)
-            if (pos[k] == wpos) {
+        for (int k = 0; k < R; ++k)
+          if (k == kb) {
 #pragma unroll
-              for (int c = 0; c < W; ++c) slot[c] = a[k][c];
-            }
-          reinterpret_cast<long long*>(slot)[W] = wkey;
-          reinterpret_cast<long long*>(slot)[W + 1] = (long long)wpos;
-        }
+            for (int c = 0; c < W; ++c) slot[c] = a[k][c];
+          }
+        reinterpret_cast<long long*>(slot)[W] = bk;
+        reinterpret_cast<long long*>(slot)[W + 1] = (long long)bp;
       }
+      if (dbc) p.dbg[25] = clock64();
       __syncthreads();
-      // ---- CTA-level winner (every warp recomputes it), pushed to every CTA of the cluster
-      {
-        const double* s = warpSlot + (lane & (PNW - 1)) * SL;
+      if (dbc) p.dbg[26] = clock64();
+      // ---- CTA-level winner, pushed to every CTA of the cluster (st.async completes their mbarrier)
+      if (warp * 32 < SL * (int)CL) {
+        const double* s = sm.warpSlot[lane & (PNW - 1)];
         const long long k2 = reinterpret_cast<const long long*>(s)[W];
         const int p2 = (int)reinterpret_cast<const long long*>(s)[W + 1];
-        long long ckey;
-        int cpos;
-        argmax_redux(k2, p2, ckey, cpos);
-        const unsigned bal = __ballot_sync(0xffffffffu, k2 == ckey && p2 == cpos);
-        const int ww = __ffs(bal) - 1;
-        const unsigned long long* srcw = reinterpret_cast<const unsigned long long*>(warpSlot + ww * SL);
-        const uint32_t base = smem_u32(cluSlot + (par * MAXCL + (int)rank) * SL);
-        for (int u = tid; u < SL * (int)CL; u += PT) {
-          const int dest = u / SL, e = u - dest * SL;
-          dsmem_st_u64(dsmem_map(base + 8u * e, dest), srcw[e]);
+        const int ww = argmax_lane(k2, p2, lane < PNW);
+        const unsigned long long* srcw = reinterpret_cast<const unsigned long long*>(sm.warpSlot[ww]);
+        const uint32_t base = smem_u32(&sm.cluSlot[par][rank][0]);
+        if (tid < SL * (int)CL) {
+          const int dest = tid / SL, e = tid - dest * SL;
+          st_async_u64(dsmem_map(base + 8u * e, dest), srcw[e], dsmem_map(barAddr[par], dest));
         }
       }
-      cluster_sync_all();
+      if (dbc) p.dbg[27] = clock64();
+      mbar_wait(reinterpret_cast<uint64_t*>(&sm.bars[par]), (uint32_t)((j >> 1) & 1));
+      if (dbc) p.dbg[28] = clock64();
       // ---- cluster-level winner = pivot row
-      long long mkey;
-      int mpos;
-      int wc;
+      const double* urow;
       {
-        const double* s = cluSlot + (par * MAXCL + (lane & ((int)CL - 1))) * SL;
+        const double* s = sm.cluSlot[par][lane & ((int)CL - 1)];
         const long long k3 = reinterpret_cast<const long long*>(s)[W];
         const int p3 = (int)reinterpret_cast<const long long*>(s)[W + 1];
-        argmax_redux(k3, p3, mkey, mpos);
-        const unsigned bal = __ballot_sync(0xffffffffu, k3 == mkey && p3 == mpos);
-        wc = __ffs(bal) - 1;
+        urow = sm.cluSlot[par][argmax_lane(k3, p3, lane < (int)CL)];
       }
-      const double* urow = cluSlot + (par * MAXCL + wc) * SL;
+      const long long mkey = reinterpret_cast<const long long*>(urow)[W];
+      const int mpos = (int)reinterpret_cast<const long long*>(urow)[W + 1];
       const bool sing = (mkey <= 0);
       const double rinv = sing ? 0.0 : 1.0 / urow[j];
+      if (dbc) p.dbg[29] = clock64() + (long long)(rinv == 123.456);
+      // the pivot row comes from below the top block: stage its rest-of-panel columns now
+      if (ext > 0) {
+        int sp = -1;
+#pragma unroll
+        for (int k = 0; k < R; ++k)
+          if (pos[k] == mpos && spos[k] >= c0 + w) sp = spos[k];
+        const unsigned bal = __ballot_sync(0xffffffffu, sp >= 0);
+        if (bal) {
+          const int L = __ffs(bal) - 1;
+          sp = __shfl_sync(0xffffffffu, sp, L);
+          int slot = 0;
+          if (lane == L) {
+            slot = W + atomicAdd(&sm.moveCount, 1);
+            sm.moveDst[slot] = dj;
+          }
+          slot = __shfl_sync(0xffffffffu, slot, L);
+          const double* srow = A + (long long)sp * lda;
+          for (int e = lane; e < ext; e += 32) {
+            const int col = e < nLeft ? p.pc0 + e : c0 + w + (e - nLeft);
+            cp_async8(&sm.moveBuf[slot][e], srow + col, true);
+          }
+          cp_async_commit();
+        }
+      }
 #pragma unroll
       for (int k = 0; k < R; ++k) {
         if (pos[k] == mpos)
@@ -187,72 +279,79 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
           for (int c = j + 1; c < W; ++c) a[k][c] = fma(-l, urow[c], a[k][c]);
         }
       }
+      if (dbg) p.dbg[2 + j] = clock64();
       if (rank == 0 && tid == 0) {
         p.ipiv[dj] = mpos;
         if (sing && *p.info == 0) *p.info = dj + 1;
       }
     }
   }
+  if (dbg) p.dbg[1] = clock64();
 
-  // ---- rows go to their pivoted positions (these w columns live in registers)
+  // ---- rows go to their pivoted positions.  Unmoved rows of a warp are 32 consecutive matrix rows:
+  //      transpose through shared memory so that every store instruction writes whole 128-byte lines.
 #pragma unroll
   for (int k = 0; k < R; ++k) {
-    if (pos[k] < 0) continue;
-    double* dst = A + (long long)pos[k] * lda + c0;
+    const int wbase = k * (int)(CL * PT) + (int)rank * PT + warp * 32;
+    const bool moved = pos[k] >= 0 && pos[k] != spos[k];
     if (p.vec) {
+      __syncwarp();
 #pragma unroll
-      for (int c = 0; c < W; c += 2)
-        if (c < w) *reinterpret_cast<double2*>(dst + c) = make_double2(a[k][c], a[k][c + 1]);
-    } else {
+      for (int c = 0; c < W; ++c) sm.tile[warp][lane][c] = a[k][c];
+      __syncwarp();
+      const unsigned movedMask = __ballot_sync(0xffffffffu, moved);
+#pragma unroll
+      for (int i = 0; i < LPR; ++i) {
+        const int r = i * RPI + lane / LPR, cp = lane % LPR;
+        if (wbase + r < m && 2 * cp < w && !((movedMask >> r) & 1u))
+          *reinterpret_cast<double2*>(A + (long long)(c0 + wbase + r) * lda + c0 + 2 * cp) =
+              make_double2(sm.tile[warp][r][2 * cp], sm.tile[warp][r][2 * cp + 1]);
+      }
+      if (moved) {
+        double* dst = A + (long long)pos[k] * lda + c0;
+#pragma unroll
+        for (int c = 0; c < W; c += 2)
+          if (c < w) *reinterpret_cast<double2*>(dst + c) = make_double2(a[k][c], a[k][c + 1]);
+      }
+    } else if (pos[k] >= 0) {
+      double* dst = A + (long long)pos[k] * lda + c0;
 #pragma unroll
       for (int c = 0; c < W; ++c)
         if (c < w) dst[c] = a[k][c];
     }
-    if (pos[k] < c0 + w) p.grpSrcTop[pos[k]] = spos[k];
-    if (spos[k] < c0 + w) p.grpBDst[spos[k]] = (pos[k] >= c0 + w) ? pos[k] : -1;
-  }
-
-  // ---- move the rest of the moved rows inside the enclosing panel (read all, barrier, write all)
-  const int nLeft = c0 - p.pc0;
-  const int ext = nLeft + (p.pc1 - (c0 + w));
-  if (ext > 0) {  // uniform
-    __syncthreads();  // moveCount = 0 visible
-#pragma unroll
-    for (int k = 0; k < R; ++k) {
-      const bool moved = pos[k] >= 0 && pos[k] != spos[k];
-      unsigned mask = __ballot_sync(0xffffffffu, moved);
-      while (mask) {
-        const int L = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const int sp = __shfl_sync(0xffffffffu, spos[k], L);
-        const int dp = __shfl_sync(0xffffffffu, pos[k], L);
-        int slot = 0;
-        if (lane == 0) slot = atomicAdd(moveCount, 1);
-        slot = __shfl_sync(0xffffffffu, slot, 0);
-        const double* srow = A + (long long)sp * lda;
-        for (int e = lane; e < ext; e += 32) {
-          const int col = e < nLeft ? p.pc0 + e : c0 + w + (e - nLeft);
-          moveBuf[slot * MAXEXT + e] = srow[col];
-        }
-        if (lane == 0) moveDst[slot] = dp;
+    if (pos[k] >= 0) {
+      if (pos[k] < c0 + w) p.grpSrcTop[pos[k]] = spos[k];
+      if (spos[k] < c0 + w) {
+        p.grpBDst[spos[k]] = (pos[k] >= c0 + w) ? pos[k] : -1;
+        sm.moveDst[spos[k] - c0] = moved ? pos[k] : -1;  // only threads of CTA 0 own top rows
       }
     }
+  }
+  if (dbg) p.dbg[20] = clock64();
+
+  // ---- rest-of-panel columns of the moved rows: all reads (cp.async above) done, barrier, then write
+  if (ext > 0) {  // uniform
+    cp_async_wait<0>();
     cluster_sync_all();
-    const int cnt = *moveCount;
-    for (int s = warp; s < cnt; s += PNW) {
-      double* drow = A + (long long)moveDst[s] * lda;
+    const int cnt = sm.moveCount;
+    const int nslots = W + cnt;
+    for (int s = warp; s < nslots; s += PNW) {
+      if (s < W && (rank != 0 || s >= w || s >= m)) continue;
+      const int d = sm.moveDst[s];
+      if (d < 0) continue;
+      double* drow = A + (long long)d * lda;
       for (int e = lane; e < ext; e += 32) {
         const int col = e < nLeft ? p.pc0 + e : c0 + w + (e - nLeft);
-        drow[col] = moveBuf[s * MAXEXT + e];
+        drow[col] = sm.moveBuf[s][e];
       }
     }
   }
+  if (dbg) p.dbg[21] = clock64();
 }
 
 template <int W, int R>
 static size_t leaf_smem() {
-  return (size_t)(PNW * (W + 2) + 2 * MAXCL * (W + 2) + MAXMOVE * MAXEXT) * sizeof(double) +
-         (MAXMOVE + 4) * sizeof(int);
+  return sizeof(LeafSmem<W>) + 16;
 }
 
 template <int W, int R>
@@ -472,87 +571,119 @@ __global__ void lu_rhs_perm_kernel(double* __restrict__ b, const int* __restrict
   }
 }
 
-// y[r0+i] -= sum_{c in [c0,c1)} Mx[r0+i][c] * x[c]     (one warp per row)
-__global__ void lu_gemv_sub_kernel(const double* __restrict__ Mx, long long lda, const double* x, double* y,
-                                   int r0, int nr, int c0, int c1) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= nr) return;
-  const double* row = Mx + (long long)(r0 + warp) * lda;
-  double s = 0.0;
-  for (int c = c0 + lane; c < c1; c += 32) s = fma(row[c], x[c], s);
-  s = warp_sum(s);
-  if (lane == 0) y[r0 + warp] -= s;
-}
+// One step of the blocked triangular solve (BS = 128 rows per block).  Forward (unit lower) visits
+// blocks top-down, backward (upper) bottom-up.  In the step for block [kb, kb+bs):
+//   CTA 0     : applies the previous block's solution x_prev to its own rows, then solves the
+//               diagonal block held in shared memory (32-wide sub-blocks, warp-shuffle substitution);
+//   CTAs >= 1 : apply x_prev to all remaining rows, one warp per row (rows of L / U are contiguous).
+// One launch per block; the kernel boundary is the only synchronisation.
+constexpr int TS_BS = 128;
+constexpr int TS_LD = TS_BS + 1;
 
-__global__ void __launch_bounds__(256) lu_trsv_lower_block_kernel(const double* __restrict__ LU, long long lda,
-                                                                   double* __restrict__ b, int kb, int bs) {
-  __shared__ double y[256];
-  __shared__ double Ts[32][33];
+template <bool UPPER>
+__global__ void __launch_bounds__(256) lu_trisolve_step_kernel(const double* __restrict__ LU, long long lda,
+                                                               double* __restrict__ b, int n, int kprev,
+                                                               int bsprev, int kb, int bs) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double* T = reinterpret_cast<double*>(smraw);  // [TS_BS][TS_LD]
+  double* xs = T + TS_BS * TS_LD;                // [TS_BS] previous block's solution
+  double* ys = xs + TS_BS;                       // [TS_BS] this block's right-hand side / solution
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < bs) y[tid] = b[kb + tid];
-  __syncthreads();
-  for (int sb = 0; sb < bs; sb += 32) {
-    const int sw = min(32, bs - sb);
-    for (int e = tid; e < 32 * 32; e += 256) {
-      const int r = e >> 5, c = e & 31;
-      Ts[r][c] = (r < sw && c < r) ? LU[(long long)(kb + sb + r) * lda + kb + sb + c] : 0.0;
-    }
+  if (kprev >= 0)
+    for (int c = tid; c < bsprev; c += 256) xs[c] = b[kprev + c];
+  if (blockIdx.x > 0) {
     __syncthreads();
-    if (warp == 0) {
-      double yi = lane < sw ? y[sb + lane] : 0.0;
-      for (int r = 0; r < sw; ++r) {
-        const double yr = __shfl_sync(0xffffffffu, yi, r);
-        if (lane > r) yi = fma(-Ts[lane][r], yr, yi);
-      }
-      if (lane < sw) y[sb + lane] = yi;
-    }
-    __syncthreads();
-    for (int i = sb + sw + tid; i < bs; i += 256) {
-      const double* row = LU + (long long)(kb + i) * lda + kb + sb;
-      double s = y[i];
-      for (int c = 0; c < sw; ++c) s = fma(-row[c], y[sb + c], s);
-      y[i] = s;
-    }
-    __syncthreads();
+    const int idx = (blockIdx.x - 1) * 8 + warp;
+    const int r = UPPER ? idx : kb + bs + idx;
+    if (r >= (UPPER ? kb : n)) return;
+    const double* row = LU + (long long)r * lda + kprev;
+    double s = 0.0;
+    for (int c = lane; c < bsprev; c += 32) s = fma(row[c], xs[c], s);
+    s = warp_sum(s);
+    if (lane == 0) b[r] -= s;
+    return;
   }
-  if (tid < bs) b[kb + tid] = y[tid];
-}
-
-__global__ void __launch_bounds__(256) lu_trsv_upper_block_kernel(const double* __restrict__ LU, long long lda,
-                                                                   double* __restrict__ b, int kb, int bs) {
-  __shared__ double y[256];
-  __shared__ double Ts[32][33];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid < bs) y[tid] = b[kb + tid];
+  // ---- CTA 0: the diagonal block streams into shared memory (cp.async) while the rows of this block
+  //      receive the previous block's update straight from global memory (16 rows per warp, all loads
+  //      of a warp in flight together).
+  {
+    const int c = tid & (TS_BS - 1);
+    for (int i = tid >> 7; i < bs; i += 2)
+      cp_async8(&T[i * TS_LD + c], LU + (long long)(kb + i) * lda + kb + c, c < bs);
+    cp_async_commit();
+  }
+  if (tid < bs) ys[tid] = b[kb + tid];
+  __syncthreads();
+  if (kprev >= 0) {
+    constexpr int RPW = TS_BS / 8;  // rows per warp
+    constexpr int CPL = TS_BS / 32;  // columns per lane
+    // branch-free, clamped addresses: all RPW*CPL loads of a lane are issued before the first FMA
+    double v[RPW][CPL];
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+      const int i = min(warp * RPW + rr, bs - 1);
+      const double* row = LU + (long long)(kb + i) * lda + kprev;
+#pragma unroll
+      for (int u = 0; u < CPL; ++u) v[rr][u] = __ldg(row + min(lane + 32 * u, bsprev - 1));
+    }
+    double xv[CPL];
+#pragma unroll
+    for (int u = 0; u < CPL; ++u) xv[u] = (lane + 32 * u < bsprev) ? xs[lane + 32 * u] : 0.0;
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int u = 0; u < CPL; ++u) sacc = fma(v[rr][u], xv[u], sacc);
+      const double t = warp_sum(sacc);
+      const int i = warp * RPW + rr;
+      if (lane == 0 && i < bs) ys[i] -= t;
+    }
+  }
+  cp_async_wait<0>();
   __syncthreads();
   const int nsb = (bs + 31) / 32;
-  for (int q = nsb - 1; q >= 0; --q) {
-    const int sb = q * 32;
+  for (int q = 0; q < nsb; ++q) {
+    const int sb = UPPER ? (nsb - 1 - q) * 32 : q * 32;
     const int sw = min(32, bs - sb);
-    for (int e = tid; e < 32 * 32; e += 256) {
-      const int r = e >> 5, c = e & 31;
-      Ts[r][c] = (r < sw && c < sw && c >= r) ? LU[(long long)(kb + sb + r) * lda + kb + sb + c] : 0.0;
-    }
-    __syncthreads();
     if (warp == 0) {
-      double yi = lane < sw ? y[sb + lane] : 0.0;
-      for (int r = sw - 1; r >= 0; --r) {
-        if (lane == r) yi = yi / Ts[r][r];
-        const double yr = __shfl_sync(0xffffffffu, yi, r);
-        if (lane < r) yi = fma(-Ts[lane][r], yr, yi);
+      double t[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) t[r] = (lane < sw && r < sw) ? T[(sb + lane) * TS_LD + sb + r] : 0.0;
+      double yi = lane < sw ? ys[sb + lane] : 0.0;
+      if (!UPPER) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const double yr = __shfl_sync(0xffffffffu, yi, r);
+          if (lane > r) yi = fma(-t[r], yr, yi);
+        }
+      } else {
+        double dinv = 1.0;
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+          if (lane == r) dinv = t[r];
+        dinv = (lane < sw) ? 1.0 / dinv : 1.0;  // one reciprocal per lane, off the dependent chain
+#pragma unroll
+        for (int r = 31; r >= 0; --r) {
+          if (r < sw) {
+            if (lane == r) yi = yi * dinv;
+            const double yr = __shfl_sync(0xffffffffu, yi, r);
+            if (lane < r) yi = fma(-t[r], yr, yi);
+          }
+        }
       }
-      if (lane < sw) y[sb + lane] = yi;
+      if (lane < sw) ys[sb + lane] = yi;
     }
     __syncthreads();
-    for (int i = tid; i < sb; i += 256) {
-      const double* row = LU + (long long)(kb + i) * lda + kb + sb;
-      double s = y[i];
-      for (int c = 0; c < sw; ++c) s = fma(-row[c], y[sb + c], s);
-      y[i] = s;
+    // remaining rows of the block
+    const int i = UPPER ? tid : sb + sw + tid;
+    if (UPPER ? (i < sb) : (i < bs)) {
+      double s = ys[i];
+      for (int c = 0; c < sw; ++c) s = fma(-T[i * TS_LD + sb + c], ys[sb + c], s);
+      ys[i] = s;
     }
     __syncthreads();
   }
-  if (tid < bs) b[kb + tid] = y[tid];
+  if (tid < bs) b[kb + tid] = ys[tid];
 }
 
 // ------------------------------------------------------------------ host-side plan / scheduler
@@ -564,6 +695,8 @@ struct LuPlan {
   int *permSrcTop = nullptr, *permBDst = nullptr, *permBSrc = nullptr, *permNBot = nullptr;
   int* posContent = nullptr;
   double *S = nullptr, *S2 = nullptr;
+  cudaStream_t panelStream = nullptr;  // high priority: next panel overlaps the trailing update
+  cudaEvent_t evFork = nullptr, evJoin = nullptr;
   // CUDA-graph cache of the factorisation for one set of buffers
   cudaGraphExec_t exec = nullptr;
   long long graphLaunches = 0;
@@ -617,6 +750,11 @@ int lu_plan_create(int n, LuPlan** out) {
   const size_t sbytes = sizeof(double) * (size_t)256 * (size_t)n;
   WG_CUDA(cudaMalloc(&p->S, sbytes));
   WG_CUDA(cudaMalloc(&p->S2, sbytes));
+  int prLow = 0, prHigh = 0;
+  WG_CUDA(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
+  WG_CUDA(cudaStreamCreateWithPriority(&p->panelStream, cudaStreamNonBlocking, prHigh));
+  WG_CUDA(cudaEventCreateWithFlags(&p->evFork, cudaEventDisableTiming));
+  WG_CUDA(cudaEventCreateWithFlags(&p->evJoin, cudaEventDisableTiming));
   *out = p;
   return WG_OK;
 }
@@ -624,6 +762,9 @@ int lu_plan_create(int n, LuPlan** out) {
 void lu_plan_destroy(LuPlan* p) {
   if (!p) return;
   if (p->exec) cudaGraphExecDestroy(p->exec);
+  if (p->panelStream) cudaStreamDestroy(p->panelStream);
+  if (p->evFork) cudaEventDestroy(p->evFork);
+  if (p->evJoin) cudaEventDestroy(p->evJoin);
   cudaFree(p->grpSrcTop);
   cudaFree(p->grpBDst);
   cudaFree(p->permSrcTop);
@@ -662,6 +803,7 @@ static int leaf(FactorCtx& c, int c0, int w, int pc0, int pc1) {
   pa.grpSrcTop = c.p->grpSrcTop;
   pa.grpBDst = c.p->grpBDst;
   pa.vec = c.vecA && (c0 % 2 == 0) && (w % 2 == 0);
+  pa.dbg = (g_dbg_buf && c0 == g_dbg_c0) ? g_dbg_buf : nullptr;
   auto pick_cl = [&](int rows_per_cta) {
     int cl = 1;
     while (cl * rows_per_cta < m) cl <<= 1;
@@ -693,28 +835,43 @@ static int panel_rec(FactorCtx& c, int c0, int w, int pc0, int pc1) {
   return panel_rec(c, c0 + w1, w - w1, pc0, pc1);
 }
 
+static int panel_width_class(LuPlan* p, int m) {
+  if (m <= p->maxCL * PT * 2) return 16;
+  if (m <= p->maxCL * PT * 4) return 8;
+  return 0;
+}
+
+// Right-looking blocked LU.  With look-ahead, panel k+1 is factored on a high-priority side stream as
+// soon as its own columns have received update k, while the main stream finishes the rest of the
+// trailing update; the leaf panels (16 SMs, latency bound) hide behind the DMMA GEMM.
 static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStream_t st) {
   const int n = p->n, NB = p->nb;
   FactorCtx c{p, A, lda, ipiv, info, st, 16, 0};
   c.vecA = (lda % 2 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0);
+  const bool look = g_lookahead != 0;
   WG_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
+  if (panel_width_class(p, n) == 0) {
+    wg_set_error("lu_factor: n=%d exceeds the leaf-panel capacity (%d rows) of this build", n,
+                 p->maxCL * PT * 4);
+    return WG_ERR_UNSUPPORTED;
+  }
+  bool panelDone = false;  // panel [k, k+nb) already factored by the look-ahead of the previous step
   for (int k = 0, pnl = 0; k < n; k += NB, ++pnl) {
     const int nb = NB < n - k ? NB : n - k;
-    const int m = n - k;
-    if (m <= p->maxCL * PT * 2)
-      c.wb = 16;
-    else if (m <= p->maxCL * PT * 4)
-      c.wb = 8;
-    else {
-      wg_set_error("lu_factor: n=%d exceeds the leaf-panel capacity (%d rows) of this build", n,
-                   p->maxCL * PT * 4);
-      return WG_ERR_UNSUPPORTED;
+    int rc;
+    if (!panelDone) {
+      c.st = st;
+      c.wb = panel_width_class(p, n - k);
+      rc = panel_rec(c, k, nb, k, k + nb);
+      if (rc) return rc;
     }
-    int rc = panel_rec(c, k, nb, k, k + nb);
-    if (rc) return rc;
-    lu_perm_compose_kernel<<<1, 256, 0, st>>>(n, k, nb, c.wb, p->grpSrcTop, p->grpBDst, p->posContent,
-                                              p->permSrcTop, p->permBDst, p->permBSrc, p->permNBot + pnl);
-    WG_LAUNCH_CHECK();
+    c.st = st;
+    if (!panelDone) {
+      lu_perm_compose_kernel<<<1, 256, 0, st>>>(n, k, nb, panel_width_class(p, n - k), p->grpSrcTop, p->grpBDst,
+                                                p->posContent, p->permSrcTop, p->permBDst, p->permBSrc,
+                                                p->permNBot + pnl);
+      WG_LAUNCH_CHECK();
+    }
     if (n - nb > 0) {
       const int vec = c.vecA && (k % 2 == 0) && (nb % 2 == 0) && (n % 2 == 0);
       dim3 grid(wg_cdiv(n - nb, 2048), nb);
@@ -725,12 +882,37 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
                                                  p->permNBot + pnl, p->S, p->S2, vec);
       WG_LAUNCH_CHECK();
     }
+    panelDone = false;
     const int rest = n - k - nb;
-    if (rest > 0) {
-      rc = trsm_rec(A + (long long)k * lda + k, lda, A + (long long)k * lda + k + nb, lda, nb, rest, st);
+    if (rest <= 0) break;
+    rc = trsm_rec(A + (long long)k * lda + k, lda, A + (long long)k * lda + k + nb, lda, nb, rest, st);
+    if (rc) return rc;
+    double* C22 = A + (long long)(k + nb) * lda + k + nb;
+    const double* L21 = A + (long long)(k + nb) * lda + k;
+    const double* U12 = A + (long long)k * lda + k + nb;
+    const int nb2 = NB < rest ? NB : rest;
+    if (look && rest > nb2) {
+      // update the next panel's columns first, fork the panel factorisation, then the rest
+      rc = dgemm_sub(C22, L21, U12, rest, nb2, nb, lda, lda, lda, st);
       if (rc) return rc;
-      rc = dgemm_sub(A + (long long)(k + nb) * lda + k + nb, A + (long long)(k + nb) * lda + k,
-                     A + (long long)k * lda + k + nb, rest, rest, nb, lda, lda, lda, st);
+      WG_CUDA(cudaEventRecord(p->evFork, st));
+      WG_CUDA(cudaStreamWaitEvent(p->panelStream, p->evFork, 0));
+      c.st = p->panelStream;
+      c.wb = panel_width_class(p, rest);
+      rc = panel_rec(c, k + nb, nb2, k + nb, k + nb + nb2);
+      if (rc) return rc;
+      lu_perm_compose_kernel<<<1, 256, 0, p->panelStream>>>(n, k + nb, nb2, c.wb, p->grpSrcTop, p->grpBDst,
+                                                            p->posContent, p->permSrcTop, p->permBDst,
+                                                            p->permBSrc, p->permNBot + pnl + 1);
+      WG_LAUNCH_CHECK();
+      WG_CUDA(cudaEventRecord(p->evJoin, p->panelStream));
+      c.st = st;
+      rc = dgemm_sub(C22 + nb2, L21, U12 + nb2, rest, rest - nb2, nb, lda, lda, lda, st);
+      if (rc) return rc;
+      WG_CUDA(cudaStreamWaitEvent(st, p->evJoin, 0));
+      panelDone = true;
+    } else {
+      rc = dgemm_sub(C22, L21, U12, rest, rest, nb, lda, lda, lda, st);
       if (rc) return rc;
     }
   }
@@ -777,26 +959,35 @@ int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t
   const int n = p->n, NB = p->nb;
   lu_rhs_perm_kernel<<<1, 1024, 0, st>>>(b, p->permSrcTop, p->permBDst, p->permBSrc, p->permNBot, n, NB);
   WG_LAUNCH_CHECK();
-  const int BS = 256;
-  for (int kb = 0; kb < n; kb += BS) {
-    const int bs = BS < n - kb ? BS : n - kb;
-    if (kb > 0) {
-      lu_gemv_sub_kernel<<<wg_cdiv(bs, 8), 256, 0, st>>>(LU, lda, b, b, kb, bs, 0, kb);
-      WG_LAUNCH_CHECK();
-    }
-    lu_trsv_lower_block_kernel<<<1, 256, 0, st>>>(LU, lda, b, kb, bs);
-    WG_LAUNCH_CHECK();
+  const size_t smem = (size_t)(TS_BS * TS_LD + 2 * TS_BS) * sizeof(double);
+  static bool configured = false;
+  if (!configured) {
+    WG_CUDA(cudaFuncSetAttribute(lu_trisolve_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WG_CUDA(cudaFuncSetAttribute(lu_trisolve_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
   }
-  const int nblk = wg_cdiv(n, BS);
-  for (int q = nblk - 1; q >= 0; --q) {
-    const int kb = q * BS;
-    const int bs = BS < n - kb ? BS : n - kb;
-    if (kb + bs < n) {
-      lu_gemv_sub_kernel<<<wg_cdiv(bs, 8), 256, 0, st>>>(LU, lda, b, b, kb, bs, kb + bs, n);
-      WG_LAUNCH_CHECK();
-    }
-    lu_trsv_upper_block_kernel<<<1, 256, 0, st>>>(LU, lda, b, kb, bs);
+  const int nblk = wg_cdiv(n, TS_BS);
+  int kprev = -1, bsprev = 0;
+  for (int q = 0; q < nblk; ++q) {
+    const int kb = q * TS_BS;
+    const int bs = TS_BS < n - kb ? TS_BS : n - kb;
+    const int rest = n - kb - bs;
+    const int grid = 1 + ((kprev >= 0 && rest > 0) ? wg_cdiv(rest, 8) : 0);
+    lu_trisolve_step_kernel<false><<<grid, 256, smem, st>>>(LU, lda, b, n, kprev, bsprev, kb, bs);
     WG_LAUNCH_CHECK();
+    kprev = kb;
+    bsprev = bs;
+  }
+  kprev = -1;
+  bsprev = 0;
+  for (int q = nblk - 1; q >= 0; --q) {
+    const int kb = q * TS_BS;
+    const int bs = TS_BS < n - kb ? TS_BS : n - kb;
+    const int grid = 1 + ((kprev >= 0 && kb > 0) ? wg_cdiv(kb, 8) : 0);
+    lu_trisolve_step_kernel<true><<<grid, 256, smem, st>>>(LU, lda, b, n, kprev, bsprev, kb, bs);
+    WG_LAUNCH_CHECK();
+    kprev = kb;
+    bsprev = bs;
   }
   return WG_OK;
 }
