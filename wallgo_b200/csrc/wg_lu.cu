@@ -90,25 +90,29 @@ __device__ __forceinline__ void st_async_u64(uint32_t remote_addr, unsigned long
                : "memory");
 }
 
-template <int W>
+template <int W, int R>
 struct LeafSmem {
   static constexpr int SL = W + 2;   // row values, key bits, position
   static constexpr int TW = W + 1;   // padded tile row
   double warpSlot[PNW][SL];          // per-warp pivot candidates of the current column
   double cluSlot[2][MAXCL][SL];      // per-CTA candidates, double buffered by column parity
   double moveBuf[MAXMOVE][MAXEXT];   // rest-of-panel data of rows that change position
-  double tile[PNW][32][TW];          // coalescing transposes for the load / store of the leaf block
+  double tile[PNW][R][32][TW];       // the leaf block itself: load transpose, finished columns, store
   unsigned long long bars[2];
   int moveDst[MAXMOVE];
   int moveCount;
 };
 
 // One leaf of the panel recursion: rows [c0, n) x columns [c0, c0+w), w <= W, factored by one cluster.
-// Thread t of CTA r keeps rows c0 + k*CL*PT + r*PT + t (k < R) in registers for the whole kernel.
+// Thread t of CTA r owns rows c0 + k*CL*PT + r*PT + t (k < R).  The not-yet-eliminated columns of a
+// row live in a ROTATING register window (a[k][0] is always the current column), so the column loop is
+// a real loop with static register indices and a small instruction footprint (a fully unrolled body is
+// ~180 KB of SASS and stalls on instruction fetch); finished columns are parked in the shared-memory
+// tile that is also used for the coalesced load and store of the block.
 template <int W, int R>
 __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  using SM = LeafSmem<W>;
+  using SM = LeafSmem<W, R>;
   SM& sm = *reinterpret_cast<SM*>(smraw);
   constexpr int SL = SM::SL;
   constexpr int LPR = W / 2;        // lanes per row when moving double2
@@ -151,173 +155,165 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
     pos[k] = valid ? c0 + lr : -1;
     spos[k] = pos[k];
     if (p.vec) {
-      __syncwarp();
 #pragma unroll
       for (int i = 0; i < LPR; ++i) {
         const int r = i * RPI + lane / LPR, cp = lane % LPR;
         double2 v = make_double2(0.0, 0.0);
         if (wbase + r < m && 2 * cp < w)
           v = *reinterpret_cast<const double2*>(A + (long long)(c0 + wbase + r) * lda + c0 + 2 * cp);
-        sm.tile[warp][r][2 * cp] = v.x;
-        sm.tile[warp][r][2 * cp + 1] = v.y;
+        sm.tile[warp][k][r][2 * cp] = v.x;
+        sm.tile[warp][k][r][2 * cp + 1] = v.y;
       }
-      __syncwarp();
-#pragma unroll
-      for (int c = 0; c < W; ++c) a[k][c] = sm.tile[warp][lane][c];
     } else {
       const double* src = A + (long long)(c0 + lr) * lda + c0;
 #pragma unroll
-      for (int c = 0; c < W; ++c) a[k][c] = (valid && c < w) ? src[c] : 0.0;
+      for (int c = 0; c < W; ++c) sm.tile[warp][k][lane][c] = (valid && c < w) ? src[c] : 0.0;
     }
   }
+  __syncwarp();
+#pragma unroll
+  for (int k = 0; k < R; ++k)
+#pragma unroll
+    for (int c = 0; c < W; ++c) a[k][c] = sm.tile[warp][k][lane][c];
   cluster_sync_all();  // mbarriers of every CTA initialised before anybody signals them
   if (dbg) p.dbg[22] = clock64();
 
-  const uint32_t barAddr[2] = {smem_u32(&sm.bars[0]), smem_u32(&sm.bars[1])};
-  constexpr int NPUSH = 0;
-  (void)NPUSH;
+  const uint32_t barBase = smem_u32(&sm.bars[0]);
 
+#pragma unroll 1
+  for (int j = 0; j < w; ++j) {
+    const int dj = c0 + j;
+    const int par = j & 1;
+    if (tid == 0) mbar_expect_tx(reinterpret_cast<uint64_t*>(&sm.bars[par]), (uint32_t)(CL * SL * 8));
+    // ---- thread-local, then warp-level candidate (current column = window slot 0)
+    long long bk = -1;
+    int bp = INT_MAX, kb = 0;
 #pragma unroll
-  for (int j = 0; j < W; ++j) {
-    if (j < w) {  // uniform
-      const int dj = c0 + j;
-      const int par = j & 1;
-      if (tid == 0) mbar_expect_tx(reinterpret_cast<uint64_t*>(&sm.bars[par]), (uint32_t)(CL * SL * 8));
-      const bool dbc = dbg && j == 8;
-      if (dbc) p.dbg[24] = clock64();
-      // ---- thread-local, then warp-level candidate
-      long long bk = -1;
-      int bp = INT_MAX, kb = 0;
+    for (int k = 0; k < R; ++k) {
+      const bool act = pos[k] >= dj;
+      const long long key = act ? __double_as_longlong(fabs(a[k][0])) : -1LL;
+      const int pp = act ? pos[k] : INT_MAX;
+      if (key > bk || (key == bk && pp < bp)) {
+        bk = key;
+        bp = pp;
+        kb = k;
+      }
+    }
+    if (lane == argmax_lane(bk, bp, true)) {
+      double* slot = sm.warpSlot[warp];
 #pragma unroll
-      for (int k = 0; k < R; ++k) {
-        const bool act = pos[k] >= dj;
-        const long long key = act ? __double_as_longlong(fabs(a[k][j])) : -1LL;
-        const int pp = act ? pos[k] : INT_MAX;
-        if (key > bk || (key == bk && pp < bp)) {
-          bk = key;
-          bp = pp;
-          kb = k;
+      for (int k = 0; k < R; ++k)
+        if (k == kb) {
+#pragma unroll
+          for (int c = 0; c < W; ++c) slot[c] = a[k][c];
         }
+      reinterpret_cast<long long*>(slot)[W] = bk;
+      reinterpret_cast<long long*>(slot)[W + 1] = (long long)bp;
+    }
+    __syncthreads();
+    // ---- CTA-level winner, pushed to every CTA of the cluster (st.async completes their mbarrier)
+    if (warp * 32 < SL * (int)CL) {
+      const double* s = sm.warpSlot[lane & (PNW - 1)];
+      const long long k2 = reinterpret_cast<const long long*>(s)[W];
+      const int p2 = (int)reinterpret_cast<const long long*>(s)[W + 1];
+      const int ww = argmax_lane(k2, p2, lane < PNW);
+      const unsigned long long* srcw = reinterpret_cast<const unsigned long long*>(sm.warpSlot[ww]);
+      const uint32_t base = smem_u32(&sm.cluSlot[par][rank][0]);
+      if (tid < SL * (int)CL) {
+        const int dest = tid / SL, e = tid - dest * SL;
+        st_async_u64(dsmem_map(base + 8u * e, dest), srcw[e], dsmem_map(barBase + 8u * par, dest));
       }
-      if (lane == argmax_lane(bk, bp, true)) {
-        double* slot = sm.warpSlot[warp];
+    }
+    mbar_wait(reinterpret_cast<uint64_t*>(&sm.bars[par]), (uint32_t)((j >> 1) & 1));
+    // ---- cluster-level winner = pivot row (window-aligned: urow[0] is the pivot element)
+    const double* urow;
+    {
+      const double* s = sm.cluSlot[par][lane & ((int)CL - 1)];
+      const long long k3 = reinterpret_cast<const long long*>(s)[W];
+      const int p3 = (int)reinterpret_cast<const long long*>(s)[W + 1];
+      urow = sm.cluSlot[par][argmax_lane(k3, p3, lane < (int)CL)];
+    }
+    const long long mkey = reinterpret_cast<const long long*>(urow)[W];
+    const int mpos = (int)reinterpret_cast<const long long*>(urow)[W + 1];
+    const bool sing = (mkey <= 0);
+    const double rinv = sing ? 0.0 : 1.0 / urow[0];
+    // the pivot row comes from below the top block: stage its rest-of-panel columns now
+    if (ext > 0) {
+      int sp = -1;
 #pragma unroll
-        for (int k = 0; k < R; ++k)
-          if (k == kb) {
-#pragma unroll
-            for (int c = 0; c < W; ++c) slot[c] = a[k][c];
-          }
-        reinterpret_cast<long long*>(slot)[W] = bk;
-        reinterpret_cast<long long*>(slot)[W + 1] = (long long)bp;
-      }
-      if (dbc) p.dbg[25] = clock64();
-      __syncthreads();
-      if (dbc) p.dbg[26] = clock64();
-      // ---- CTA-level winner, pushed to every CTA of the cluster (st.async completes their mbarrier)
-      if (warp * 32 < SL * (int)CL) {
-        const double* s = sm.warpSlot[lane & (PNW - 1)];
-        const long long k2 = reinterpret_cast<const long long*>(s)[W];
-        const int p2 = (int)reinterpret_cast<const long long*>(s)[W + 1];
-        const int ww = argmax_lane(k2, p2, lane < PNW);
-        const unsigned long long* srcw = reinterpret_cast<const unsigned long long*>(sm.warpSlot[ww]);
-        const uint32_t base = smem_u32(&sm.cluSlot[par][rank][0]);
-        if (tid < SL * (int)CL) {
-          const int dest = tid / SL, e = tid - dest * SL;
-          st_async_u64(dsmem_map(base + 8u * e, dest), srcw[e], dsmem_map(barAddr[par], dest));
+      for (int k = 0; k < R; ++k)
+        if (pos[k] == mpos && spos[k] >= c0 + w) sp = spos[k];
+      const unsigned bal = __ballot_sync(0xffffffffu, sp >= 0);
+      if (bal) {
+        const int L = __ffs(bal) - 1;
+        sp = __shfl_sync(0xffffffffu, sp, L);
+        int slot = 0;
+        if (lane == L) {
+          slot = W + atomicAdd(&sm.moveCount, 1);
+          sm.moveDst[slot] = dj;
         }
-      }
-      if (dbc) p.dbg[27] = clock64();
-      mbar_wait(reinterpret_cast<uint64_t*>(&sm.bars[par]), (uint32_t)((j >> 1) & 1));
-      if (dbc) p.dbg[28] = clock64();
-      // ---- cluster-level winner = pivot row
-      const double* urow;
-      {
-        const double* s = sm.cluSlot[par][lane & ((int)CL - 1)];
-        const long long k3 = reinterpret_cast<const long long*>(s)[W];
-        const int p3 = (int)reinterpret_cast<const long long*>(s)[W + 1];
-        urow = sm.cluSlot[par][argmax_lane(k3, p3, lane < (int)CL)];
-      }
-      const long long mkey = reinterpret_cast<const long long*>(urow)[W];
-      const int mpos = (int)reinterpret_cast<const long long*>(urow)[W + 1];
-      const bool sing = (mkey <= 0);
-      const double rinv = sing ? 0.0 : 1.0 / urow[j];
-      if (dbc) p.dbg[29] = clock64() + (long long)(rinv == 123.456);
-      // the pivot row comes from below the top block: stage its rest-of-panel columns now
-      if (ext > 0) {
-        int sp = -1;
-#pragma unroll
-        for (int k = 0; k < R; ++k)
-          if (pos[k] == mpos && spos[k] >= c0 + w) sp = spos[k];
-        const unsigned bal = __ballot_sync(0xffffffffu, sp >= 0);
-        if (bal) {
-          const int L = __ffs(bal) - 1;
-          sp = __shfl_sync(0xffffffffu, sp, L);
-          int slot = 0;
-          if (lane == L) {
-            slot = W + atomicAdd(&sm.moveCount, 1);
-            sm.moveDst[slot] = dj;
-          }
-          slot = __shfl_sync(0xffffffffu, slot, L);
-          const double* srow = A + (long long)sp * lda;
-          for (int e = lane; e < ext; e += 32) {
-            const int col = e < nLeft ? p.pc0 + e : c0 + w + (e - nLeft);
-            cp_async8(&sm.moveBuf[slot][e], srow + col, true);
-          }
-          cp_async_commit();
+        slot = __shfl_sync(0xffffffffu, slot, L);
+        const double* srow = A + (long long)sp * lda;
+        for (int e = lane; e < ext; e += 32) {
+          const int col = e < nLeft ? p.pc0 + e : c0 + w + (e - nLeft);
+          cp_async8(&sm.moveBuf[slot][e], srow + col, true);
         }
+        cp_async_commit();
       }
+    }
+    double uv[W];
 #pragma unroll
-      for (int k = 0; k < R; ++k) {
-        if (pos[k] == mpos)
-          pos[k] = dj;
-        else if (pos[k] == dj)
-          pos[k] = mpos;
-        if (pos[k] > dj && !sing) {
-          const double l = a[k][j] * rinv;
-          a[k][j] = l;
+    for (int c = 1; c < W; ++c) uv[c] = urow[c];
 #pragma unroll
-          for (int c = j + 1; c < W; ++c) a[k][c] = fma(-l, urow[c], a[k][c]);
-        }
-      }
-      if (dbg) p.dbg[2 + j] = clock64();
-      if (rank == 0 && tid == 0) {
-        p.ipiv[dj] = mpos;
-        if (sing && *p.info == 0) *p.info = dj + 1;
-      }
+    for (int k = 0; k < R; ++k) {
+      if (pos[k] == mpos)
+        pos[k] = dj;
+      else if (pos[k] == dj)
+        pos[k] = mpos;
+      const bool elim = pos[k] > dj && !sing;
+      const double l = elim ? a[k][0] * rinv : a[k][0];   // multiplier, or the finished U / L entry
+      sm.tile[warp][k][lane][j] = l;
+      const double ml = elim ? -l : 0.0;
+#pragma unroll
+      for (int c = 1; c < W; ++c) a[k][c - 1] = fma(ml, uv[c], a[k][c]);  // eliminate + rotate window
+    }
+    if (dbg) p.dbg[2 + (j & 15)] = clock64();
+    if (rank == 0 && tid == 0) {
+      p.ipiv[dj] = mpos;
+      if (sing && *p.info == 0) *p.info = dj + 1;
     }
   }
   if (dbg) p.dbg[1] = clock64();
 
   // ---- rows go to their pivoted positions.  Unmoved rows of a warp are 32 consecutive matrix rows:
-  //      transpose through shared memory so that every store instruction writes whole 128-byte lines.
+  //      the tile is stored so that every instruction writes whole 128-byte lines.
+  __syncwarp();
 #pragma unroll
   for (int k = 0; k < R; ++k) {
     const int wbase = k * (int)(CL * PT) + (int)rank * PT + warp * 32;
     const bool moved = pos[k] >= 0 && pos[k] != spos[k];
     if (p.vec) {
-      __syncwarp();
-#pragma unroll
-      for (int c = 0; c < W; ++c) sm.tile[warp][lane][c] = a[k][c];
-      __syncwarp();
       const unsigned movedMask = __ballot_sync(0xffffffffu, moved);
 #pragma unroll
       for (int i = 0; i < LPR; ++i) {
         const int r = i * RPI + lane / LPR, cp = lane % LPR;
         if (wbase + r < m && 2 * cp < w && !((movedMask >> r) & 1u))
           *reinterpret_cast<double2*>(A + (long long)(c0 + wbase + r) * lda + c0 + 2 * cp) =
-              make_double2(sm.tile[warp][r][2 * cp], sm.tile[warp][r][2 * cp + 1]);
+              make_double2(sm.tile[warp][k][r][2 * cp], sm.tile[warp][k][r][2 * cp + 1]);
       }
       if (moved) {
         double* dst = A + (long long)pos[k] * lda + c0;
 #pragma unroll
         for (int c = 0; c < W; c += 2)
-          if (c < w) *reinterpret_cast<double2*>(dst + c) = make_double2(a[k][c], a[k][c + 1]);
+          if (c < w)
+            *reinterpret_cast<double2*>(dst + c) =
+                make_double2(sm.tile[warp][k][lane][c], sm.tile[warp][k][lane][c + 1]);
       }
     } else if (pos[k] >= 0) {
       double* dst = A + (long long)pos[k] * lda + c0;
 #pragma unroll
       for (int c = 0; c < W; ++c)
-        if (c < w) dst[c] = a[k][c];
+        if (c < w) dst[c] = sm.tile[warp][k][lane][c];
     }
     if (pos[k] >= 0) {
       if (pos[k] < c0 + w) p.grpSrcTop[pos[k]] = spos[k];
@@ -351,7 +347,7 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
 
 template <int W, int R>
 static size_t leaf_smem() {
-  return sizeof(LeafSmem<W>) + 16;
+  return sizeof(LeafSmem<W, R>) + 16;
 }
 
 template <int W, int R>
