@@ -1,0 +1,163 @@
+"""TEST DOUBLE for wallgo_b200.engine.BoltzmannEngine backed by the CPU oracle.
+
+Only for CPU tests of the host-side plumbing (drop-in subclass, result wrapping, truncation logic)
+in a container without a GPU.  It implements the engine's method surface with NumPy; the product
+never imports this file."""
+import numpy as np
+
+from oracle import boltzmann_oracle as bo
+
+
+class _NP:
+    """numpy array with the two tensor methods the host code uses."""
+
+    def __init__(self, arr):
+        self.arr = arr
+
+    def cpu(self):
+        return self
+
+    def numpy(self):
+        return self.arr
+
+    def clone(self):
+        return _NP(self.arr.copy())
+
+    def copy_(self, other, non_blocking=False):
+        self.arr[...] = other.arr if isinstance(other, _NP) else other
+        return self
+
+    def __mul__(self, other):
+        return _NP(self.arr * (other.arr if isinstance(other, _NP) else other))
+
+
+class _FakeStream:
+    def synchronize(self):
+        pass
+
+
+class _FakeCuda:
+    @staticmethod
+    def current_stream(dev=None):
+        return _FakeStream()
+
+
+class _FakeTorch:
+    cuda = _FakeCuda()
+
+    @staticmethod
+    def from_numpy(a):
+        return a
+
+    @staticmethod
+    def empty_like(x):
+        return _NP(np.empty_like(x.arr))
+
+
+class FakeEngine:
+    def __init__(self, P, M, N, device=None):
+        self.P, self.M, self.N = P, M, N
+        self.M1, self.N1 = M - 1, N - 1
+        self.q = self.N1 ** 2
+        self.n = P * self.M1 * self.q
+        self.torch = _FakeTorch()
+        self.S = _NP(np.zeros(self.n))
+        self.dF_in = _NP(np.zeros(self.n))
+        self.A = None
+        self.tables = None
+        self.launches = 0
+        self.dev = None
+        self.mats = [None] * 9
+
+    def close(self):
+        pass
+
+    # static
+    def set_grid(self, chi, rz, rp, pz, pp, dpzdrz, dppdrp):
+        self.grid = [np.array(x, dtype=float) for x in (chi, rz, rp, pz, pp, dpzdrz, dppdrp)]
+
+    def set_statistics(self, s):
+        self.stat = np.array(s, dtype=float)
+
+    def build_basis(self):
+        self.tab = bo.build_tables(self.M, self.N, "Cardinal", "Chebyshev", "Spectral")
+
+    def set_tables(self, Tchi, Dchi, DchiFull, Trz, Drz, Trp):
+        ident = lambda m: np.allclose(m, np.identity(m.shape[0]))  # noqa: E731
+        basisM = "Cardinal" if ident(Tchi) else "Chebyshev"
+        basisN = "Cardinal" if ident(Trz) else "Chebyshev"
+        fd = basisM == "Cardinal" and np.count_nonzero(Dchi) <= 3 * Dchi.shape[0]
+        self.tab = bo.build_tables(self.M, self.N, basisM, basisN, "Finite Difference" if fd else "Spectral")
+
+    def set_transforms(self, mats):
+        self.mats = [None if m is None else np.array(m, dtype=float) for m in mats]
+
+    def get_tables(self):
+        t = self.tab
+        return dict(Tchi=t.Tchi, Dchi=t.Dchi, DchiFull=t.DchiFull, Trz=t.Trz, Drz=t.Drz, Trp=t.Trp)
+
+    def change_basis(self, stage, src, dst):
+        x = src.arr.reshape(self.P, self.M1, self.N1, self.N1)
+        for ax in range(3):
+            m = self.mats[3 * stage + ax]
+            if m is not None:
+                x = np.moveaxis(np.tensordot(m, x, axes=([1], [ax + 1])), 0, ax + 1)
+        dst.arr[...] = x.reshape(-1)
+
+    def collision_apply(self, x, y):
+        _, _, coll = bo.assemble(self.pb, want_collision=True)
+        y.arr[...] = coll @ x.arr
+
+    def set_collision(self, c):
+        self.coll = np.array(c, dtype=float).reshape(self.P, self.N1, self.N1, self.P, self.N1, self.N1)
+
+    # per solve
+    def upload_profiles(self, T, v, msq, dxidchi):
+        self.prof = (np.array(T, float), np.array(v, float), np.array(msq, float).reshape(self.P, self.M + 1),
+                     np.array(dxidchi, float))
+
+    def _problem(self, vw, mult):
+        chi, rz, rp, pz, pp, dpzdrz, dppdrp = self.grid
+        T, v, msq, dxidchi = self.prof
+        return bo.Problem(tab=self.tab, xi_dxidchi=dxidchi, pz=pz, pp=pp, dpzdrz=dpzdrz, dppdrp=dppdrp, T=T, v=v,
+                          msq=msq, vw=vw, statistics=self.stat, collision=self.coll, collisionMultiplier=mult)
+
+    def assemble(self, vw, collisionMultiplier=1.0, parts=3, A=None):
+        self.pb = self._problem(vw, collisionMultiplier)
+        op, src = bo.assemble(self.pb)
+        self.A, self.S = _NP(op), _NP(src.copy())
+        return self.A
+
+    def factor(self):
+        pass
+
+    def solve(self, b=None):
+        b = self.S if b is None else b
+        b.arr[...] = np.linalg.solve(self.A.arr, b.arr)
+        return b
+
+    def info(self):
+        return 0
+
+    def spectra_async(self, dF):
+        self._dF = np.array(dF.arr if isinstance(dF, _NP) else dF).reshape(self.P, self.M1, self.N1, self.N1)
+        c = np.abs(bo.to_chebyshev(self._dF, self.tab))
+        self._spectra = np.concatenate([c.sum(axis=(0, 2, 3)), c.sum(axis=(0, 1, 3)), c.sum(axis=(0, 1, 2))])
+
+    def spectra_to_host(self):
+        return self._spectra.copy()
+
+    def moments_async(self, dF, keep, roundtrip):
+        c = bo.to_chebyshev(self._dF, self.tab).copy()
+        c[:, keep[0]:] = 0
+        c[:, :, keep[1]:] = 0
+        c[:, :, :, keep[2]:] = 0
+        a = np.abs(c)
+        err = np.stack([a.sum(axis=(1, 2, 3)), a[:, keep[0] - 1].sum(axis=(1, 2)),
+                        a[:, :, keep[1] - 1].sum(axis=(1, 2)), a[:, :, :, keep[2] - 1].sum(axis=(1, 2))], axis=1)
+        dFo = bo.from_chebyshev(c, self.tab) if roundtrip else self._dF
+        pb = self._problem(0.0, 1.0)
+        self._out = (np.array(dFo), bo.moments(dFo, pb), err)
+
+    def results_to_host(self):
+        return self._out

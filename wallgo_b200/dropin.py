@@ -25,11 +25,12 @@ def makeDropInClass():
     import WallGo  # pylint: disable=import-outside-toplevel
     from WallGo.boltzmann import BoltzmannSolver as _RefSolver, ETruncationOption
     from WallGo.collisionArray import CollisionArray
+    import WallGo.results  # noqa: F401  pylint: disable=import-outside-toplevel
 
     class _WallGoTypes:
         Polynomial = WallGo.Polynomial
         BoltzmannDeltas = WallGo.BoltzmannDeltas
-        BoltzmannResults = WallGo.BoltzmannResults
+        BoltzmannResults = WallGo.results.BoltzmannResults
 
     class B200BoltzmannSolver(BoltzmannSolverB200Mixin, _RefSolver):
         """WallGo.BoltzmannSolver with every numerical step on a B200."""
