@@ -118,18 +118,38 @@ def cpu_port_one_solve(grid, particles, coll, bg):
                     msq=np.array([p.msqVacuum(b.fieldProfiles) for p in particles]), vw=float(b.velocityWall),
                     statistics=np.array([-1.0 if p.statistics == "Fermion" else 1.0 for p in particles]),
                     collision=np.asarray(coll[...]), collisionMultiplier=1.0)
-    t0 = time.perf_counter()
-    op, src = bo.assemble(pb)
-    t1 = time.perf_counter()
-    dF = np.linalg.solve(op, src).reshape(len(particles), grid.M - 1, grid.N - 1, grid.N - 1)
-    t2 = time.perf_counter()
-    del op
-    out = bo.get_deltas(pb, dF, "AUTO")
-    t3 = time.perf_counter()
+    # all host cores for BLAS, even under torchrun (which exports OMP_NUM_THREADS=1)
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        limiter = None
+    try:
+        t0 = time.perf_counter()
+        op, src = bo.assemble(pb)
+        t1 = time.perf_counter()
+        dF = np.linalg.solve(op, src).reshape(len(particles), grid.M - 1, grid.N - 1, grid.N - 1)
+        t2 = time.perf_counter()
+        del op
+        out = bo.get_deltas(pb, dF, "AUTO")
+        t3 = time.perf_counter()
+    finally:
+        if limiter is not None:
+            limiter.restore_original_limits()
     return dict(assemble_s=t1 - t0, dgesv_s=t2 - t1, moments_s=t3 - t2, total_s=t3 - t0), out
 
 
 def blas_info():
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        with threadpool_limits(limits=os.cpu_count()):
+            return ";".join(f"{d.get('internal_api')} {d.get('version')} threads={d.get('num_threads')}"
+                            for d in threadpool_info())
+    except Exception:
+        return "unknown"
+
+
+def _blas_info_unused():
     try:
         from threadpoolctl import threadpool_info
         return ";".join(f"{d.get('internal_api')} {d.get('version')} threads={d.get('num_threads')}"
@@ -367,6 +387,12 @@ def main():
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
     if a.impl == "reference":
+        # torchrun exports OMP_NUM_THREADS=1; the CPU arm must use every host core, and BLAS reads the
+        # variable when it is loaded, so restart this process once with the limit lifted.
+        if os.environ.get("OMP_NUM_THREADS") and not os.environ.get("WG_REF_REEXEC"):
+            env = dict(os.environ, WG_REF_REEXEC="1", OMP_NUM_THREADS=str(os.cpu_count()),
+                       OPENBLAS_NUM_THREADS=str(os.cpu_count()))
+            os.execve(sys.executable, [sys.executable] + sys.argv, env)
         run_reference(a)
     else:
         run_b200(a)
