@@ -204,3 +204,29 @@ def test_singular_operator_raises(cuda_device):
     eng.A.zero_()
     eng.factor()
     assert eng.info() == 1
+
+
+def test_getDeltasBatch_equals_sequential(cuda_device):
+    """Several independent systems in flight on one GPU give exactly the sequential results, in order."""
+    import wallgo_b200 as wb
+    from wallgo_b200 import synthetic
+
+    P, M, N = 2, 12, 7
+    grid = synthetic.makeGrid(M, N)
+    parts = synthetic.makeParticles(P)
+    solver = wb.BoltzmannSolver(grid)
+    solver.updateParticleList(parts)
+    solver.setCollisionArray(synthetic.makeCollision(grid, parts))
+    bgs = [synthetic.makeBackground(grid, velocityMid=-0.3 - 0.05 * i) for i in range(7)]
+    seq = []
+    for bg in bgs:
+        solver.setBackground(bg)
+        seq.append(solver.getDeltas())
+    for conc in (1, 2, 3):
+        out = solver.getDeltasBatch(bgs, concurrency=conc)
+        assert len(out) == len(bgs)
+        for a, b in zip(seq, out):
+            assert np.array_equal(a.deltaF, b.deltaF)
+            assert np.array_equal(a.Deltas.Delta11.coefficients, b.Deltas.Delta11.coefficients)
+            assert a.truncatedTail == b.truncatedTail and a.spectralPeaks == b.spectralPeaks
+    assert solver.getDeltasBatch([], concurrency=2) == []

@@ -80,6 +80,8 @@ class BoltzmannSolverB200Mixin:
         st = dict(self.__dict__)
         st["_engine"] = None
         st["_staticKey"] = None
+        st["_sibs"] = None
+        st["_stream"] = None
         return st
 
     def __deepcopy__(self, memo):
@@ -87,7 +89,7 @@ class BoltzmannSolverB200Mixin:
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_engine", "_staticKey"):
+            if k in ("_engine", "_staticKey", "_sibs", "_stream"):
                 setattr(new, k, None)
             elif k == "grid":
                 setattr(new, k, deepcopy(v, memo))
@@ -261,6 +263,108 @@ class BoltzmannSolverB200Mixin:
             info = eng.info()
             if info != 0:
                 raise np.linalg.LinAlgError("Singular matrix")
+        return self._wrapResults(dF, deltas, err, keep, peaks)
+
+    # ------------------------------------------------------------------ batches of independent systems
+    def _siblings(self, count):
+        """This solver plus (count-1) shallow clones, each with its own engine, operator buffer and CUDA
+        stream; grid, particles and collision tensor are shared (read-only while a batch runs)."""
+        import copy
+
+        sibs = getattr(self, "_sibs", None)
+        if sibs is None or len(sibs) < count:
+            sibs = [self] if sibs is None else sibs
+            while len(sibs) < count:
+                c = copy.copy(self)
+                c._engine, c._staticKey, c._sibs, c._stream = None, None, None, None
+                sibs.append(c)
+            self._sibs = sibs
+        for s_ in sibs[:count]:
+            s_.basisM, s_.basisN, s_.derivatives = self.basisM, self.basisN, self.derivatives
+            s_.collisionMultiplier, s_.truncationOption = self.collisionMultiplier, self.truncationOption
+            s_.collisionArray, s_.offEqParticles, s_.grid = self.collisionArray, self.offEqParticles, self.grid
+        return sibs[:count]
+
+    def getDeltasBatch(self, backgrounds, concurrency: int = 2):
+        """getDeltas() for a list of independent backgrounds (wall-velocity scan points, parameter points),
+        `concurrency` systems in flight on this GPU.  Each system is solved exactly as getDeltas() would;
+        the slots are staggered so that the latency-bound end of one LU overlaps the GEMM-rich start of
+        the next.  Returns the BoltzmannResults in input order."""
+        import time
+
+        nItems = len(backgrounds)
+        if nItems == 0:
+            return []
+        C = max(1, min(int(concurrency), nItems))
+        sibs = self._siblings(C)
+        torch = sibs[0]._getEngine().torch
+        for s_ in sibs:
+            eng = s_._getEngine()
+            if getattr(s_, "_stream", None) is None:
+                s_._stream = torch.cuda.Stream(device=eng.dev)
+        results = [None] * nItems
+        n = sibs[0]._getEngine().n
+        stagger = (2.0 / 3.0) * float(n) ** 3 / 20e12 / C   # rough LU time / C
+        nextItem = 0
+        state = [None] * C       # per slot: (item, phase, event, aux)
+
+        def start(slot):
+            nonlocal nextItem
+            if nextItem >= nItems:
+                state[slot] = None
+                return
+            it = nextItem
+            nextItem += 1
+            s_ = sibs[slot]
+            with torch.cuda.stream(s_._stream):
+                s_.setBackground(backgrounds[it])
+                eng = s_._solveOnDevice()
+                eng.spectra_async(eng.S)
+                eng.spectra_host.copy_(eng.spectra, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_._stream)
+            state[slot] = (it, 0, ev)
+
+        def advance(slot):
+            it, phase = state[slot][0], state[slot][1]
+            s_ = sibs[slot]
+            eng = s_._engine
+            if phase == 0:
+                keep, peaks = s_._decideTruncation(eng.spectra_host.numpy().copy())
+                with torch.cuda.stream(s_._stream):
+                    eng.moments_async(eng.S, keep, s_.truncationOption.name != "NONE")
+                    eng.out_host.copy_(eng.out, non_blocking=True)
+                    ev2 = torch.cuda.Event()
+                    ev2.record(s_._stream)
+                state[slot] = (it, 1, ev2, keep, peaks)
+            else:
+                _, _, _, keep, peaks = state[slot]
+                if eng.info() != 0:
+                    raise np.linalg.LinAlgError("Singular matrix")
+                h = eng.out_host.numpy()
+                pm = 4 * eng.P * eng.M1
+                dF = h[:eng.n].reshape(eng.P, eng.M1, eng.N1, eng.N1).copy()
+                deltas = h[eng.n:eng.n + pm].reshape(4, eng.P, eng.M1).copy()
+                err = h[eng.n + pm:].reshape(eng.P, 4).copy()
+                results[it] = s_._wrapResults(dF, deltas, err, keep, peaks)
+                start(slot)
+
+        for slot in range(C):
+            if slot > 0:
+                time.sleep(stagger)
+            start(slot)
+        while any(st is not None for st in state):
+            progressed = False
+            for slot in range(C):
+                if state[slot] is not None and state[slot][2].query():
+                    advance(slot)
+                    progressed = True
+            if not progressed:
+                oldest = min((st[0], k) for k, st in enumerate(state) if st is not None)[1]
+                state[oldest][2].synchronize()
+        return results
+
+    def _wrapResults(self, dF, deltas, err, keep, peaks):
         g = self.grid
         M1, N1 = g.M - 1, g.N - 1
         truncationError = float(np.max(err[:, 1:] / err[:, :1]))
