@@ -280,9 +280,14 @@ def run_b200(a):
     torch.cuda.synchronize()
     nsolo = min(3, K)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(nsolo)]
+    import ctypes as C
+    gms, gfl, gcnt = C.c_double(0), C.c_double(0), C.c_int(0)
+    lib.wg_profile_gemm(engines[0].h, 1, None, None, None)       # bracket the trailing-update GEMMs with events
     for i in range(nsolo):
         step(engines[0], W + i, evs[i])
     torch.cuda.synchronize()
+    lib.wg_profile_gemm(engines[0].h, 0, C.byref(gms), C.byref(gfl), C.byref(gcnt))
+    gemm_tf = gfl.value / (gms.value * 1e-3) / 1e12 if gms.value > 0 else float("nan")
     stage = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(4)] for e in evs]).mean(axis=0)
 
     pm = 4 * P * (M - 1)
@@ -373,7 +378,18 @@ def run_b200(a):
                                "spectra_moments": stage[3], "lu_tflops_solo": lu_tf_solo,
                                "note": "one system alone on the GPU, CUDA events around each stage"},
             "latency_ms_sequential_getDeltas": seq_ms,
-            "roofline": {"kernel": "blocked LU (DMMA GEMM trailing update dominates)", "bound": "tensor",
+            "roofline": {"kernel": "dgemm_sub_kernel<128,64,16,2,2,3> (trailing update of the LU, DMMA.8x8x4)",
+                         "bound": "tensor", "achieved": gemm_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": gemm_tf / fp64_peak,
+                         "traffic": 4.24e9 if (P, M, N) == (1, 40, 21) else None,
+                         "launches_timed": gcnt.value, "ms_timed": gms.value,
+                         "algorithmic": "2*M*N*K flops of every trailing-update launch / its CUDA-event duration on the "
+                                        "launching stream, summed over the solo pass (look-ahead panels run beside it); "
+                                        "traffic = dram read+write of the first-step launch (15344^2 x 256) from "
+                                        "profiles/r01_ncu_full_dgemm_128x64_2cta.csv vs 3.83e9 algorithmic",
+                         "peak_source": "measured in this run: torch.matmul (cuBLAS DGEMM) fp64 8192^3 best of 5; "
+                                        "MEASURED_PEAKS.json has no FP64 entry"},
+            "roofline_lu": {"kernel": "whole blocked LU (all kernels)", "bound": "tensor",
                          "achieved": lu_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": lu_tf / fp64_peak,
                          "traffic": None,
                          "peak_source": "measured in this run: torch.matmul (cuBLAS DGEMM) fp64 8192^3 best of 5; "
@@ -381,7 +397,8 @@ def run_b200(a):
                          "algorithmic": "steps * 2/3 n^3 LU flops / CUDA-event duration of the whole timed region "
                                         "(assembly, solves and moments count as overhead)"},
             "roofline_assembly": {"kernel": "wg_assemble_kernel", "bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak,
-                                  "unit": "GB/s", "frac": asm_gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                                  "unit": "GB/s", "frac": asm_gbs / hbm_peak,
+                                  "traffic": 1.921e9 if (P, M, N) == (1, 40, 21) else None, "peak_source": hbm_src,
                                   "algorithmic": "8n^2+8n bytes written per solve / mean CUDA-event time of wg_assemble"},
             "e2e": {"value": e2e, "unit": "solves/s", "h2d_bytes_per_step": int(nprof * 8),
                     "d2h_bytes_per_step": int((eng.nspec + eng.nout) * 8 + 4)},

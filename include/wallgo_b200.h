@@ -100,10 +100,25 @@ int wg_spectra(wg_solver* s, const double* deltaF_dev, double* spectra_dev, void
 int wg_moments(wg_solver* s, const double* deltaF_dev, const double* profiles_dev, int keepM, int keepPz,
                int keepPp, int roundtrip, double* deltaF_out_dev, double* deltas_dev, double* err_dev,
                void* stream);
+/* totalDOFs of each species (host, P doubles), used by wg_feedback */
+int wg_set_dofs(wg_solver* s, const double* dofs);
+/* Feedback of the moments into the wall equation of motion, on the device:
+ *   out_dev = [ T30_out (M-1) | T33_out (M-1) | potentialOut (M-1) | dVout ((M-1) x nFields) ]
+ * T30/T33: EOM.deltaToTmunu (equationOfMotion.py:2021-2127) for every interior z at once;
+ * potentialOut = 1/2 sum_a dof_a m2_a Delta00_a (:1545-1555); dVout = 1/2 sum_a dof_a dm2_a/dphi Delta00_a
+ * (:1418-1429).  deltas_dev as written by wg_moments; dmsq_dphi_dev[P][M-1][nFields] = Particle.msqDerivative
+ * on the interior points (may be NULL when nFields == 0). */
+int wg_feedback(wg_solver* s, const double* deltas_dev, const double* profiles_dev, const double* dmsq_dphi_dev,
+                int nFields, double velocityMid, double* out_dev, void* stream);
 /* y = (collision part of the last assembled operator) * x   (boltzmann.py:541-545) */
 int wg_collision_apply(wg_solver* s, const double* x_dev, double* y_dev, void* stream);
 /* in-place basis change of a (P, M-1, N-1, N-1) array with the matrices of wg_set_transforms */
 int wg_change_basis(wg_solver* s, int stage, const double* in_dev, double* out_dev, void* stream);
+
+/* Live timing of the dominant kernel (trailing-update GEMM of wg_factor) with CUDA events on the
+ * launching stream.  enable != 0 switches bracketing on for later wg_factor calls; every call returns
+ * and resets the sums of the launches bracketed so far (synchronise the stream first). */
+int wg_profile_gemm(wg_solver* s, int enable, double* ms, double* flops, int* count);
 
 /* ---- generic dense pieces (used by the solver; exported for tests and other callers) */
 int wg_lu_create(int n, int device, wg_lu** out);

@@ -531,6 +531,25 @@ def check_linearization(pb: Problem, dF=None):
     return abs(pDf / pEq), abs(pNl / (pEq + pDf))
 
 
+def feedback(Deltas, msq_interior, dofs, velocityMid, dmsq=None):
+    """Moment feedback into the wall EOM: T30_out, T33_out per z (EOM.deltaToTmunu,
+    equationOfMotion.py:2064-2125), potentialOut (:1545-1555), dVout (:1418-1429).
+    Deltas [4,P,M-1] = (D00,D02,D20,D11); msq_interior [P,M-1]; dmsq [P,M-1,F] or None."""
+    D00, D02, D20, D11 = Deltas
+    u0 = np.sqrt(1.0 / (1.0 - velocityMid * velocityMid))
+    u3 = u0 * velocityMid
+    ub0, ub3 = u3, u0
+    dof = np.asarray(dofs, dtype=float)[:, None]
+    A1 = 3 * D20 - D02 - msq_interior * D00
+    A2 = 3 * D02 - D20 + msq_interior * D00
+    T30 = np.sum(dof * (A1 * u3 * u0 + A2 * ub3 * ub0 + 2 * D11 * (u3 * ub0 + ub3 * u0)) / 2.0, axis=0)
+    T33 = np.sum(dof * ((A1 * u3 * u3 + A2 * ub3 * ub3 + 4 * D11 * u3 * ub3) / 2.0
+                        - (msq_interior * D00 + D02 - D20) / 2.0), axis=0)
+    pot = np.sum(dof * msq_interior * D00, axis=0) / 2
+    dV = None if dmsq is None else np.sum(dof[:, :, None] * dmsq * D00[:, :, None], axis=0) / 2
+    return T30, T33, pot, dV
+
+
 # --------------------------------------------------------------------------
 # Deterministic synthetic problems (SURVEY.md section 8d)
 # --------------------------------------------------------------------------

@@ -54,7 +54,7 @@ def make_reference_solver(P, M, N, basisM, basisN, derivatives, option, r, seed,
         particles.append(WallGo.Particle(
             name=f"p{a}", index=a,
             msqVacuum=(lambda f, a=a: 0.5 * (1 + 0.3 * a) * f.getField(0) ** 2),
-            msqDerivative=(lambda f, a=a: (1 + 0.3 * a) * f.getField(0)),
+            msqDerivative=(lambda f, a=a: np.transpose([(1 + 0.3 * a) * f.getField(0)])),
             statistics="Fermion" if a % 2 == 0 else "Boson", totalDOFs=12))
     bg = WallGo.BoltzmannBackground(-0.5, v, WallGo.Fields(phi[:, None]), T)
     solver = WallGo.BoltzmannSolver(grid, basisM, basisN, derivatives, mult,
@@ -115,6 +115,23 @@ def one_case(name, P, M, N, basisM="Cardinal", basisN="Chebyshev", derivatives="
     checks["truncErr"] = abs(ores["truncationError"] - res.truncationError) / max(res.truncationError, 1e-300)
     assert tuple(ores["truncatedTail"]) == tuple(res.truncatedTail), (ores["truncatedTail"], res.truncatedTail)
     assert tuple(ores["spectralPeaks"]) == tuple(res.spectralPeaks), (ores["spectralPeaks"], res.spectralPeaks)
+    # --- moment feedback into the wall EOM: the reference's own EOM.deltaToTmunu, called unbound (it only
+    #     reads self.particles), plus the two inline source terms of equationOfMotion.py:1418-1429, 1545-1555
+    from WallGo.equationOfMotion import EOM
+    stub = types.SimpleNamespace(particles=particles)
+    fld = solver.background.fieldProfiles
+    vmid = float(solver.background.velocityMid)
+    tm = np.array([EOM.deltaToTmunu(stub, i, fld.getFieldPoint(i + 1), vmid, res.Deltas) for i in range(M - 1)])
+    fint = fld.takeSlice(1, -1, axis=fld.overFieldPoints)
+    potOut = sum(p.totalDOFs * p.msqVacuum(fint) * res.Deltas.Delta00.coefficients[i]
+                 for i, p in enumerate(particles)) / 2
+    dVout = np.sum([p.totalDOFs * p.msqDerivative(fint) * res.Deltas.Delta00.coefficients[i, :, None]
+                    for i, p in enumerate(particles)], axis=0) / 2
+    dmsqInt = np.stack([np.asarray(p.msqDerivative(fint)) for p in particles])
+    msqInt = np.array([p.msqVacuum(fint) for p in particles])
+    oT30, oT33, oPot, odV = bo.feedback(refD, msqInt, [p.totalDOFs for p in particles], vmid, dmsqInt)
+    checks["T30"], checks["T33"] = rel(oT30, tm[:, 0]), rel(oT33, tm[:, 1])
+    checks["potOut"], checks["dVout"] = rel(oPot, potOut), rel(odV, dVout)
     lin = None
     if linearization:
         lin = solver.checkLinearization(dF.copy())
@@ -149,6 +166,8 @@ def one_case(name, P, M, N, basisM="Cardinal", basisN="Chebyshev", derivatives="
         ref_source=src, ref_deltaF=dF, ref_deltaF_trunc=res.deltaF, ref_Deltas=refD,
         ref_truncationError=res.truncationError,
         ref_truncatedTail=np.array(res.truncatedTail), ref_spectralPeaks=np.array(res.spectralPeaks),
+        velocityMid=vmid, dmsq_interior=dmsqInt, ref_T30=tm[:, 0], ref_T33=tm[:, 1], ref_potOut=np.asarray(potOut),
+        ref_dVout=np.asarray(dVout),
         ref_op_rowsum=op @ ones, ref_op_colsum=op.T @ ones,
         ref_op_diag=np.diag(op).copy(),
         ref_op_probe_rows=np.array([0, op.shape[0] // 3, op.shape[0] - 1]),

@@ -52,8 +52,13 @@ class FixtureGrid:
 class FixtureFields:
     """Stand-in for WallGo.Fields: msq is taken from the golden file, not recomputed."""
 
-    def __init__(self, msq):
+    def __init__(self, msq, dmsq_interior=None):
         self.msq = msq
+        self.dmsq = None
+        if dmsq_interior is not None:   # [P, M-1, F] -> padded to the M+1 profile points
+            P, m1, F = dmsq_interior.shape
+            self.dmsq = np.zeros((P, m1 + 2, F))
+            self.dmsq[:, 1:-1] = dmsq_interior
 
 
 class FixtureBackground:
@@ -63,8 +68,8 @@ class FixtureBackground:
         self.velocityWall = float(g["vw"])
         self.velocityProfile = g["v"]
         self.temperatureProfile = g["T"]
-        self.fieldProfiles = FixtureFields(g["msq"])
-        self.velocityMid = 0.0
+        self.fieldProfiles = FixtureFields(g["msq"], g.get("dmsq_interior"))
+        self.velocityMid = float(g["velocityMid"]) if "velocityMid" in g else 0.0
 
     def boostToPlasmaFrame(self):
         pass
@@ -76,7 +81,8 @@ def solver_from_golden(g, device=0):
 
     grid = FixtureGrid(g)
     P = int(g["P"])
-    particles = [wb.Particle(f"p{a}", a, (lambda f, a=a: f.msq[a]), None,
+    particles = [wb.Particle(f"p{a}", a, (lambda f, a=a: f.msq[a]),
+                             ((lambda f, a=a: f.dmsq[a]) if "dmsq_interior" in g else None),
                              "Fermion" if g["statistics"][a] < 0 else "Boson", int(g["dofs"][a]))
                  for a in range(P)]
     solver = wb.BoltzmannSolver(grid, str(g["basisM"]), str(g["basisN"]), str(g["derivatives"]),

@@ -79,6 +79,9 @@ class FakeEngine:
     def set_statistics(self, s):
         self.stat = np.array(s, dtype=float)
 
+    def set_dofs(self, d):
+        self.dofs = np.array(d, dtype=float)
+
     def build_basis(self):
         self.tab = bo.build_tables(self.M, self.N, "Cardinal", "Chebyshev", "Spectral")
 

@@ -32,6 +32,10 @@ def test_oracle_reproduces_reference_golden(name):
     assert relmax(out["Deltas"], g["ref_Deltas"]) < 1e-12
     assert relmax(out["deltaF"], g["ref_deltaF_trunc"]) < 1e-12
     assert abs(out["truncationError"] - float(g["ref_truncationError"])) < 1e-9 * float(g["ref_truncationError"])
+    T30, T33, pot, dV = bo.feedback(g["ref_Deltas"], g["msq"][:, 1:-1], g["dofs"], float(g["velocityMid"]),
+                                    g["dmsq_interior"])
+    assert relmax(T30, g["ref_T30"]) < 1e-13 and relmax(T33, g["ref_T33"]) < 1e-13
+    assert relmax(pot, g["ref_potOut"]) < 1e-13 and relmax(dV, g["ref_dVout"]) < 1e-13
     if "ref_linearization" in g:
         c1, c2 = bo.check_linearization(pb, g["ref_deltaF"])
         assert abs(c1 - g["ref_linearization"][0]) < 1e-9 * abs(g["ref_linearization"][0])

@@ -85,6 +85,22 @@ def test_getDeltas_matches_reference(cuda_device, name):
     assert relmax(res2.deltaF, g["ref_deltaF_trunc"]) < 1e-12
 
 
+@pytest.mark.parametrize("name", golden_names())
+def test_feedback_matches_reference(cuda_device, name):
+    """Device feedback kernel vs the reference's own EOM.deltaToTmunu and EOM source terms, computed from
+    the reference's Deltas (isolates the kernel) and from the device solve (the production sequence)."""
+    g = load_golden(name)
+    solver = solver_from_golden(g)
+    solver.getDeltas(g["ref_deltaF"])
+    fb = solver.getFeedback()
+    for key, ref in (("T30", "ref_T30"), ("T33", "ref_T33"), ("potentialOut", "ref_potOut"), ("dVout", "ref_dVout")):
+        assert relmax(fb[key], g[ref]) < 1e-12, (name, key)
+    solver.getDeltas()
+    fb = solver.getFeedback()
+    for key, ref in (("T30", "ref_T30"), ("T33", "ref_T33"), ("potentialOut", "ref_potOut"), ("dVout", "ref_dVout")):
+        assert relmax(fb[key], g[ref]) < 1e-10, (name, key)
+
+
 @pytest.mark.parametrize("name", ["tiny_P1_M6_N5", "small_P2_M12_N7"])
 def test_checkLinearization_matches_reference(cuda_device, name):
     g = load_golden(name)

@@ -36,6 +36,9 @@ SYMBOLS = {
     "wg_info": (C.c_int, [_vp, _vp, C.POINTER(C.c_int)]),
     "wg_spectra": (C.c_int, [_vp, _dp, _dp, _vp]),
     "wg_moments": (C.c_int, [_vp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _vp]),
+    "wg_profile_gemm": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "wg_set_dofs": (C.c_int, [_vp, _hd]),
+    "wg_feedback": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int, C.c_double, _dp, _vp]),
     "wg_collision_apply": (C.c_int, [_vp, _dp, _dp, _vp]),
     "wg_change_basis": (C.c_int, [_vp, C.c_int, _dp, _dp, _vp]),
     "wg_lu_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(_vp)]),

@@ -125,6 +125,7 @@ class BoltzmannSolverB200Mixin:
             _, pz, pp = g.getCoordinates()
             eng.set_grid(chi, rz, rp, pz, pp, dpzdrz, dppdrp)
             eng.set_statistics(np.array(stats))
+            eng.set_dofs(np.array([float(p.totalDOFs) for p in self.offEqParticles]))
             if (self.basisM, self.basisN, self.derivatives) == ("Cardinal", "Chebyshev", "Spectral"):
                 eng.build_basis()
             else:
@@ -264,6 +265,21 @@ class BoltzmannSolverB200Mixin:
             if info != 0:
                 raise np.linalg.LinAlgError("Singular matrix")
         return self._wrapResults(dF, deltas, err, keep, peaks)
+
+    def getFeedback(self):
+        """Out-of-equilibrium source terms of the wall EOM computed on the device from the moments of the
+        LAST getDeltas() call: dict with T30, T33 (EOM.deltaToTmunu, equationOfMotion.py:2021-2127, all
+        interior z at once), potentialOut (:1545-1555) and dVout (:1418-1429)."""
+        eng = self._getEngine()
+        bg = self.background
+        fields = bg.fieldProfiles
+        dmsq = None
+        if all(getattr(p, "msqDerivative", None) is not None for p in self.offEqParticles):
+            vals = [np.asarray(p.msqDerivative(fields), dtype=np.float64) for p in self.offEqParticles]
+            vals = [v.reshape(v.shape[0], -1) for v in vals]
+            dmsq = np.stack([v[1:-1] for v in vals])          # [P, M-1, F]
+        t30, t33, pot, dv = eng.feedback(dmsq, float(bg.velocityMid))
+        return dict(T30=t30, T33=t33, potentialOut=pot, dVout=dv)
 
     # ------------------------------------------------------------------ batches of independent systems
     def _siblings(self, count):

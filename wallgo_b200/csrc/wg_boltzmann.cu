@@ -378,7 +378,48 @@ __global__ void wg_collision_matvec_kernel(BzDims d, const double* __restrict__ 
   if (lane == 0) y[warp] = cT2[al] * s;
 }
 
+// Feedback of the moments into the wall equation of motion (consumers in equationOfMotion.py):
+//   T30_out, T33_out per z  : EOM.deltaToTmunu (equationOfMotion.py:2064-2125)
+//   potOut = 1/2 sum_a dof_a m2_a Delta00_a              : action term (:1545-1555)
+//   dVout[f] = 1/2 sum_a dof_a dm2_a/dphi_f Delta00_a     : EOM source term (:1418-1429)
+// out layout: [T30 (M1) | T33 (M1) | potOut (M1) | dVout (M1 x F)]
+__global__ void wg_feedback_kernel(BzDims d, const double* __restrict__ deltas, const double* __restrict__ prof,
+                                   const double* __restrict__ dofs, const double* __restrict__ dmsq, int F,
+                                   double u0, double u3, double* __restrict__ out) {
+  const int al = blockIdx.x * blockDim.x + threadIdx.x;
+  if (al >= d.M1) return;
+  const int PM = d.P * d.M1, L = d.M + 1;
+  const double ub0 = u3, ub3 = u0;
+  double t30 = 0.0, t33 = 0.0, pot = 0.0;
+  for (int a = 0; a < d.P; ++a) {
+    const int o = a * d.M1 + al;
+    const double D00 = deltas[o], D02 = deltas[PM + o], D20 = deltas[2 * PM + o], D11 = deltas[3 * PM + o];
+    const double msq = prof[(2 + a) * L + al + 1];
+    const double dof = dofs[a];
+    const double A1 = 3.0 * D20 - D02 - msq * D00;
+    const double A2 = 3.0 * D02 - D20 + msq * D00;
+    t30 += dof * (A1 * u3 * u0 + A2 * ub3 * ub0 + 2.0 * D11 * (u3 * ub0 + ub3 * u0)) / 2.0;
+    t33 += dof * ((A1 * u3 * u3 + A2 * ub3 * ub3 + 4.0 * D11 * u3 * ub3) / 2.0 - (msq * D00 + D02 - D20) / 2.0);
+    pot += dof * msq * D00;
+  }
+  out[al] = t30;
+  out[d.M1 + al] = t33;
+  out[2 * d.M1 + al] = pot / 2.0;
+  for (int f = 0; f < F; ++f) {
+    double sacc = 0.0;
+    for (int a = 0; a < d.P; ++a) sacc += dofs[a] * dmsq[((long long)a * d.M1 + al) * F + f] * deltas[a * d.M1 + al];
+    out[3 * d.M1 + al * F + f] = sacc / 2.0;
+  }
+}
+
 // ============================================================================ host launchers
+int bz_feedback(const BzDims& d, const double* deltas, const double* prof, const double* dofs, const double* dmsq,
+                int F, double u0, double u3, double* out, cudaStream_t st) {
+  wg_feedback_kernel<<<wg_cdiv(d.M1, 64), 64, 0, st>>>(d, deltas, prof, dofs, dmsq, F, u0, u3, out);
+  WG_LAUNCH_CHECK();
+  return WG_OK;
+}
+
 int bz_build_basis(const BzDims& d, const double* rz, double* Tchi, double* Dchi, double* DchiFull,
                    double* Trz, double* Drz, double* Trp, cudaStream_t st) {
   wg_basis_kernel<<<8, 256, 0, st>>>(d.M, d.N, rz, Tchi, Dchi, DchiFull, Trz, Drz, Trp);

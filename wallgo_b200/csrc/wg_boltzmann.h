@@ -35,6 +35,8 @@ int bz_spectra(const BzDims& d, const double* c, double* spectra, cudaStream_t s
 int bz_truncate(const BzDims& d, double* c, int keepM, int keepN1, int keepN2, double* err, cudaStream_t st);
 int bz_moments(const BzDims& d, const BzStatic& s, const double* card, const double* prof, double* deltas,
                cudaStream_t st);
+int bz_feedback(const BzDims& d, const double* deltas, const double* prof, const double* dofs, const double* dmsq,
+                int F, double u0, double u3, double* out, cudaStream_t st);
 int bz_collision_matvec(const BzDims& d, const BzStatic& s, const double* cT2, const double* x, double* y,
                         cudaStream_t st);
 

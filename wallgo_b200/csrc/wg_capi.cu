@@ -1,4 +1,5 @@
 // extern "C" boundary of libwallgo_b200.so (see include/wallgo_b200.h).
+#include <math.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -33,6 +34,7 @@ struct wg_solver {
   double *derivs = nullptr, *w1 = nullptr, *w2 = nullptr, *cT2 = nullptr;
   double *cheb = nullptr, *bufA = nullptr, *bufB = nullptr;
   int *ipiv = nullptr, *info = nullptr;
+  double* dofs = nullptr;
   wg::LuPlan* plan = nullptr;
   bool haveGrid = false, haveTables = false, haveColl = false, haveStat = false, assembled = false;
 };
@@ -77,6 +79,11 @@ int wg_debug_gemm_variant(int v) {
   wg::gemm_set_variant(v);
   return WG_OK;
 }
+int wg_profile_gemm(wg_solver* s, int enable, double* ms, double* flops, int* count) {
+  WG_REQUIRE(s, "wg_profile_gemm: NULL solver");
+  wg::lu_set_profile(enable);
+  return wg::lu_profile_read(s->plan, ms, flops, count);
+}
 int wg_set_lookahead(int on) {
   wg::lu_set_lookahead(on);
   return WG_OK;
@@ -116,7 +123,7 @@ int wg_create(int P, int M, int N, int device, wg_solver** out) {
   A_(s->st.Trz, N1 * N1) A_(s->st.Drz, N1 * N1) A_(s->st.Trp, N1 * N1)
   A_(s->st.K1, q * q) A_(s->st.K2, q * q) A_(s->st.Coll, (size_t)P * q * P * q)
   A_(s->derivs, (size_t)(2 + P) * (M + 1)) A_(s->w1, n) A_(s->w2, n) A_(s->cT2, M1)
-  A_(s->cheb, n) A_(s->bufA, n) A_(s->bufB, n) A_(s->ipiv, n) A_(s->info, (size_t)1)
+  A_(s->cheb, n) A_(s->bufA, n) A_(s->bufB, n) A_(s->ipiv, n) A_(s->info, (size_t)1) A_(s->dofs, (size_t)P)
 #undef A_
   WG_CUDA(cudaMemset(s->info, 0, sizeof(int)));
   rc = wg::lu_plan_create(d.n, &s->plan);
@@ -176,6 +183,23 @@ int wg_set_statistics(wg_solver* s, const double* statistics) {
   if (rc) return rc;
   s->haveStat = true;
   return WG_OK;
+}
+
+int wg_set_dofs(wg_solver* s, const double* dofs) {
+  WG_REQUIRE(s, "wg_set_dofs: NULL solver");
+  WG_CUDA(cudaSetDevice(s->device));
+  return h2d(s->dofs, dofs, s->d.P);
+}
+
+int wg_feedback(wg_solver* s, const double* deltas_dev, const double* profiles_dev, const double* dmsq_dphi_dev,
+                int nFields, double velocityMid, double* out_dev, void* stream) {
+  WG_REQUIRE(s && deltas_dev && profiles_dev && out_dev && nFields >= 0 && (nFields == 0 || dmsq_dphi_dev),
+             "wg_feedback: bad argument");
+  WG_REQUIRE(velocityMid > -1.0 && velocityMid < 1.0, "wg_feedback: |velocityMid| must be < 1");
+  const double u0 = sqrt(1.0 / (1.0 - velocityMid * velocityMid));  // helpers.gammaSq
+  const double u3 = u0 * velocityMid;
+  return wg::bz_feedback(s->d, deltas_dev, profiles_dev, s->dofs, dmsq_dphi_dev, nFields, u0, u3, out_dev,
+                         (cudaStream_t)stream);
 }
 
 int wg_build_basis(wg_solver* s) {

@@ -19,5 +19,7 @@ int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t
 void lu_set_tuning(int nb, int use_graph);
 void lu_set_debug(long long* dev_buf, int c0);
 void lu_set_lookahead(int on);
+void lu_set_profile(int on);
+int lu_profile_read(LuPlan* p, double* ms, double* flops, int* count);
 
 }  // namespace wg

@@ -42,6 +42,8 @@ void lu_set_debug(long long* buf, int c0) {
 static int g_nb = 256;
 static int g_use_graph = 0;
 static int g_lookahead = 1;
+static int g_profile = 0;
+void lu_set_profile(int on) { g_profile = on; }
 void lu_set_tuning(int nb, int use_graph) {
   if (nb >= 32 && nb <= 256 && nb % 16 == 0) g_nb = nb;
   g_use_graph = use_graph;
@@ -775,6 +777,10 @@ struct LuPlan {
   double *S = nullptr, *S2 = nullptr;
   cudaStream_t panelStream = nullptr;  // high priority: next panel overlaps the trailing update
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
+  // optional live timing of the trailing-update GEMM launches (bench roofline)
+  std::vector<cudaEvent_t> profEv;
+  std::vector<double> profFlops;
+  int profCount = 0;
   // CUDA-graph cache of the factorisation for one set of buffers
   cudaGraphExec_t exec = nullptr;
   long long graphLaunches = 0;
@@ -843,6 +849,7 @@ void lu_plan_destroy(LuPlan* p) {
   if (p->panelStream) cudaStreamDestroy(p->panelStream);
   if (p->evFork) cudaEventDestroy(p->evFork);
   if (p->evJoin) cudaEventDestroy(p->evJoin);
+  for (cudaEvent_t e : p->profEv) cudaEventDestroy(e);
   cudaFree(p->grpSrcTop);
   cudaFree(p->grpBDst);
   cudaFree(p->permSrcTop);
@@ -913,6 +920,41 @@ static int panel_rec(FactorCtx& c, int c0, int w, int pc0, int pc1) {
                  A + (long long)c0 * lda + c0 + w1, n - c0 - w1, w - w1, w1, lda, lda, lda, c.st);
   if (rc) return rc;
   return panel_rec(c, c0 + w1, w - w1, pc0, pc1);
+}
+
+// brackets one trailing-update GEMM with CUDA events when profiling is on (never during graph capture)
+static void prof_mark(LuPlan* p, cudaStream_t st, double flops, bool begin) {
+  if (!g_profile || g_use_graph) return;
+  const size_t idx = 2 * (size_t)p->profCount + (begin ? 0 : 1);
+  while (p->profEv.size() <= idx) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    p->profEv.push_back(e);
+  }
+  cudaEventRecord(p->profEv[idx], st);
+  if (begin) {
+    if (p->profFlops.size() <= (size_t)p->profCount) p->profFlops.resize(p->profCount + 1);
+    p->profFlops[p->profCount] = flops;
+  } else {
+    ++p->profCount;
+  }
+}
+
+// sums the bracketed launches since the last reset (caller has synchronised the stream)
+int lu_profile_read(LuPlan* p, double* ms, double* flops, int* count) {
+  double tms = 0.0, tfl = 0.0;
+  for (int i = 0; i < p->profCount; ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, p->profEv[2 * i], p->profEv[2 * i + 1]) == cudaSuccess) {
+      tms += t;
+      tfl += p->profFlops[i];
+    }
+  }
+  if (ms) *ms = tms;
+  if (flops) *flops = tfl;
+  if (count) *count = p->profCount;
+  p->profCount = 0;
+  return WG_OK;
 }
 
 static int panel_width_class(LuPlan* p, int m) {
@@ -987,13 +1029,17 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
       WG_LAUNCH_CHECK();
       WG_CUDA(cudaEventRecord(p->evJoin, p->panelStream));
       c.st = st;
+      prof_mark(p, st, 2.0 * rest * (double)(rest - nb2) * nb, true);
       rc = dgemm_sub(C22 + nb2, L21, U12 + nb2, rest, rest - nb2, nb, lda, lda, lda, st);
       if (rc) return rc;
+      prof_mark(p, st, 0.0, false);
       WG_CUDA(cudaStreamWaitEvent(st, p->evJoin, 0));
       panelDone = true;
     } else {
+      prof_mark(p, st, 2.0 * rest * (double)rest * nb, true);
       rc = dgemm_sub(C22, L21, U12, rest, rest, nb, lda, lda, lda, st);
       if (rc) return rc;
+      prof_mark(p, st, 0.0, false);
     }
   }
   return WG_OK;

@@ -87,6 +87,28 @@ class BoltzmannEngine:
         assert s.size == self.P
         check(self.lib.wg_set_statistics(self.h, host_ptr(s)), "wg_set_statistics")
 
+    def set_dofs(self, dofs):
+        d = np.ascontiguousarray(dofs, dtype=np.float64)
+        assert d.size == self.P
+        check(self.lib.wg_set_dofs(self.h, host_ptr(d)), "wg_set_dofs")
+
+    def feedback(self, dmsq, velocityMid: float):
+        """T30_out, T33_out, potentialOut [M-1] and dVout [M-1, F] from the device-resident Deltas of the
+        last moments call (one tiny upload of dm2/dphi, one tiny download)."""
+        torch = self.torch
+        n, pm = self.n, 4 * self.P * self.M1
+        F = 0 if dmsq is None else int(np.asarray(dmsq).shape[-1])
+        out = torch.empty((3 + F) * self.M1, dtype=torch.float64, device=self.dev)
+        dptr = 0
+        if F:
+            d = torch.from_numpy(np.ascontiguousarray(dmsq, dtype=np.float64).reshape(self.P, self.M1, F)).to(self.dev)
+            dptr = d.data_ptr()
+        check(self.lib.wg_feedback(self.h, self.out[n:].data_ptr(), self.prof.data_ptr(), dptr, F,
+                                   float(velocityMid), out.data_ptr(), self._stream()), "wg_feedback")
+        h = out.cpu().numpy()
+        M1 = self.M1
+        return h[:M1].copy(), h[M1:2 * M1].copy(), h[2 * M1:3 * M1].copy(), h[3 * M1:].reshape(M1, F).copy()
+
     def build_basis(self):
         check(self.lib.wg_build_basis(self.h), "wg_build_basis")
 
