@@ -209,7 +209,26 @@ def known_answer_delta00():
         assert err < 1e-14
 
 
+def interpolation_case(name, P, M, Nf, Nt, seed):
+    """CollisionArray.interpolateCollisionArray of the live reference (collisionArray.py:390-478)."""
+    gridF = WallGo.Grid(M, Nf, 0.05, 100.0)
+    gridT = WallGo.Grid(M, Nt, 0.05, 100.0)
+    parts = [WallGo.Particle(f"p{a}", a, lambda f: f.getField(0), lambda f: f.getField(0), "Fermion", 1)
+             for a in range(P)]
+    rng = np.random.default_rng(seed)
+    C = rng.standard_normal((P, Nf - 1, Nf - 1, P, Nf - 1, Nf - 1))
+    poly = Polynomial(C.copy(), gridF, ("Array", "Cardinal", "Cardinal", "Array", "Chebyshev", "Chebyshev"),
+                      CollisionArray.AXIS_TYPES, endpoints=False)
+    src = CollisionArray.newFromPolynomial(poly, parts)
+    out = CollisionArray.interpolateCollisionArray(src, gridT)
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), P=P, M=M, Nf=Nf, Nt=Nt, source=C,
+                        ref_interpolated=np.array(out[...]), basis=out.getBasisType())
+    print(f"{name:28s} interpolated {C.shape} -> {out[...].shape}")
+
+
 if __name__ == "__main__":
+    interpolation_case("interp_P1_N9_to_N5", 1, 6, 9, 5, 0)
+    interpolation_case("interp_P2_N7_to_N5", 2, 6, 7, 5, 1)
     known_answer_delta00()
     one_case("tiny_P1_M6_N5", 1, 6, 5, store_operator=True, linearization=True)
     one_case("small_P2_M12_N7", 2, 12, 7, linearization=True)

@@ -175,6 +175,21 @@ def test_host_collision_change_basis():
     assert ca.getBasisType() == "Cardinal" and ca.getBasisSize() == N - 1
 
 
+@pytest.mark.parametrize("name", ["interp_P1_N9_to_N5", "interp_P2_N7_to_N5"])
+def test_host_collision_interpolation_matches_reference(name):
+    """CollisionArray.interpolateCollisionArray vs the live reference's output (golden)."""
+    import wallgo_b200 as wb
+
+    g = load_golden(name)
+    P, M, Nf, Nt = int(g["P"]), int(g["M"]), int(g["Nf"]), int(g["Nt"])
+    src = wb.CollisionArray(wb.Grid(M, Nf, 0.05, 100.0), "Chebyshev", [None] * P, g["source"])
+    out = wb.CollisionArray.interpolateCollisionArray(src, wb.Grid(M, Nt, 0.05, 100.0))
+    assert out.getBasisType() == str(g["basis"]) and out[...].shape == g["ref_interpolated"].shape
+    assert relmax(out[...], g["ref_interpolated"]) < 1e-12
+    with pytest.raises(AssertionError):
+        wb.CollisionArray.interpolateCollisionArray(src, wb.Grid(M, Nf + 2, 0.05, 100.0))
+
+
 @pytest.mark.parametrize("name", golden_names())
 def test_host_truncation_decision(name):
     """The host half of checkSpectralConvergence, fed with spectra computed by the oracle."""

@@ -162,6 +162,45 @@ class CollisionArray:
     def getBasisType(self):
         return self.basisType
 
+    @staticmethod
+    def interpolateCollisionArray(srcCollision, targetGrid):
+        """Collision tensor computed on a finer momentum grid (N_f) brought to `targetGrid` (N <= N_f - 1):
+        the Chebyshev series in the polynomial axes is truncated and the collocation axes are evaluated at
+        the target nodes with the Lagrange cardinals of the source grid (reference
+        collisionArray.py:390-478, polynomial.py:300-443).  The result has the source's basis type.
+        Note: like the reference, the evaluated array (points, a, b, j, k) is reshaped without a transpose,
+        which is only an identity re-labelling for a single species."""
+        import copy
+
+        from .spectral import lobattoNodes
+
+        nT = targetGrid.N - 1
+        assert targetGrid.N <= srcCollision.getBasisSize(), (
+            f"CollisionArray interpolation error: target grid size ({targetGrid.N}) must be smaller than or "
+            f"equal to the source grid size ({srcCollision.getBasisSize() + 1}).")
+        src = copy.deepcopy(srcCollision)
+        src.changeBasis("Chebyshev")
+        nF = src.size
+        _, rzF, rpF = lobattoNodes(src.grid.M, src.grid.N)
+        _, rzT, rpT = lobattoNodes(targetGrid.M, targetGrid.N)
+
+        def lagrange(xT, xFull, idx):
+            out = np.ones((xT.size, idx.size))
+            for n_, i in enumerate(idx):
+                for k in range(xFull.size):
+                    if k != i:
+                        out[:, n_] *= (xT - xFull[k]) / (xFull[i] - xFull[k])
+            return out
+
+        Lz = lagrange(rzT, np.concatenate([[-1.0], rzF, [1.0]]), np.arange(1, nF + 1))   # [beta_T, beta_F]
+        Lp = lagrange(rpT, np.concatenate([rpF, [1.0]]), np.arange(0, nF))               # [gamma_T, gamma_F]
+        ev = np.einsum("xb,yg,abgcjk->xyacjk", Lz, Lp, src.data)                          # (bT, gT, a, b, j, k)
+        P = len(src.particles)
+        ev = ev.reshape(nT * nT, P, P, nF, nF)[..., :nT, :nT]
+        data = np.ascontiguousarray(ev).reshape(P, nT, nT, P, nT, nT)
+        out = CollisionArray(targetGrid, "Chebyshev", src.particles, data)
+        return out.changeBasis(srcCollision.getBasisType())
+
     def changeBasis(self, newBasisType):
         """Inverse-transpose transform of the two polynomial axes (polynomial.py:282-297)."""
         from .spectral import chebyshevMatrix, lobattoNodes
