@@ -200,6 +200,8 @@ def run_b200(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     lib = _lib.load()
     lib.wg_set_tuning(a.nb, a.graph)
+    if a.bulk_hi >= 0:
+        lib.wg_set_bulk_priority_rest(a.bulk_hi)
     P, M, N = WORKLOADS[a.workload]
     K, W = a.steps, a.warmup
     nsys = K + W
@@ -282,18 +284,24 @@ def run_b200(a):
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(nsolo)]
     import ctypes as C
     gms, gfl, gcnt = C.c_double(0), C.c_double(0), C.c_int(0)
-    lib.wg_profile_gemm(engines[0].h, 1, None, None, None)       # bracket the trailing-update GEMMs with events
     for i in range(nsolo):
         step(engines[0], W + i, evs[i])
     torch.cuda.synchronize()
+    # one more solo factorisation on plain streams (events cannot sit inside the CUDA graph) with every
+    # trailing-update GEMM launch bracketed by CUDA events on its launching stream
+    lib.wg_set_tuning(a.nb, 0)
+    lib.wg_profile_gemm(engines[0].h, 1, None, None, None)
+    step(engines[0], W)
+    torch.cuda.synchronize()
     lib.wg_profile_gemm(engines[0].h, 0, C.byref(gms), C.byref(gfl), C.byref(gcnt))
+    lib.wg_set_tuning(a.nb, a.graph)
     gemm_tf = gfl.value / (gms.value * 1e-3) / 1e12 if gms.value > 0 else float("nan")
     stage = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(4)] for e in evs]).mean(axis=0)
 
     pm = 4 * P * (M - 1)
     gathered = torch.empty(world * pm, dtype=torch.float64, device=dev) if world > 1 else None
     sampler = ClockSampler(local)
-    stagger = (2.0 / 3.0) * float(n) ** 3 / 20e12 / C_
+    stagger = (2.0 / 3.0) * float(n) ** 3 / 20e12 / C_ if a.stagger < 0 else a.stagger
     barrier()
     torch.cuda.synchronize()
     if rank == 0:
@@ -428,8 +436,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2a", choices=sorted(WORKLOADS))
     ap.add_argument("--nb", type=int, default=256)
-    ap.add_argument("--graph", type=int, default=0)
+    ap.add_argument("--graph", type=int, default=1)
     ap.add_argument("--concurrency", type=int, default=2)
+    ap.add_argument("--bulk-hi", type=int, default=-1, help="developer knob: wg_set_bulk_priority_rest")
+    ap.add_argument("--stagger", type=float, default=-1.0, help="developer knob: seconds between slot starts")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-budget-s", type=float, default=150.0)
     a = ap.parse_args()

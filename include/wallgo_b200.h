@@ -44,6 +44,10 @@ long long wg_launch_count(void);
 int wg_set_tuning(int nb, int use_graph);
 /* on: factor panel k+1 on a high-priority stream while the trailing update of panel k runs (default 1) */
 int wg_set_lookahead(int on);
+/* rest: once the trailing matrix has at most this many rows the bulk of each LU step also runs on a
+ * high-priority stream, so a second system sharing the GPU cannot starve this one's latency-bound tail
+ * (default 8192; 0 disables) */
+int wg_set_bulk_priority_rest(int rest);
 
 /* ---- lifecycle : BoltzmannSolver.__init__ + updateParticleList (boltzmann.py:52-139) */
 int wg_create(int P, int M, int N, int device, wg_solver** out);

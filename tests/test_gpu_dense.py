@@ -100,6 +100,32 @@ def test_lu_random(env, n, lda_pad):
     assert np.max(np.abs(x - xr)) / np.max(np.abs(xr)) < 1e-10
 
 
+@pytest.mark.parametrize("n", [300, 700, 2600])
+def test_lu_schedules_are_bit_identical(env, n):
+    """CUDA-graph replay (default), plain streams, and no look-ahead are schedules of the same arithmetic:
+    factors, pivots and solutions must agree bit for bit."""
+    torch, lib, _ = env
+    rng = np.random.default_rng(7 * n)
+    A = rng.standard_normal((n, n))
+    b = rng.standard_normal(n)
+    outs = []
+    try:
+        for graph, look in ((1, 1), (0, 1), (0, 0), (1, 0)):
+            lib.wg_set_tuning(256, graph)
+            lib.wg_set_lookahead(look)
+            LU, ipiv, info, x = _lu(env, A, b)
+            assert info == 0
+            outs.append((LU, ipiv, x))
+            LU2, ipiv2, _, x2 = _lu(env, A, b)     # run-to-run determinism of the same schedule
+            assert np.array_equal(LU, LU2) and np.array_equal(ipiv, ipiv2) and np.array_equal(x, x2)
+    finally:
+        lib.wg_set_tuning(256, 1)
+        lib.wg_set_lookahead(1)
+    for LU, ipiv, x in outs[1:]:
+        assert np.array_equal(outs[0][0], LU) and np.array_equal(outs[0][1], ipiv) and np.array_equal(outs[0][2], x)
+    _check_factors(A, outs[0][0], outs[0][1])
+
+
 @pytest.mark.parametrize("n", [8, 50, 300])
 def test_lu_pivots_match_c_oracle(env, n):
     """Same pivot rule as dgetf2 (first maximal |a| in the column): identical ipiv and factors to rounding."""

@@ -1,4 +1,5 @@
 // extern "C" boundary of libwallgo_b200.so (see include/wallgo_b200.h).
+#include <limits.h>
 #include <math.h>
 #include <stdarg.h>
 #include <string.h>
@@ -12,6 +13,7 @@
 
 static thread_local char g_err[512] = "";
 long long g_wg_launches = 0;
+thread_local int g_wg_launch_prio = INT_MIN;
 void wg_set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -83,6 +85,10 @@ int wg_profile_gemm(wg_solver* s, int enable, double* ms, double* flops, int* co
   WG_REQUIRE(s, "wg_profile_gemm: NULL solver");
   wg::lu_set_profile(enable);
   return wg::lu_profile_read(s->plan, ms, flops, count);
+}
+int wg_set_bulk_priority_rest(int rest) {
+  wg::lu_set_bulk_hi(rest);
+  return WG_OK;
 }
 int wg_set_lookahead(int on) {
   wg::lu_set_lookahead(on);
@@ -414,6 +420,13 @@ int wg_lu_destroy(wg_lu* p) {
 int wg_lu_factor(wg_lu* p, double* A_dev, long long lda, int* ipiv_dev, int* info_dev, void* stream) {
   WG_REQUIRE(p, "wg_lu_factor: NULL plan");
   return wg::lu_factor(p->plan, A_dev, lda, ipiv_dev, info_dev, (cudaStream_t)stream);
+}
+
+/* developer probe (not part of the public header): event timeline of the look-ahead LU */
+int wg_debug_lu_trace(wg_lu* p, int on, double* out, int maxSteps) {
+  wg::lu_set_trace(on);
+  if (!p || !out) return 0;
+  return wg::lu_trace_read(p->plan, out, maxSteps);
 }
 
 int wg_lu_solve(wg_lu* p, const double* LU_dev, long long lda, double* b_dev, void* stream) {

@@ -38,8 +38,33 @@ extern long long g_wg_launches;  // kernels launched by this library (bench acco
 
 static inline int wg_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Priority carried by kernel launches of the LU (INT_MIN: none).  Stream priorities are not kept by
+// stream capture, so the critical-chain kernels carry theirs as a launch attribute: it becomes the
+// kernel node's priority inside a captured CUDA graph and is harmless on a plain stream launch.
+extern thread_local int g_wg_launch_prio;
+
 #ifdef __CUDACC__
+#include <limits.h>
 namespace wg {
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_prio(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                      Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = 0;
+  if (g_wg_launch_prio != INT_MIN) {
+    attr[0].id = cudaLaunchAttributePriority;
+    attr[0].val.priority = g_wg_launch_prio;
+    cfg.numAttrs = 1;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 // ---------------------------------------------------------------- FP64 tensor-core MMA
 // D(8x8) = A(8x4, row) * B(4x8, col) + C.  lane = 4*g + t :

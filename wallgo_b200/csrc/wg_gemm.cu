@@ -156,7 +156,7 @@ static int launch_cfg(double* C, const double* A, const double* B, int M, int N,
       WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
       configured = true;
     }
-    kern<<<grid, NT, SMEM, st>>>(C, A, B, M, N, K, ldc, lda, ldb);
+    WG_CUDA(launch_prio(kern, grid, dim3(NT), SMEM, st, C, A, B, M, N, K, ldc, lda, ldb));
   } else {
     auto kern = dgemm_sub_kernel<BM, BN, BK, WARPS_M, WARPS_N, STAGES, false, MINB>;
     static bool configured = false;
@@ -164,7 +164,7 @@ static int launch_cfg(double* C, const double* A, const double* B, int M, int N,
       WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
       configured = true;
     }
-    kern<<<grid, NT, SMEM, st>>>(C, A, B, M, N, K, ldc, lda, ldb);
+    WG_CUDA(launch_prio(kern, grid, dim3(NT), SMEM, st, C, A, B, M, N, K, ldc, lda, ldb));
   }
   WG_LAUNCH_CHECK();
   return WG_OK;

@@ -40,10 +40,12 @@ void lu_set_debug(long long* buf, int c0) {
   g_dbg_c0 = c0;
 }
 static int g_nb = 256;
-static int g_use_graph = 0;
+static int g_use_graph = 1;  // replay the factorisation as a CUDA graph (node priorities keep the chain ahead)
 static int g_lookahead = 1;
 static int g_profile = 0;
+static int g_trace = 0;
 void lu_set_profile(int on) { g_profile = on; }
+void lu_set_trace(int on) { g_trace = on; }
 void lu_set_tuning(int nb, int use_graph) {
   if (nb >= 32 && nb <= 256 && nb % 16 == 0) g_nb = nb;
   g_use_graph = use_graph;
@@ -367,13 +369,18 @@ static int launch_leaf(const PanelArgs& pa, int CL, cudaStream_t st) {
   cfg.blockDim = dim3(PT, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (g_wg_launch_prio != INT_MIN) {
+    attr[1].id = cudaLaunchAttributePriority;
+    attr[1].val.priority = g_wg_launch_prio;
+    cfg.numAttrs = 2;
+  }
   WG_CUDA(cudaLaunchKernelEx(&cfg, kern, pa));
   ++g_wg_launches;
   return WG_OK;
@@ -434,13 +441,19 @@ __global__ void lu_perm_compose_kernel(int n, int k, int nb, int wb, const int* 
 }
 
 // ------------------------------------------------------------------ panel permutation: apply
-// columns outside [k, k+nb): c' in [0, n-nb) -> col = c' < k ? c' : c' + nb
-__global__ void lu_perm_gather_kernel(const double* __restrict__ A, long long lda, int n, int k, int nb,
+// The row permutation of panel [k, k+nb) is applied to a set of columns given as two segments:
+// c' in [0, ncol) -> col = c' < split ? c' + off0 : c' + off1.  The critical chain (next panel's columns)
+// and the bulk (everything else outside the panel) use it with different maps and staging buffers.
+struct ColMap {
+  int ncol, split, off0, off1;
+};
+
+__global__ void lu_perm_gather_kernel(const double* __restrict__ A, long long lda, ColMap cm, int k,
                                       const int* __restrict__ srcTop, const int* __restrict__ bSrc,
                                       const int* __restrict__ nbotPtr, double* __restrict__ S,
                                       double* __restrict__ S2, int vec) {
   const int i = blockIdx.y;
-  const int ncol = n - nb;
+  const int ncol = cm.ncol;
   const int nbot = *nbotPtr;
   const int src1 = srcTop[k + i];
   const bool do1 = src1 != k + i;
@@ -453,25 +466,25 @@ __global__ void lu_perm_gather_kernel(const double* __restrict__ A, long long ld
   double* s2 = S2 + (long long)i * ncol;
   if (vec) {
     for (int c = 2 * (blockIdx.x * blockDim.x + threadIdx.x); c < ncol; c += 2 * gridDim.x * blockDim.x) {
-      const int col = c < k ? c : c + nb;
+      const int col = c < cm.split ? c + cm.off0 : c + cm.off1;
       if (do1) *reinterpret_cast<double2*>(s1 + c) = *reinterpret_cast<const double2*>(r1 + col);
       if (do2) *reinterpret_cast<double2*>(s2 + c) = *reinterpret_cast<const double2*>(r2 + col);
     }
   } else {
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncol; c += gridDim.x * blockDim.x) {
-      const int col = c < k ? c : c + nb;
+      const int col = c < cm.split ? c + cm.off0 : c + cm.off1;
       if (do1) s1[c] = r1[col];
       if (do2) s2[c] = r2[col];
     }
   }
 }
 
-__global__ void lu_perm_write_kernel(double* __restrict__ A, long long lda, int n, int k, int nb,
+__global__ void lu_perm_write_kernel(double* __restrict__ A, long long lda, ColMap cm, int k,
                                      const int* __restrict__ srcTop, const int* __restrict__ bDst,
                                      const int* __restrict__ nbotPtr, const double* __restrict__ S,
                                      const double* __restrict__ S2, int vec) {
   const int i = blockIdx.y;
-  const int ncol = n - nb;
+  const int ncol = cm.ncol;
   const int nbot = *nbotPtr;
   const bool do1 = srcTop[k + i] != k + i;
   const bool do2 = i < nbot;
@@ -483,13 +496,13 @@ __global__ void lu_perm_write_kernel(double* __restrict__ A, long long lda, int 
   const double* s2 = S2 + (long long)i * ncol;
   if (vec) {
     for (int c = 2 * (blockIdx.x * blockDim.x + threadIdx.x); c < ncol; c += 2 * gridDim.x * blockDim.x) {
-      const int col = c < k ? c : c + nb;
+      const int col = c < cm.split ? c + cm.off0 : c + cm.off1;
       if (do1) *reinterpret_cast<double2*>(r1 + col) = *reinterpret_cast<const double2*>(s1 + c);
       if (do2) *reinterpret_cast<double2*>(r2 + col) = *reinterpret_cast<const double2*>(s2 + c);
     }
   } else {
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncol; c += gridDim.x * blockDim.x) {
-      const int col = c < k ? c : c + nb;
+      const int col = c < cm.split ? c + cm.off0 : c + cm.off1;
       if (do1) r1[col] = s1[c];
       if (do2) r2[col] = s2[c];
     }
@@ -600,11 +613,11 @@ static int trsm_rec(const double* L, long long ldl, double* B, long long ldb, in
   if (w <= 32) {
     const int grid = wg_cdiv(ncols, 64);
     if (w <= 8)
-      lu_trsm_base_kernel<8><<<grid, 64, 0, st>>>(L, ldl, B, ldb, w, ncols);
+      WG_CUDA(launch_prio(lu_trsm_base_kernel<8>, dim3(grid), dim3(64), 0, st, L, ldl, B, ldb, w, ncols));
     else if (w <= 16)
-      lu_trsm_base_kernel<16><<<grid, 64, 0, st>>>(L, ldl, B, ldb, w, ncols);
+      WG_CUDA(launch_prio(lu_trsm_base_kernel<16>, dim3(grid), dim3(64), 0, st, L, ldl, B, ldb, w, ncols));
     else
-      lu_trsm_base_kernel<32><<<grid, 64, 0, st>>>(L, ldl, B, ldb, w, ncols);
+      WG_CUDA(launch_prio(lu_trsm_base_kernel<32>, dim3(grid), dim3(64), 0, st, L, ldl, B, ldb, w, ncols));
     WG_LAUNCH_CHECK();
     return WG_OK;
   }
@@ -616,7 +629,7 @@ static int trsm_rec(const double* L, long long ldl, double* B, long long ldb, in
                                    (int)(256 * TLDB * sizeof(double))));
       configured = true;
     }
-    lu_trsm_strip_kernel<<<wg_cdiv(ncols, TSC), 256, smem, st>>>(L, ldl, B, ldb, w, ncols);
+    WG_CUDA(launch_prio(lu_trsm_strip_kernel, dim3(wg_cdiv(ncols, TSC)), dim3(256), smem, st, L, ldl, B, ldb, w, ncols));
     WG_LAUNCH_CHECK();
     return WG_OK;
   }
@@ -774,13 +787,21 @@ struct LuPlan {
   int *grpSrcTop = nullptr, *grpBDst = nullptr;
   int *permSrcTop = nullptr, *permBDst = nullptr, *permBSrc = nullptr, *permNBot = nullptr;
   int* posContent = nullptr;
-  double *S = nullptr, *S2 = nullptr;
-  cudaStream_t panelStream = nullptr;  // high priority: next panel overlaps the trailing update
+  double *S = nullptr, *S2 = nullptr;      // row staging of the bulk permutation (256 x n each)
+  double *Sc = nullptr, *Sc2 = nullptr;    // row staging of the chain permutation (256 x 256 each)
+  cudaStream_t panelStream = nullptr;  // highest priority: the critical chain (next panel's columns + panel)
+  cudaStream_t bulkHiStream = nullptr; // bulk work of the latency-bound end of the factorisation
+  int prioChain = 0, prioBulkHi = 0;
+  cudaEvent_t evPhase = nullptr;
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
   // optional live timing of the trailing-update GEMM launches (bench roofline)
   std::vector<cudaEvent_t> profEv;
   std::vector<double> profFlops;
   int profCount = 0;
+  // developer timeline: per top-level step {step start, fork, wide TRSM done, wide GEMM done} on the main
+  // stream and {panel done} on the panel stream
+  std::vector<cudaEvent_t> traceEv;
+  int traceSteps = 0;
   // CUDA-graph cache of the factorisation for one set of buffers
   cudaGraphExec_t exec = nullptr;
   long long graphLaunches = 0;
@@ -788,6 +809,12 @@ struct LuPlan {
   long long glda = 0;
   int* gipiv = nullptr;
   int* ginfo = nullptr;
+  // CUDA-graph cache of the triangular solves for one (factors, right-hand side) pair
+  cudaGraphExec_t solveExec = nullptr;
+  long long solveLaunches = 0;
+  const double* sLU = nullptr;
+  long long slda = 0;
+  double* sb = nullptr;
 };
 
 template <int W, int R>
@@ -834,9 +861,15 @@ int lu_plan_create(int n, LuPlan** out) {
   const size_t sbytes = sizeof(double) * (size_t)256 * (size_t)n;
   WG_CUDA(cudaMalloc(&p->S, sbytes));
   WG_CUDA(cudaMalloc(&p->S2, sbytes));
+  WG_CUDA(cudaMalloc(&p->Sc, sizeof(double) * 256 * 256));
+  WG_CUDA(cudaMalloc(&p->Sc2, sizeof(double) * 256 * 256));
   int prLow = 0, prHigh = 0;
   WG_CUDA(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
   WG_CUDA(cudaStreamCreateWithPriority(&p->panelStream, cudaStreamNonBlocking, prHigh));
+  p->prioChain = prHigh;
+  p->prioBulkHi = prHigh < prLow ? prHigh + 1 : prHigh;
+  WG_CUDA(cudaStreamCreateWithPriority(&p->bulkHiStream, cudaStreamNonBlocking, p->prioBulkHi));
+  WG_CUDA(cudaEventCreateWithFlags(&p->evPhase, cudaEventDisableTiming));
   WG_CUDA(cudaEventCreateWithFlags(&p->evFork, cudaEventDisableTiming));
   WG_CUDA(cudaEventCreateWithFlags(&p->evJoin, cudaEventDisableTiming));
   *out = p;
@@ -846,10 +879,14 @@ int lu_plan_create(int n, LuPlan** out) {
 void lu_plan_destroy(LuPlan* p) {
   if (!p) return;
   if (p->exec) cudaGraphExecDestroy(p->exec);
+  if (p->solveExec) cudaGraphExecDestroy(p->solveExec);
   if (p->panelStream) cudaStreamDestroy(p->panelStream);
+  if (p->bulkHiStream) cudaStreamDestroy(p->bulkHiStream);
+  if (p->evPhase) cudaEventDestroy(p->evPhase);
   if (p->evFork) cudaEventDestroy(p->evFork);
   if (p->evJoin) cudaEventDestroy(p->evJoin);
   for (cudaEvent_t e : p->profEv) cudaEventDestroy(e);
+  for (cudaEvent_t e : p->traceEv) cudaEventDestroy(e);
   cudaFree(p->grpSrcTop);
   cudaFree(p->grpBDst);
   cudaFree(p->permSrcTop);
@@ -859,6 +896,8 @@ void lu_plan_destroy(LuPlan* p) {
   cudaFree(p->posContent);
   cudaFree(p->S);
   cudaFree(p->S2);
+  cudaFree(p->Sc);
+  cudaFree(p->Sc2);
   delete p;
 }
 
@@ -940,6 +979,31 @@ static void prof_mark(LuPlan* p, cudaStream_t st, double flops, bool begin) {
   }
 }
 
+static void trace_mark(LuPlan* p, cudaStream_t st, int step, int slot) {
+  if (!g_trace || g_use_graph) return;
+  const size_t idx = 5 * (size_t)step + slot;
+  while (p->traceEv.size() <= idx) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    p->traceEv.push_back(e);
+  }
+  cudaEventRecord(p->traceEv[idx], st);
+  if (step + 1 > p->traceSteps) p->traceSteps = step + 1;
+}
+
+// out[5*step + slot] = ms since the first event (NaN where nothing was recorded); returns the step count
+int lu_trace_read(LuPlan* p, double* out, int maxSteps) {
+  const int ns = p->traceSteps < maxSteps ? p->traceSteps : maxSteps;
+  for (int i = 0; i < 5 * ns; ++i) {
+    float t = 0.f;
+    out[i] = ((size_t)i < p->traceEv.size() && cudaEventElapsedTime(&t, p->traceEv[0], p->traceEv[i]) == cudaSuccess)
+                 ? (double)t
+                 : -1.0;
+  }
+  (void)cudaGetLastError();
+  return ns;
+}
+
 // sums the bracketed launches since the last reset (caller has synchronised the stream)
 int lu_profile_read(LuPlan* p, double* ms, double* flops, int* count) {
   double tms = 0.0, tfl = 0.0;
@@ -963,9 +1027,29 @@ static int panel_width_class(LuPlan* p, int m) {
   return 0;
 }
 
-// Right-looking blocked LU.  With look-ahead, panel k+1 is factored on a high-priority side stream as
-// soon as its own columns have received update k, while the main stream finishes the rest of the
-// trailing update; the leaf panels (16 SMs, latency bound) hide behind the DMMA GEMM.
+static int g_hi_rest = 8192;  // bulk work moves to the high-priority bulk stream once the trailing matrix is this small
+void lu_set_bulk_hi(int rest) { g_hi_rest = rest; }
+
+static int apply_perm(LuPlan* p, double* A, long long lda, ColMap cm, int k, int nb, int pnl, double* S, double* S2,
+                      int vecA, cudaStream_t st) {
+  if (cm.ncol <= 0) return WG_OK;
+  const int vec = vecA && ((cm.ncol | cm.split | cm.off0 | cm.off1) % 2 == 0);
+  dim3 grid(wg_cdiv(cm.ncol, 2048), nb);
+  WG_CUDA(launch_prio(lu_perm_gather_kernel, grid, dim3(256), 0, st, A, lda, cm, k, p->permSrcTop, p->permBSrc,
+                      p->permNBot + pnl, S, S2, vec));
+  WG_LAUNCH_CHECK();
+  WG_CUDA(launch_prio(lu_perm_write_kernel, grid, dim3(256), 0, st, A, lda, cm, k, p->permSrcTop, p->permBDst,
+                      p->permNBot + pnl, S, S2, vec));
+  WG_LAUNCH_CHECK();
+  return WG_OK;
+}
+
+// Right-looking blocked LU with a look-ahead critical chain.  After panel k is factored, everything the
+// NEXT panel needs -- the row interchanges, the triangular solve and the update of its own columns, then
+// its factorisation -- runs on the highest-priority "chain" stream; the bulk of step k (interchanges of all
+// other columns, U12, trailing update on the DMMA GEMM) runs beside it.  The chain is latency bound (16 SMs),
+// the bulk is throughput bound, so one hides behind the other; once the trailing matrix is small the bulk
+// also moves to a high-priority stream so that a second system sharing the GPU cannot starve this one's tail.
 static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStream_t st) {
   const int n = p->n, NB = p->nb;
   FactorCtx c{p, A, lda, ipiv, info, st, 16, 0};
@@ -977,70 +1061,89 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
                  p->maxCL * PT * 4);
     return WG_ERR_UNSUPPORTED;
   }
-  bool panelDone = false;  // panel [k, k+nb) already factored by the look-ahead of the previous step
+  struct PrioGuard {
+    ~PrioGuard() { g_wg_launch_prio = INT_MIN; }
+  } prioGuard;
+  cudaStream_t bs = st;    // stream of the bulk work
+  int bulkPrio = INT_MIN;
+  bool panelDone = false;  // panel [k, k+nb) already factored by the chain of the previous step
   for (int k = 0, pnl = 0; k < n; k += NB, ++pnl) {
     const int nb = NB < n - k ? NB : n - k;
     int rc;
+    trace_mark(p, bs, pnl, 0);
     if (!panelDone) {
-      c.st = st;
+      c.st = bs;
       c.wb = panel_width_class(p, n - k);
       rc = panel_rec(c, k, nb, k, k + nb);
       if (rc) return rc;
-    }
-    c.st = st;
-    if (!panelDone) {
-      lu_perm_compose_kernel<<<1, 256, 0, st>>>(n, k, nb, panel_width_class(p, n - k), p->grpSrcTop, p->grpBDst,
-                                                p->posContent, p->permSrcTop, p->permBDst, p->permBSrc,
-                                                p->permNBot + pnl);
-      WG_LAUNCH_CHECK();
-    }
-    if (n - nb > 0) {
-      const int vec = c.vecA && (k % 2 == 0) && (nb % 2 == 0) && (n % 2 == 0);
-      dim3 grid(wg_cdiv(n - nb, 2048), nb);
-      lu_perm_gather_kernel<<<grid, 256, 0, st>>>(A, lda, n, k, nb, p->permSrcTop, p->permBSrc,
-                                                  p->permNBot + pnl, p->S, p->S2, vec);
-      WG_LAUNCH_CHECK();
-      lu_perm_write_kernel<<<grid, 256, 0, st>>>(A, lda, n, k, nb, p->permSrcTop, p->permBDst,
-                                                 p->permNBot + pnl, p->S, p->S2, vec);
+      WG_CUDA(launch_prio(lu_perm_compose_kernel, dim3(1), dim3(256), 0, bs, n, k, nb, c.wb, p->grpSrcTop, p->grpBDst,
+                          p->posContent, p->permSrcTop, p->permBDst, p->permBSrc, p->permNBot + pnl));
       WG_LAUNCH_CHECK();
     }
     panelDone = false;
     const int rest = n - k - nb;
-    if (rest <= 0) break;
-    rc = trsm_rec(A + (long long)k * lda + k, lda, A + (long long)k * lda + k + nb, lda, nb, rest, st);
-    if (rc) return rc;
+    const int nb2 = NB < rest ? NB : rest;
     double* C22 = A + (long long)(k + nb) * lda + k + nb;
     const double* L21 = A + (long long)(k + nb) * lda + k;
-    const double* U12 = A + (long long)k * lda + k + nb;
-    const int nb2 = NB < rest ? NB : rest;
-    if (look && rest > nb2) {
-      // update the next panel's columns first, fork the panel factorisation, then the rest
-      rc = dgemm_sub(C22, L21, U12, rest, nb2, nb, lda, lda, lda, st);
+    double* U12 = A + (long long)k * lda + k + nb;
+    const double* L11 = A + (long long)k * lda + k;
+    if (!(look && rest > nb2)) {
+      rc = apply_perm(p, A, lda, ColMap{n - nb, k, 0, nb}, k, nb, pnl, p->S, p->S2, c.vecA, bs);
       if (rc) return rc;
-      WG_CUDA(cudaEventRecord(p->evFork, st));
-      WG_CUDA(cudaStreamWaitEvent(p->panelStream, p->evFork, 0));
-      c.st = p->panelStream;
-      c.wb = panel_width_class(p, rest);
-      rc = panel_rec(c, k + nb, nb2, k + nb, k + nb + nb2);
+      if (rest <= 0) break;
+      rc = trsm_rec(L11, lda, U12, lda, nb, rest, bs);
       if (rc) return rc;
-      lu_perm_compose_kernel<<<1, 256, 0, p->panelStream>>>(n, k + nb, nb2, c.wb, p->grpSrcTop, p->grpBDst,
-                                                            p->posContent, p->permSrcTop, p->permBDst,
-                                                            p->permBSrc, p->permNBot + pnl + 1);
-      WG_LAUNCH_CHECK();
-      WG_CUDA(cudaEventRecord(p->evJoin, p->panelStream));
-      c.st = st;
-      prof_mark(p, st, 2.0 * rest * (double)(rest - nb2) * nb, true);
-      rc = dgemm_sub(C22 + nb2, L21, U12 + nb2, rest, rest - nb2, nb, lda, lda, lda, st);
+      prof_mark(p, bs, 2.0 * rest * (double)rest * nb, true);
+      rc = dgemm_sub(C22, L21, U12, rest, rest, nb, lda, lda, lda, bs);
       if (rc) return rc;
-      prof_mark(p, st, 0.0, false);
-      WG_CUDA(cudaStreamWaitEvent(st, p->evJoin, 0));
-      panelDone = true;
-    } else {
-      prof_mark(p, st, 2.0 * rest * (double)rest * nb, true);
-      rc = dgemm_sub(C22, L21, U12, rest, rest, nb, lda, lda, lda, st);
-      if (rc) return rc;
-      prof_mark(p, st, 0.0, false);
+      prof_mark(p, bs, 0.0, false);
+      continue;
     }
+    if (bs == st && rest <= g_hi_rest) {
+      WG_CUDA(cudaEventRecord(p->evPhase, st));
+      WG_CUDA(cudaStreamWaitEvent(p->bulkHiStream, p->evPhase, 0));
+      bs = p->bulkHiStream;
+      bulkPrio = p->prioBulkHi;
+    }
+    // ---- critical chain: columns of the next panel, then the next panel itself
+    cudaStream_t cs = p->panelStream;
+    WG_CUDA(cudaEventRecord(p->evFork, bs));
+    WG_CUDA(cudaStreamWaitEvent(cs, p->evFork, 0));
+    g_wg_launch_prio = p->prioChain;
+    rc = apply_perm(p, A, lda, ColMap{nb2, nb2, k + nb, 0}, k, nb, pnl, p->Sc, p->Sc2, c.vecA, cs);
+    if (rc) return rc;
+    rc = trsm_rec(L11, lda, U12, lda, nb, nb2, cs);
+    if (rc) return rc;
+    rc = dgemm_sub(C22, L21, U12, rest, nb2, nb, lda, lda, lda, cs);
+    if (rc) return rc;
+    c.st = cs;
+    c.wb = panel_width_class(p, rest);
+    rc = panel_rec(c, k + nb, nb2, k + nb, k + nb + nb2);
+    if (rc) return rc;
+    WG_CUDA(launch_prio(lu_perm_compose_kernel, dim3(1), dim3(256), 0, cs, n, k + nb, nb2, c.wb, p->grpSrcTop,
+                        p->grpBDst, p->posContent, p->permSrcTop, p->permBDst, p->permBSrc, p->permNBot + pnl + 1));
+    WG_LAUNCH_CHECK();
+    WG_CUDA(cudaEventRecord(p->evJoin, cs));
+    trace_mark(p, cs, pnl, 4);
+    g_wg_launch_prio = bulkPrio;
+    // ---- bulk: every other column
+    rc = apply_perm(p, A, lda, ColMap{n - nb - nb2, k, 0, nb + nb2}, k, nb, pnl, p->S, p->S2, c.vecA, bs);
+    if (rc) return rc;
+    trace_mark(p, bs, pnl, 1);
+    rc = trsm_rec(L11, lda, U12 + nb2, lda, nb, rest - nb2, bs);
+    if (rc) return rc;
+    trace_mark(p, bs, pnl, 2);
+    prof_mark(p, bs, 2.0 * rest * (double)(rest - nb2) * nb, true);
+    rc = dgemm_sub(C22 + nb2, L21, U12 + nb2, rest, rest - nb2, nb, lda, lda, lda, bs);
+    if (rc) return rc;
+    prof_mark(p, bs, 0.0, false);
+    trace_mark(p, bs, pnl, 3);
+    WG_CUDA(cudaStreamWaitEvent(bs, p->evJoin, 0));
+    panelDone = true;
+  }
+  if (bs != st) {
+    WG_CUDA(cudaEventRecord(p->evPhase, bs));
+    WG_CUDA(cudaStreamWaitEvent(st, p->evPhase, 0));
   }
   return WG_OK;
 }
@@ -1068,7 +1171,7 @@ int lu_factor(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStr
       return rc;
     }
     WG_CUDA(e);
-    WG_CUDA(cudaGraphInstantiate(&p->exec, graph, 0));
+    WG_CUDA(cudaGraphInstantiateWithFlags(&p->exec, graph, cudaGraphInstantiateFlagUseNodePriority));
     cudaGraphDestroy(graph);
     p->gA = A;
     p->glda = lda;
@@ -1080,8 +1183,43 @@ int lu_factor(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStr
   return WG_OK;
 }
 
+static int solve_enqueue(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st);
+
 int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st) {
   WG_REQUIRE(p && LU && b && lda >= p->n, "lu_solve: bad arguments");
+  if (!g_use_graph) return solve_enqueue(p, LU, lda, b, st);
+  if (!p->solveExec || p->sLU != LU || p->slda != lda || p->sb != b) {
+    if (p->solveExec) {
+      cudaGraphExecDestroy(p->solveExec);
+      p->solveExec = nullptr;
+    }
+    cudaStream_t cs;
+    WG_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    WG_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    const long long before = g_wg_launches;
+    int rc = solve_enqueue(p, LU, lda, b, cs);
+    p->solveLaunches = g_wg_launches - before;
+    g_wg_launches = before;
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(cs, &graph);
+    cudaStreamDestroy(cs);
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    WG_CUDA(e);
+    WG_CUDA(cudaGraphInstantiate(&p->solveExec, graph, 0));
+    cudaGraphDestroy(graph);
+    p->sLU = LU;
+    p->slda = lda;
+    p->sb = b;
+  }
+  WG_CUDA(cudaGraphLaunch(p->solveExec, st));
+  g_wg_launches += p->solveLaunches;
+  return WG_OK;
+}
+
+static int solve_enqueue(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st) {
   const int n = p->n, NB = p->nb;
   lu_rhs_perm_kernel<<<1, 1024, 0, st>>>(b, p->permSrcTop, p->permBDst, p->permBSrc, p->permNBot, n, NB);
   WG_LAUNCH_CHECK();
