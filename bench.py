@@ -185,6 +185,52 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
+def run_scan(a, world, rank, local):
+    """Second half of the BASELINE metric: wall-velocity scan points/s.  256 independent vw points of the
+    cfg4-sized system (P=4, M=30, N=11, n=11600) sharded round-robin over the ranks (strong scaling), every
+    point one full assemble+LU+moments through the public class with host buffers, one NCCL all_gather of
+    the moment tables at the end.  A point here is ONE Boltzmann solve at that vw: the EOM pressure
+    iteration around it is the reference's own unmodified host code (out of scope)."""
+    import torch
+    import torch.distributed as dist
+
+    import wallgo_b200 as wb
+    from wallgo_b200 import scan, synthetic
+
+    P, M, N = WORKLOADS[a.scan_workload]
+    npts = a.scan_points
+    grid = synthetic.makeGrid(M, N)
+    particles = synthetic.makeParticles(P)
+    coll = synthetic.makeCollision(grid, particles)
+    bgs = [synthetic.makeBackground(grid, velocityMid=-(0.05 + 0.48 * i / max(1, npts - 1))) for i in range(npts)]
+    solver = wb.BoltzmannSolver(grid, device=local)
+    solver.updateParticleList(particles)
+    solver.setCollisionArray(coll)
+    scan.scanDeltas(lambda: solver, bgs[:4 * world])      # warm-up: graphs captured, slots allocated
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    table = scan.scanDeltas(lambda: solver, bgs)
+    torch.cuda.synchronize()
+    el = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([el], dtype=torch.float64, device=torch.device("cuda", local))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        el = float(t.item())
+    assert table.shape == (npts, 4 * P * (M - 1)) and np.all(np.isfinite(table))
+    n = P * (M - 1) * (N - 1) ** 2
+    out = {"metric": "vw scan pts/sec", "value": npts / el, "unit": "points/s", "points": npts, "seconds": el,
+           "scaling": "strong", "workload": f"{a.scan_workload}: P={P} M={M} N={N} n={n}, vw in [0.05, 0.53]",
+           "point": "one Boltzmann solve (assemble+LU+truncation+moments) per vw through getDeltasBatch, host buffers "
+                    "in/out; NCCL all_gather of the moment tables",
+           "concurrency_per_gpu": wb.BoltzmannSolver.autoConcurrency(n),
+           "checksum": float(np.sum(table[:, :P * (M - 1)]))}
+    del solver
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
@@ -248,6 +294,8 @@ def run_b200(a):
         vws.append(float(b.velocityWall))
     profs = torch.from_numpy(profs_h).to(dev)
     keep = (M - 1, N - 1, N - 1)
+    if a.concurrency <= 0:
+        a.concurrency = wb.BoltzmannSolver.autoConcurrency(n)
     C_ = max(1, min(a.concurrency, K))
     sibs = solver._siblings(C_)
     engines = []
@@ -365,6 +413,7 @@ def run_b200(a):
     assert np.all(np.isfinite(res.Deltas.Delta00.coefficients))
     eng = engines[0]
 
+    scan_line = run_scan(a, world, rank, local) if a.scan_points > 0 else None
     if rank == 0:
         hbm_peak, hbm_src = measured_peaks()
         lu_flops = 2.0 / 3.0 * float(n) ** 3
@@ -412,6 +461,8 @@ def run_b200(a):
                     "d2h_bytes_per_step": int((eng.nspec + eng.nout) * 8 + 4)},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if scan_line is not None:
+            line["scan"] = scan_line
         if world == 1 and not a.no_cpu_baseline:
             try:
                 t, _ = cpu_port_one_solve(grid, particles, coll, bgs[W])
@@ -437,10 +488,12 @@ def main():
     ap.add_argument("--workload", default="cfg2a", choices=sorted(WORKLOADS))
     ap.add_argument("--nb", type=int, default=256)
     ap.add_argument("--graph", type=int, default=1)
-    ap.add_argument("--concurrency", type=int, default=2)
+    ap.add_argument("--concurrency", type=int, default=0, help="independent systems in flight per GPU (0: auto)")
     ap.add_argument("--bulk-hi", type=int, default=-1, help="developer knob: wg_set_bulk_priority_rest")
     ap.add_argument("--stagger", type=float, default=-1.0, help="developer knob: seconds between slot starts")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scan-points", type=int, default=256, help="vw-scan points of the secondary metric (0: skip)")
+    ap.add_argument("--scan-workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--ref-budget-s", type=float, default=150.0)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup

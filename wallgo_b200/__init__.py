@@ -6,7 +6,13 @@ Public surface:
   Grid, Grid3Scales, Particle, BoltzmannBackground, CollisionArray, ETruncationOption
   engine.BoltzmannEngine     thin torch/ctypes wrapper over the C ABI (include/wallgo_b200.h)
 """
-from .boltzmann import BoltzmannSolver
+import os as _os
+
+# Independent systems share one GPU through one stream (CUDA graph) per slot; the default of 8 hardware
+# work queues would serialise more than 8 of them.  Only effective if set before the CUDA context exists.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+from .boltzmann import BoltzmannSolver  # noqa: E402
 from .containers import (BoltzmannBackground, BoltzmannDeltas, BoltzmannResults, CollisionArray,
                          ETruncationOption, Particle, Polynomial)
 from .grid import Grid, Grid3Scales

@@ -301,16 +301,32 @@ class BoltzmannSolverB200Mixin:
             s_.collisionArray, s_.offEqParticles, s_.grid = self.collisionArray, self.offEqParticles, self.grid
         return sibs[:count]
 
-    def getDeltasBatch(self, backgrounds, concurrency: int = 2):
+    @staticmethod
+    def autoConcurrency(n: int, freeBytes: int | None = None) -> int:
+        """How many independent systems of size n to keep in flight on one B200.  A single LU of this size
+        cannot fill the GPU during its latency-bound panel chain (16 SMs), so a few large systems or many
+        small ones share it (measured: n=15600: 3, n=8700: 4, n=1900: 32 slots)."""
+        c = 3 if n >= 12000 else 4 if n >= 6000 else 8 if n >= 2500 else 32
+        if freeBytes is not None:
+            perSlot = 8 * n * n + 2 * 8 * 256 * n + 64 * n + (1 << 20)
+            c = max(1, min(c, int(0.6 * freeBytes) // perSlot))
+        return c
+
+    def getDeltasBatch(self, backgrounds, concurrency: int | None = None):
         """getDeltas() for a list of independent backgrounds (wall-velocity scan points, parameter points),
-        `concurrency` systems in flight on this GPU.  Each system is solved exactly as getDeltas() would;
-        the slots are staggered so that the latency-bound end of one LU overlaps the GEMM-rich start of
-        the next.  Returns the BoltzmannResults in input order."""
+        `concurrency` systems in flight on this GPU (None: autoConcurrency).  Each system is solved exactly
+        as getDeltas() would; every slot replays its factorisation as one CUDA graph on its own stream, and
+        the slots are staggered so that the latency-bound end of one LU overlaps the GEMM-rich start of the
+        next.  Returns the BoltzmannResults in input order."""
         import time
 
         nItems = len(backgrounds)
         if nItems == 0:
             return []
+        if concurrency is None or int(concurrency) <= 0:
+            eng0 = self._getEngine()
+            free = eng0.torch.cuda.mem_get_info(eng0.dev)[0]
+            concurrency = self.autoConcurrency(eng0.n, free + (8 * eng0.n * eng0.n if eng0.A is not None else 0))
         C = max(1, min(int(concurrency), nItems))
         sibs = self._siblings(C)
         torch = sibs[0]._getEngine().torch

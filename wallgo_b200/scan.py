@@ -39,18 +39,26 @@ def gatherPoints(localValues: np.ndarray, nPoints: int, width: int, device=None)
     return full
 
 
-def scanDeltas(makeSolver, backgrounds, device=None) -> np.ndarray:
-    """Solve one Boltzmann system per background on this rank's share and gather
-    [nPoints, 4*P*(M-1)] moment tables.  `makeSolver()` builds this rank's own solver."""
+def scanDeltas(makeSolver, backgrounds, device=None, concurrency=None) -> np.ndarray:
+    """Solve one Boltzmann system per background on this rank's share (several systems in flight on the
+    rank's GPU, see BoltzmannSolver.getDeltasBatch) and gather the [nPoints, 4*P*(M-1)] moment tables.
+    `makeSolver()` builds this rank's own solver."""
     import torch.distributed as dist
 
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
     solver = makeSolver()
+    mine = shardPoints(len(backgrounds), rank, world)
+    if hasattr(solver, "getDeltasBatch"):
+        results = solver.getDeltasBatch([backgrounds[i] for i in mine], concurrency=concurrency)
+    else:
+        results = []
+        for i in mine:
+            solver.setBackground(backgrounds[i])
+            results.append(solver.getDeltas())
     rows = []
-    for i in shardPoints(len(backgrounds), rank, world):
-        solver.setBackground(backgrounds[i])
-        d = solver.getDeltas().Deltas
+    for res in results:
+        d = res.Deltas
         rows.append(np.concatenate([d.Delta00.coefficients.ravel(), d.Delta02.coefficients.ravel(),
                                     d.Delta20.coefficients.ravel(), d.Delta11.coefficients.ravel()]))
     width = rows[0].size if rows else 0
