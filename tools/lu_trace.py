@@ -6,6 +6,7 @@ import wallgo_b200 as wb
 from wallgo_b200 import _lib, synthetic
 lib = _lib.load()
 lib.wg_debug_lu_trace.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+lib.wg_set_tuning(256, int(os.environ.get("WG_GRAPH", "0")))
 P, M, N = (int(x) for x in (sys.argv[1:4] if len(sys.argv) > 3 else (1, 40, 21)))
 grid = synthetic.makeGrid(M, N); parts = synthetic.makeParticles(P)
 s = wb.BoltzmannSolver(grid); s.updateParticleList(parts)

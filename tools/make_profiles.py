@@ -39,11 +39,11 @@ def raw_page(rep, dst):
         w = csv.writer(f); w.writerow(["metric", "unit"] + [f"launch{j}" for j in range(len(rows) - 2)])
         for i in idx: w.writerow([hdr[i], units[i]] + [r[i] for r in rows[2:]])
 
-launch_list("launches_r1b_cfg2a.csv", f"{tag}_cfg2a")
+launch_list("launches_r1c_cfg2a.csv", f"{tag}_cfg2a")
 raw_page("prof_gemm_r1_v1.ncu-rep", f"{tag}_ncu_full_dgemm_128x64_2cta.csv")
 raw_page("prof_gemm_r1.ncu-rep", f"{tag}_ncu_full_dgemm_128x128_1cta.csv")
 raw_page("prof_assemble_r1.ncu-rep", f"{tag}_ncu_full_assemble.csv")
-raw_page("prof_leaf_r1.ncu-rep", f"{tag}_ncu_full_panel_leaf_unrolled.csv")
+raw_page("prof_leaf_r3.ncu-rep", f"{tag}_ncu_full_panel_leaf.csv")
 for f in ("bench_1gpu.json", "leaf_timing.log"):
     if os.path.exists(os.path.join(G, f)): shutil.copy(os.path.join(G, f), os.path.join(P, f"{tag}_{f}"))
 print(sorted(os.listdir(P)))

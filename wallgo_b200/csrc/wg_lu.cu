@@ -188,6 +188,8 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
   for (int j = 0; j < w; ++j) {
     const int dj = c0 + j;
     const int par = j & 1;
+    const bool dbgc = dbg && j == 8;
+    if (dbgc) p.dbg[24] = clock64();
     if (tid == 0) mbar_expect_tx(reinterpret_cast<uint64_t*>(&sm.bars[par]), (uint32_t)(CL * SL * 8));
     // ---- thread-local, then warp-level candidate (current column = window slot 0)
     long long bk = -1;
@@ -203,7 +205,9 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
         kb = k;
       }
     }
-    if (lane == argmax_lane(bk, bp, true)) {
+    const int wl = argmax_lane(bk, bp, true);
+    if (dbgc) p.dbg[25] = clock64();
+    if (lane == wl) {
       double* slot = sm.warpSlot[warp];
 #pragma unroll
       for (int k = 0; k < R; ++k)
@@ -214,7 +218,9 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
       reinterpret_cast<long long*>(slot)[W] = bk;
       reinterpret_cast<long long*>(slot)[W + 1] = (long long)bp;
     }
+    if (dbgc) p.dbg[26] = clock64();
     __syncthreads();
+    if (dbgc) p.dbg[27] = clock64();
     // ---- CTA-level winner, pushed to every CTA of the cluster (st.async completes their mbarrier)
     if (warp * 32 < SL * (int)CL) {
       const double* s = sm.warpSlot[lane & (PNW - 1)];
@@ -228,7 +234,9 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
         st_async_u64(dsmem_map(base + 8u * e, dest), srcw[e], dsmem_map(barBase + 8u * par, dest));
       }
     }
+    if (dbgc) p.dbg[28] = clock64();
     mbar_wait(reinterpret_cast<uint64_t*>(&sm.bars[par]), (uint32_t)((j >> 1) & 1));
+    if (dbgc) p.dbg[29] = clock64();
     // ---- cluster-level winner = pivot row (window-aligned: urow[0] is the pivot element)
     const double* urow;
     {
@@ -241,6 +249,7 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
     const int mpos = (int)reinterpret_cast<const long long*>(urow)[W + 1];
     const bool sing = (mkey <= 0);
     const double rinv = sing ? 0.0 : 1.0 / urow[0];
+    if (dbgc) p.dbg[30] = clock64() + (rinv == 12345.678 ? 1 : 0);
     // the pivot row comes from below the top block: stage its rest-of-panel columns now
     if (ext > 0) {
       int sp = -1;
@@ -265,6 +274,7 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
         cp_async_commit();
       }
     }
+    if (dbgc) p.dbg[31] = clock64();
     double uv[W];
 #pragma unroll
     for (int c = 1; c < W; ++c) uv[c] = urow[c];
