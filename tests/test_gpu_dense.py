@@ -126,6 +126,27 @@ def test_lu_schedules_are_bit_identical(env, n):
     _check_factors(A, outs[0][0], outs[0][1])
 
 
+@pytest.mark.parametrize("n", [40, 700, 2600])
+def test_lu_32_column_leaves(env, n):
+    """The alternative 32-column leaf panel (rotating register window) is a different blocking of the same
+    partial-pivoting LU: same pivots on a generic matrix, factors equal to rounding."""
+    torch, lib, _ = env
+    rng = np.random.default_rng(11 * n)
+    A = rng.standard_normal((n, n))
+    b = rng.standard_normal(n)
+    LU0, ipiv0, info0, x0 = _lu(env, A, b)
+    try:
+        lib.wg_debug_leaf32(1)
+        LU1, ipiv1, info1, x1 = _lu(env, A, b)
+    finally:
+        lib.wg_debug_leaf32(0)
+    assert info0 == info1 == 0
+    assert np.array_equal(ipiv0, ipiv1)
+    assert np.max(np.abs(LU0 - LU1)) / np.max(np.abs(LU0)) < 1e-11
+    assert np.max(np.abs(x0 - x1)) / np.max(np.abs(x0)) < 1e-9
+    _check_factors(A, LU1, ipiv1)
+
+
 @pytest.mark.parametrize("n", [8, 50, 300])
 def test_lu_pivots_match_c_oracle(env, n):
     """Same pivot rule as dgetf2 (first maximal |a| in the column): identical ipiv and factors to rounding."""

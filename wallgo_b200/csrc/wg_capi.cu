@@ -90,6 +90,11 @@ int wg_set_bulk_priority_rest(int rest) {
   wg::lu_set_bulk_hi(rest);
   return WG_OK;
 }
+/* developer knob (not part of the public header): 32-column leaf panels on/off */
+int wg_debug_leaf32(int on) {
+  wg::lu_set_leaf32(on);
+  return WG_OK;
+}
 int wg_set_lookahead(int on) {
   wg::lu_set_lookahead(on);
   return WG_OK;

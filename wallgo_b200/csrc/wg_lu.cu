@@ -31,7 +31,6 @@ constexpr int PT = 512;       // threads per leaf-panel CTA
 constexpr int PNW = PT / 32;  // warps per leaf-panel CTA
 constexpr int MAXCL = 16;     // largest cluster
 constexpr int MAXEXT = 248;   // widest "rest of the panel" a leaf has to move (NB - 8)
-constexpr int MAXMOVE = 32;   // most rows a leaf can move per CTA (2 * 16)
 
 static long long* g_dbg_buf = nullptr;  // developer probe: timestamps of the leaf starting at column g_dbg_c0
 static int g_dbg_c0 = -1;
@@ -44,6 +43,11 @@ static int g_use_graph = 1;  // replay the factorisation as a CUDA graph (node p
 static int g_lookahead = 1;
 static int g_profile = 0;
 static int g_trace = 0;
+// 32-column leaves (fully rotating register window) whenever one row per thread fits the cluster.  Off by
+// default: measured 3 550-3 800 cycles per column against 2 800 for 16-column leaves (the candidate row is
+// twice as long), which cancels the eight TRSM+GEMM pairs per panel it saves.
+static int g_leaf32 = 0;
+void lu_set_leaf32(int on) { g_leaf32 = on; }
 void lu_set_profile(int on) { g_profile = on; }
 void lu_set_trace(int on) { g_trace = on; }
 void lu_set_tuning(int nb, int use_graph) {
@@ -96,12 +100,14 @@ __device__ __forceinline__ void st_async_u64(uint32_t remote_addr, unsigned long
 
 template <int W, int R>
 struct LeafSmem {
-  static constexpr int SL = W + 2;   // row values, key bits, position
-  static constexpr int TW = W + 1;   // padded tile row
+  static constexpr int SL = W + 2;           // row values, key bits, position
+  static constexpr int TC = W > 16 ? 16 : W; // columns per pass through the transposition tile
+  static constexpr int TW = TC + 1;          // padded tile row
+  static constexpr int MAXMOVE = 2 * W;      // most rows a leaf can move per CTA
   double warpSlot[PNW][SL];          // per-warp pivot candidates of the current column
   double cluSlot[2][MAXCL][SL];      // per-CTA candidates, double buffered by column parity
   double moveBuf[MAXMOVE][MAXEXT];   // rest-of-panel data of rows that change position
-  double tile[PNW][R][32][TW];       // the leaf block itself: load transpose, finished columns, store
+  double tile[PNW][R][32][TW];       // load/store transposition; W <= 16: also parks the finished columns
   unsigned long long bars[2];
   int moveDst[MAXMOVE];
   int moveCount;
@@ -111,15 +117,20 @@ struct LeafSmem {
 // Thread t of CTA r owns rows c0 + k*CL*PT + r*PT + t (k < R).  The not-yet-eliminated columns of a
 // row live in a ROTATING register window (a[k][0] is always the current column), so the column loop is
 // a real loop with static register indices and a small instruction footprint (a fully unrolled body is
-// ~180 KB of SASS and stalls on instruction fetch); finished columns are parked in the shared-memory
-// tile that is also used for the coalesced load and store of the block.
+// ~180 KB of SASS and stalls on instruction fetch).  W <= 16: finished columns are parked in the
+// shared-memory tile that is also used for the coalesced load and store of the block.  W = 32 (one row per
+// thread): the window rotates fully -- the finished entry re-enters at the tail, candidate rows are pushed
+// with their finished tail zeroed so the update leaves it untouched -- and after W steps the registers hold
+// the finished row in column order; the tile only transposes 16 columns at a time.
 template <int W, int R>
 __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p) {
   extern __shared__ __align__(16) unsigned char smraw[];
   using SM = LeafSmem<W, R>;
   SM& sm = *reinterpret_cast<SM*>(smraw);
   constexpr int SL = SM::SL;
-  constexpr int LPR = W / 2;        // lanes per row when moving double2
+  constexpr int TC = SM::TC;
+  constexpr bool ROT = (W > 16);    // fully rotating window (finished entries stay in registers)
+  constexpr int LPR = TC / 2;       // lanes per row when moving double2
   constexpr int RPI = 32 / LPR;     // rows per warp instruction
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -140,11 +151,13 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
     sm.moveCount = 0;
   }
   // the top w rows always leave or change position: stage their rest-of-panel columns right away
-  if (rank == 0 && warp < w && warp < m && ext > 0) {
-    const double* srow = A + (long long)(c0 + warp) * lda;
-    for (int e = lane; e < ext; e += 32) {
-      const int col = e < nLeft ? p.pc0 + e : c0 + w + (e - nLeft);
-      cp_async8(&sm.moveBuf[warp][e], srow + col, true);
+  if (rank == 0 && ext > 0) {
+    for (int rr = warp; rr < w && rr < m; rr += PNW) {
+      const double* srow = A + (long long)(c0 + rr) * lda;
+      for (int e = lane; e < ext; e += 32) {
+        const int col = e < nLeft ? p.pc0 + e : c0 + w + (e - nLeft);
+        cp_async8(&sm.moveBuf[rr][e], srow + col, true);
+      }
     }
   }
   cp_async_commit();
@@ -153,32 +166,40 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
   int pos[R], spos[R];
 #pragma unroll
   for (int k = 0; k < R; ++k) {
-    const int wbase = k * (int)(CL * PT) + (int)rank * PT + warp * 32;  // first row of this warp's 32
-    const int lr = wbase + lane;
-    const bool valid = lr < m;
-    pos[k] = valid ? c0 + lr : -1;
+    const int lr = k * (int)(CL * PT) + (int)rank * PT + warp * 32 + lane;
+    pos[k] = lr < m ? c0 + lr : -1;
     spos[k] = pos[k];
-    if (p.vec) {
-#pragma unroll
-      for (int i = 0; i < LPR; ++i) {
-        const int r = i * RPI + lane / LPR, cp = lane % LPR;
-        double2 v = make_double2(0.0, 0.0);
-        if (wbase + r < m && 2 * cp < w)
-          v = *reinterpret_cast<const double2*>(A + (long long)(c0 + wbase + r) * lda + c0 + 2 * cp);
-        sm.tile[warp][k][r][2 * cp] = v.x;
-        sm.tile[warp][k][r][2 * cp + 1] = v.y;
-      }
-    } else {
-      const double* src = A + (long long)(c0 + lr) * lda + c0;
-#pragma unroll
-      for (int c = 0; c < W; ++c) sm.tile[warp][k][lane][c] = (valid && c < w) ? src[c] : 0.0;
-    }
   }
-  __syncwarp();
 #pragma unroll
-  for (int k = 0; k < R; ++k)
+  for (int h = 0; h < W / TC; ++h) {   // TC columns per pass through the transposition tile
 #pragma unroll
-    for (int c = 0; c < W; ++c) a[k][c] = sm.tile[warp][k][lane][c];
+    for (int k = 0; k < R; ++k) {
+      const int wbase = k * (int)(CL * PT) + (int)rank * PT + warp * 32;  // first row of this warp's 32
+      const int lr = wbase + lane;
+      const bool valid = lr < m;
+      if (p.vec) {
+#pragma unroll
+        for (int i = 0; i < LPR; ++i) {
+          const int r = i * RPI + lane / LPR, cp = lane % LPR;
+          double2 v = make_double2(0.0, 0.0);
+          if (wbase + r < m && h * TC + 2 * cp < w)
+            v = *reinterpret_cast<const double2*>(A + (long long)(c0 + wbase + r) * lda + c0 + h * TC + 2 * cp);
+          sm.tile[warp][k][r][2 * cp] = v.x;
+          sm.tile[warp][k][r][2 * cp + 1] = v.y;
+        }
+      } else {
+        const double* src = A + (long long)(c0 + lr) * lda + c0 + h * TC;
+#pragma unroll
+        for (int c = 0; c < TC; ++c) sm.tile[warp][k][lane][c] = (valid && h * TC + c < w) ? src[c] : 0.0;
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < R; ++k)
+#pragma unroll
+      for (int c = 0; c < TC; ++c) a[k][h * TC + c] = sm.tile[warp][k][lane][c];
+    __syncwarp();
+  }
   cluster_sync_all();  // mbarriers of every CTA initialised before anybody signals them
   if (dbg) p.dbg[22] = clock64();
 
@@ -229,9 +250,18 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
       const int ww = argmax_lane(k2, p2, lane < PNW);
       const unsigned long long* srcw = reinterpret_cast<const unsigned long long*>(sm.warpSlot[ww]);
       const uint32_t base = smem_u32(&sm.cluSlot[par][rank][0]);
-      if (tid < SL * (int)CL) {
-        const int dest = tid / SL, e = tid - dest * SL;
-        st_async_u64(dsmem_map(base + 8u * e, dest), srcw[e], dsmem_map(barBase + 8u * par, dest));
+      if constexpr (SL * MAXCL <= PT) {
+        if (tid < SL * (int)CL) {
+          const int dest = tid / SL, e = tid - dest * SL;
+          st_async_u64(dsmem_map(base + 8u * e, dest), srcw[e], dsmem_map(barBase + 8u * par, dest));
+        }
+      } else {
+        for (int idx = tid; idx < SL * (int)CL; idx += PT) {   // SL * CL exceeds the CTA (W = 32, 16 CTAs)
+          const int dest = idx / SL, e = idx - dest * SL;
+          unsigned long long v = srcw[e];
+          if (ROT && e >= W - j && e < W) v = 0ull;   // finished tail of the window: must not take part in the update
+          st_async_u64(dsmem_map(base + 8u * e, dest), v, dsmem_map(barBase + 8u * par, dest));
+        }
       }
     }
     if (dbgc) p.dbg[28] = clock64();
@@ -275,21 +305,38 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
       }
     }
     if (dbgc) p.dbg[31] = clock64();
-    double uv[W];
+    if constexpr (!ROT) {
+      double uv[W];
 #pragma unroll
-    for (int c = 1; c < W; ++c) uv[c] = urow[c];
+      for (int c = 1; c < W; ++c) uv[c] = urow[c];
 #pragma unroll
-    for (int k = 0; k < R; ++k) {
-      if (pos[k] == mpos)
-        pos[k] = dj;
-      else if (pos[k] == dj)
-        pos[k] = mpos;
-      const bool elim = pos[k] > dj && !sing;
-      const double l = elim ? a[k][0] * rinv : a[k][0];   // multiplier, or the finished U / L entry
-      sm.tile[warp][k][lane][j] = l;
-      const double ml = elim ? -l : 0.0;
+      for (int k = 0; k < R; ++k) {
+        if (pos[k] == mpos)
+          pos[k] = dj;
+        else if (pos[k] == dj)
+          pos[k] = mpos;
+        const bool elim = pos[k] > dj && !sing;
+        const double l = elim ? a[k][0] * rinv : a[k][0];   // multiplier, or the finished U / L entry
+        sm.tile[warp][k][lane][j] = l;
+        const double ml = elim ? -l : 0.0;
 #pragma unroll
-      for (int c = 1; c < W; ++c) a[k][c - 1] = fma(ml, uv[c], a[k][c]);  // eliminate + rotate window
+        for (int c = 1; c < W; ++c) a[k][c - 1] = fma(ml, uv[c], a[k][c]);  // eliminate + rotate window
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        if (pos[k] == mpos)
+          pos[k] = dj;
+        else if (pos[k] == dj)
+          pos[k] = mpos;
+        const bool elim = pos[k] > dj && !sing;
+        const double l = elim ? a[k][0] * rinv : a[k][0];
+        const double ml = elim ? -l : 0.0;
+        // the pushed row carries zeros in its finished tail, so the FMA is a plain move there
+#pragma unroll
+        for (int c = 1; c < W; ++c) a[k][c - 1] = fma(ml, urow[c], a[k][c]);
+        a[k][W - 1] = l;
+      }
     }
     if (dbg) p.dbg[2 + (j & 15)] = clock64();
     if (rank == 0 && tid == 0) {
@@ -299,36 +346,65 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
   }
   if (dbg) p.dbg[1] = clock64();
 
+  if constexpr (ROT) {
+    // a leaf narrower than W: finish the rotation so that column i sits in register i
+#pragma unroll 1
+    for (int j = w; j < W; ++j) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const double t0 = a[k][0];
+#pragma unroll
+        for (int c = 1; c < W; ++c) a[k][c - 1] = a[k][c];
+        a[k][W - 1] = t0;
+      }
+    }
+  }
+
   // ---- rows go to their pivoted positions.  Unmoved rows of a warp are 32 consecutive matrix rows:
   //      the tile is stored so that every instruction writes whole 128-byte lines.
   __syncwarp();
 #pragma unroll
-  for (int k = 0; k < R; ++k) {
-    const int wbase = k * (int)(CL * PT) + (int)rank * PT + warp * 32;
-    const bool moved = pos[k] >= 0 && pos[k] != spos[k];
-    if (p.vec) {
-      const unsigned movedMask = __ballot_sync(0xffffffffu, moved);
+  for (int h = 0; h < W / TC; ++h) {
+    if constexpr (ROT) {
 #pragma unroll
-      for (int i = 0; i < LPR; ++i) {
-        const int r = i * RPI + lane / LPR, cp = lane % LPR;
-        if (wbase + r < m && 2 * cp < w && !((movedMask >> r) & 1u))
-          *reinterpret_cast<double2*>(A + (long long)(c0 + wbase + r) * lda + c0 + 2 * cp) =
-              make_double2(sm.tile[warp][k][r][2 * cp], sm.tile[warp][k][r][2 * cp + 1]);
-      }
-      if (moved) {
-        double* dst = A + (long long)pos[k] * lda + c0;
+      for (int k = 0; k < R; ++k)
 #pragma unroll
-        for (int c = 0; c < W; c += 2)
-          if (c < w)
-            *reinterpret_cast<double2*>(dst + c) =
-                make_double2(sm.tile[warp][k][lane][c], sm.tile[warp][k][lane][c + 1]);
-      }
-    } else if (pos[k] >= 0) {
-      double* dst = A + (long long)pos[k] * lda + c0;
-#pragma unroll
-      for (int c = 0; c < W; ++c)
-        if (c < w) dst[c] = sm.tile[warp][k][lane][c];
+        for (int c = 0; c < TC; ++c) sm.tile[warp][k][lane][c] = a[k][h * TC + c];
+      __syncwarp();
     }
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const int wbase = k * (int)(CL * PT) + (int)rank * PT + warp * 32;
+      const bool moved = pos[k] >= 0 && pos[k] != spos[k];
+      if (p.vec) {
+        const unsigned movedMask = __ballot_sync(0xffffffffu, moved);
+#pragma unroll
+        for (int i = 0; i < LPR; ++i) {
+          const int r = i * RPI + lane / LPR, cp = lane % LPR;
+          if (wbase + r < m && h * TC + 2 * cp < w && !((movedMask >> r) & 1u))
+            *reinterpret_cast<double2*>(A + (long long)(c0 + wbase + r) * lda + c0 + h * TC + 2 * cp) =
+                make_double2(sm.tile[warp][k][r][2 * cp], sm.tile[warp][k][r][2 * cp + 1]);
+        }
+        if (moved) {
+          double* dst = A + (long long)pos[k] * lda + c0 + h * TC;
+#pragma unroll
+          for (int c = 0; c < TC; c += 2)
+            if (h * TC + c < w)
+              *reinterpret_cast<double2*>(dst + c) =
+                  make_double2(sm.tile[warp][k][lane][c], sm.tile[warp][k][lane][c + 1]);
+        }
+      } else if (pos[k] >= 0) {
+        double* dst = A + (long long)pos[k] * lda + c0 + h * TC;
+#pragma unroll
+        for (int c = 0; c < TC; ++c)
+          if (h * TC + c < w) dst[c] = sm.tile[warp][k][lane][c];
+      }
+    }
+    if constexpr (ROT) __syncwarp();
+  }
+#pragma unroll
+  for (int k = 0; k < R; ++k) {
+    const bool moved = pos[k] >= 0 && pos[k] != spos[k];
     if (pos[k] >= 0) {
       if (pos[k] < c0 + w) p.grpSrcTop[pos[k]] = spos[k];
       if (spos[k] < c0 + w) {
@@ -945,6 +1021,7 @@ static int leaf(FactorCtx& c, int c0, int w, int pc0, int pc1) {
   };
   // one row per thread whenever the cluster can hold the block: the column loop is issue bound
   // (4 warps per scheduler), so fewer rows per thread is ~20% faster per column
+  if (c.wb == 32) return launch_leaf<32, 1>(pa, pick_cl(PT), c.st);
   if (c.wb == 16) {
     if (m <= c.p->maxCL * PT) return launch_leaf<16, 1>(pa, pick_cl(PT), c.st);
     return launch_leaf<16, 2>(pa, pick_cl(PT * 2), c.st);
@@ -1032,6 +1109,7 @@ int lu_profile_read(LuPlan* p, double* ms, double* flops, int* count) {
 }
 
 static int panel_width_class(LuPlan* p, int m) {
+  if (g_leaf32 && m <= p->maxCL * PT) return 32;
   if (m <= p->maxCL * PT * 2) return 16;
   if (m <= p->maxCL * PT * 4) return 8;
   return 0;
