@@ -325,15 +325,21 @@ class BoltzmannSolverB200Mixin:
             return []
         if concurrency is None or int(concurrency) <= 0:
             eng0 = self._getEngine()
-            free = eng0.torch.cuda.mem_get_info(eng0.dev)[0]
-            concurrency = self.autoConcurrency(eng0.n, free + (8 * eng0.n * eng0.n if eng0.A is not None else 0))
+            if getattr(self, "_autoSlots", None) is None or self._autoSlots[0] != eng0.n:
+                free = eng0.torch.cuda.mem_get_info(eng0.dev)[0]      # ~30 ms: asked once per system size
+                have = sum(8 * eng0.n * eng0.n for s_ in (getattr(self, "_sibs", None) or [self])
+                           if s_._engine is not None and s_._engine.A is not None)
+                self._autoSlots = (eng0.n, self.autoConcurrency(eng0.n, free + have))
+            concurrency = self._autoSlots[1]
         C = max(1, min(int(concurrency), nItems))
         sibs = self._siblings(C)
         torch = sibs[0]._getEngine().torch
+        import ctypes
         for s_ in sibs:
             eng = s_._getEngine()
             if getattr(s_, "_stream", None) is None:
                 s_._stream = torch.cuda.Stream(device=eng.dev)
+            eng.stream_ptr = ctypes.c_void_p(s_._stream.cuda_stream)   # pinned for the duration of the batch
         results = [None] * nItems
         n = sibs[0]._getEngine().n
         stagger = (2.0 / 3.0) * float(n) ** 3 / 20e12 / C   # rough LU time / C
@@ -381,19 +387,24 @@ class BoltzmannSolverB200Mixin:
                 results[it] = s_._wrapResults(dF, deltas, err, keep, peaks)
                 start(slot)
 
-        for slot in range(C):
-            if slot > 0:
-                time.sleep(stagger)
-            start(slot)
-        while any(st is not None for st in state):
-            progressed = False
+        try:
             for slot in range(C):
-                if state[slot] is not None and state[slot][2].query():
-                    advance(slot)
-                    progressed = True
-            if not progressed:
-                oldest = min((st[0], k) for k, st in enumerate(state) if st is not None)[1]
-                state[oldest][2].synchronize()
+                if slot > 0 and stagger > 1e-3:
+                    time.sleep(stagger)
+                start(slot)
+            while any(st is not None for st in state):
+                progressed = False
+                for slot in range(C):
+                    if state[slot] is not None and state[slot][2].query():
+                        advance(slot)
+                        progressed = True
+                if not progressed:
+                    oldest = min((st[0], k) for k, st in enumerate(state) if st is not None)[1]
+                    state[oldest][2].synchronize()
+        finally:
+            for s_ in sibs:
+                if s_._engine is not None:
+                    s_._engine.stream_ptr = None
         return results
 
     def _wrapResults(self, dF, deltas, err, keep, peaks):

@@ -55,6 +55,7 @@ class BoltzmannEngine:
         self.out_host = torch.empty(self.nout, dtype=f64).pin_memory()
         self.dF_in = torch.empty(self.n, dtype=f64, device=self.dev)
         self.launches = 0  # kernels launched through this engine (rough, for bench accounting)
+        self.stream_ptr = None
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -69,6 +70,9 @@ class BoltzmannEngine:
             pass
 
     def _stream(self):
+        # batch drivers pin the slot's stream once (stream_ptr) instead of asking torch on every call
+        if self.stream_ptr is not None:
+            return self.stream_ptr
         return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
 
     def _ensure_A(self):

@@ -129,12 +129,24 @@ def basisChangeMatrices(M, N, basisM, basisN):
 
 
 def tailConverging(coeffs, offset: int) -> bool:
-    """Sign of the least-squares slope of log|c_n| (reference polynomial.py:994-1033)."""
+    """Sign of the least-squares slope of log|c_n| (reference polynomial.py:994-1033).  The slope of a
+    straight-line fit has the sign of sum((x - mean x)(y - mean y)); that closed form decides whenever it
+    is clear of rounding, anything borderline or non-finite goes through np.polyfit exactly as the reference
+    does."""
     m = len(coeffs)
     if m < 2:
         return False
+    with np.errstate(divide="ignore"):
+        y = np.log(np.abs(coeffs))
+    if np.all(np.isfinite(y)):
+        xc = np.arange(m, dtype=np.float64)
+        xc -= xc.mean()
+        yc = y - y.mean()
+        s = float(xc @ yc)
+        if abs(s) > 1e-8 * float(np.abs(xc) @ np.abs(yc)):
+            return s < 0.0
     x = np.arange(m) + offset
-    fit = np.polyfit(x, np.log(np.abs(coeffs)), 1, cov=(m >= 3))
+    fit = np.polyfit(x, y, 1, cov=(m >= 3))
     slope = fit[0][0] if m >= 3 else fit[0]
     return bool(slope < 0)
 
