@@ -115,6 +115,9 @@ def test_checkLinearization_matches_reference(cuda_device, name):
     (2, 10, 9, dict(r=0.05, seed=5)),
     (3, 8, 7, dict(collisionMultiplier=1e-2, seed=7)),
     (1, 24, 13, dict(seed=2)),
+    (4, 8, 7, dict(seed=11)),              # four species (configs 4 and 5): off-diagonal blocks are collision only
+    (1, 6, 31, dict(seed=3)),              # N = 31, the momentum grid of config 5 (q = 900)
+    (2, 5, 21, dict(r=0.05, seed=4)),      # N = 21 with two species
 ])
 def test_against_oracle_on_seeded_inputs(cuda_device, oracle, P, M, N, kw):
     """Sizes without a golden file: CUDA vs the oracle on the same synthetic inputs."""
