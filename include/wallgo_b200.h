@@ -92,6 +92,14 @@ int wg_factor(wg_solver* s, double* A_dev, long long lda, void* stream);
 /* ... and the triangular solves; b_dev (n) is overwritten by the solution.  May be called again with
  * another right-hand side (checkLinearization re-uses the factors, boltzmann.py:541-550). */
 int wg_solve(wg_solver* s, const double* LU_dev, long long lda, double* b_dev, void* stream);
+/* Batched form for scans / many small systems: B independent systems (one solver handle, operator buffer,
+ * source vector and stream each) are assembled, factored and solved; call b is enqueued on streams[b], so
+ * the systems overlap on the GPU (a single LU cannot fill a B200 during its panel chain).  Equivalent to B
+ * times wg_assemble(parts = 3) + wg_factor + wg_solve; S_dev[b] holds deltaF of system b afterwards.
+ * Returns the first non-zero code (systems before it are enqueued). */
+int wg_assemble_factor_solve_batched(int B, wg_solver* const* s, const double* const* profiles_dev,
+                                     const double* vw, const double* collisionMultiplier, double* const* A_dev,
+                                     const long long* lda, double* const* S_dev, void* const* streams);
 /* synchronises `stream` and returns LAPACK-style info of the last wg_factor */
 int wg_info(wg_solver* s, void* stream, int* info_host);
 /* checkSpectralConvergence, first half (boltzmann.py:376-397): Chebyshev coefficients (kept inside the

@@ -249,3 +249,42 @@ def test_getDeltasBatch_equals_sequential(cuda_device):
             assert np.array_equal(a.Deltas.Delta11.coefficients, b.Deltas.Delta11.coefficients)
             assert a.truncatedTail == b.truncatedTail and a.spectralPeaks == b.spectralPeaks
     assert solver.getDeltasBatch([], concurrency=2) == []
+
+
+def test_batched_c_abi_equals_single_calls(cuda_device):
+    """wg_assemble_factor_solve_batched (B systems, B streams, one C call) gives exactly the deltaF of the
+    single-system calls."""
+    import torch
+    import wallgo_b200 as wb
+    from wallgo_b200 import synthetic
+    from wallgo_b200.engine import BoltzmannEngine
+
+    P, M, N = 2, 10, 7
+    grid = synthetic.makeGrid(M, N)
+    parts = synthetic.makeParticles(P)
+    solver = wb.BoltzmannSolver(grid)
+    solver.updateParticleList(parts)
+    solver.setCollisionArray(synthetic.makeCollision(grid, parts))
+    bgs = [synthetic.makeBackground(grid, velocityMid=-0.3 - 0.07 * i) for i in range(3)]
+    sibs = solver._siblings(3)
+    engines, vws, single = [], [], []
+    for s_, bg in zip(sibs, bgs):
+        s_.setBackground(bg)
+        eng = s_._getEngine()
+        s_._uploadBackground(eng)
+        vw = float(s_.background.velocityWall)
+        eng.assemble(vw, 1.0)
+        eng.factor()
+        eng.solve()
+        single.append(eng.S.clone())
+        engines.append(eng)
+        vws.append(vw)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in engines]
+    for st in streams:
+        st.wait_stream(torch.cuda.current_stream())
+    BoltzmannEngine.solve_batched(engines, vws, [1.0] * 3, streams)
+    torch.cuda.synchronize()
+    for eng, ref in zip(engines, single):
+        assert eng.info() == 0
+        assert torch.equal(eng.S, ref)

@@ -34,6 +34,9 @@ SYMBOLS = {
     "wg_assemble": (C.c_int, [_vp, _dp, C.c_double, C.c_double, C.c_int, _dp, C.c_longlong, _dp, _vp]),
     "wg_factor": (C.c_int, [_vp, _dp, C.c_longlong, _vp]),
     "wg_solve": (C.c_int, [_vp, _dp, C.c_longlong, _dp, _vp]),
+    "wg_assemble_factor_solve_batched": (C.c_int, [C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_double),
+                                                   C.POINTER(C.c_double), C.POINTER(_vp), C.POINTER(C.c_longlong),
+                                                   C.POINTER(_vp), C.POINTER(_vp)]),
     "wg_info": (C.c_int, [_vp, _vp, C.POINTER(C.c_int)]),
     "wg_spectra": (C.c_int, [_vp, _dp, _dp, _vp]),
     "wg_moments": (C.c_int, [_vp, _dp, _dp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _vp]),

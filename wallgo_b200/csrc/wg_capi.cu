@@ -310,6 +310,22 @@ int wg_solve(wg_solver* s, const double* LU_dev, long long lda, double* b_dev, v
   return wg::lu_solve(s->plan, LU_dev, lda, b_dev, (cudaStream_t)stream);
 }
 
+int wg_assemble_factor_solve_batched(int B, wg_solver* const* s, const double* const* profiles_dev,
+                                     const double* vw, const double* collisionMultiplier, double* const* A_dev,
+                                     const long long* lda, double* const* S_dev, void* const* streams) {
+  WG_REQUIRE(B >= 0 && (B == 0 || (s && profiles_dev && vw && collisionMultiplier && A_dev && lda && S_dev && streams)),
+             "wg_assemble_factor_solve_batched: NULL argument");
+  for (int b = 0; b < B; ++b) {
+    int rc = wg_assemble(s[b], profiles_dev[b], vw[b], collisionMultiplier[b], 3, A_dev[b], lda[b], S_dev[b], streams[b]);
+    if (rc) return rc;
+    rc = wg_factor(s[b], A_dev[b], lda[b], streams[b]);
+    if (rc) return rc;
+    rc = wg_solve(s[b], A_dev[b], lda[b], S_dev[b], streams[b]);
+    if (rc) return rc;
+  }
+  return WG_OK;
+}
+
 int wg_info(wg_solver* s, void* stream, int* info_host) {
   WG_REQUIRE(s && info_host, "wg_info: NULL argument");
   WG_CUDA(cudaMemcpyAsync(info_host, s->info, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));

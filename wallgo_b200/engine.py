@@ -211,6 +211,27 @@ class BoltzmannEngine:
         check(self.lib.wg_change_basis(self.h, int(stage), src.data_ptr(), dst.data_ptr(), self._stream()),
               "wg_change_basis")
 
+    # ------------------------------------------------------------------ batched form of the C ABI
+    @staticmethod
+    def solve_batched(engines, vws, collisionMultipliers, streams):
+        """assemble + LU + solve of several engines' current backgrounds with one C call
+        (wg_assemble_factor_solve_batched); engine b is enqueued on streams[b] (torch.cuda.Stream)."""
+        B = len(engines)
+        if B == 0:
+            return
+        lib = engines[0].lib
+        vp = C.c_void_p * B
+        hs = vp(*[e.h for e in engines])
+        profs = vp(*[e.prof.data_ptr() for e in engines])
+        As = vp(*[e._ensure_A().data_ptr() for e in engines])
+        Ss = vp(*[e.S.data_ptr() for e in engines])
+        sts = vp(*[st.cuda_stream for st in streams])
+        ldas = (C.c_longlong * B)(*[e.A.stride(0) for e in engines])
+        vw = (C.c_double * B)(*[float(v) for v in vws])
+        cm = (C.c_double * B)(*[float(c) for c in collisionMultipliers])
+        check(lib.wg_assemble_factor_solve_batched(B, hs, profs, vw, cm, As, ldas, Ss, sts),
+              "wg_assemble_factor_solve_batched")
+
     # ------------------------------------------------------------------ fused device step (bench)
     def step_device(self, vw: float, collisionMultiplier: float, keep, roundtrip: bool = True):
         """assemble -> LU -> solve -> spectra -> truncate/moments, inputs already in HBM, no host sync."""
