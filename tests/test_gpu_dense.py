@@ -126,6 +126,37 @@ def test_lu_schedules_are_bit_identical(env, n):
     _check_factors(A, outs[0][0], outs[0][1])
 
 
+def test_lu_near_far_split_is_bit_identical(env):
+    """n >= 8192 splits the bulk columns over two streams (the far part runs a step behind): a pure
+    re-scheduling, so factors and pivots equal the unsplit schedule bit for bit, on streams and as a graph."""
+    torch, lib, _ = env
+    n = 8448
+    rng = np.random.default_rng(5)
+    A = rng.standard_normal((n, n))
+    outs = []
+    try:
+        for graph, split in ((1, 1), (1, 0), (0, 1)):
+            lib.wg_set_tuning(256, graph)
+            lib.wg_debug_split(split)
+            LU, ipiv, info, _ = _lu(env, A)
+            assert info == 0
+            outs.append((LU, ipiv))
+    finally:
+        lib.wg_set_tuning(256, 1)
+        lib.wg_debug_split(1)
+    for LU, ipiv in outs[1:]:
+        assert np.array_equal(outs[0][1], ipiv) and np.array_equal(outs[0][0], LU)
+    # P A = L U on a sample of rows (the full product at this size is a CPU-minute)
+    LU, ipiv = outs[0]
+    perm = np.arange(n)
+    for i, pv in enumerate(ipiv):
+        perm[i], perm[pv] = perm[pv], perm[i]
+    rows = rng.choice(n, size=64, replace=False)
+    L = np.tril(LU, -1) + np.eye(n)
+    U = np.triu(LU)
+    assert np.max(np.abs(L[rows] @ U - A[perm[rows]])) < 1e-9
+
+
 @pytest.mark.parametrize("n", [40, 700, 2600])
 def test_lu_32_column_leaves(env, n):
     """The alternative 32-column leaf panel (rotating register window) is a different blocking of the same

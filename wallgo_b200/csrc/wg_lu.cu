@@ -877,6 +877,9 @@ struct LuPlan {
   double *Sc = nullptr, *Sc2 = nullptr;    // row staging of the chain permutation (256 x 256 each)
   cudaStream_t panelStream = nullptr;  // highest priority: the critical chain (next panel's columns + panel)
   cudaStream_t bulkHiStream = nullptr; // bulk work of the latency-bound end of the factorisation
+  cudaStream_t farStream = nullptr;    // bulk work of the right-most columns while the trailing matrix is large
+  double *Sf = nullptr, *Sf2 = nullptr;
+  cudaEvent_t evFar = nullptr, evNear = nullptr;
   int prioChain = 0, prioBulkHi = 0;
   cudaEvent_t evPhase = nullptr;
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
@@ -956,6 +959,13 @@ int lu_plan_create(int n, LuPlan** out) {
   p->prioBulkHi = prHigh < prLow ? prHigh + 1 : prHigh;
   WG_CUDA(cudaStreamCreateWithPriority(&p->bulkHiStream, cudaStreamNonBlocking, p->prioBulkHi));
   WG_CUDA(cudaEventCreateWithFlags(&p->evPhase, cudaEventDisableTiming));
+  WG_CUDA(cudaStreamCreateWithPriority(&p->farStream, cudaStreamNonBlocking, prLow));
+  WG_CUDA(cudaEventCreateWithFlags(&p->evFar, cudaEventDisableTiming));
+  WG_CUDA(cudaEventCreateWithFlags(&p->evNear, cudaEventDisableTiming));
+  if (n >= 8192) {
+    WG_CUDA(cudaMalloc(&p->Sf, sbytes));
+    WG_CUDA(cudaMalloc(&p->Sf2, sbytes));
+  }
   WG_CUDA(cudaEventCreateWithFlags(&p->evFork, cudaEventDisableTiming));
   WG_CUDA(cudaEventCreateWithFlags(&p->evJoin, cudaEventDisableTiming));
   *out = p;
@@ -968,6 +978,11 @@ void lu_plan_destroy(LuPlan* p) {
   if (p->solveExec) cudaGraphExecDestroy(p->solveExec);
   if (p->panelStream) cudaStreamDestroy(p->panelStream);
   if (p->bulkHiStream) cudaStreamDestroy(p->bulkHiStream);
+  if (p->farStream) cudaStreamDestroy(p->farStream);
+  if (p->evFar) cudaEventDestroy(p->evFar);
+  if (p->evNear) cudaEventDestroy(p->evNear);
+  cudaFree(p->Sf);
+  cudaFree(p->Sf2);
   if (p->evPhase) cudaEventDestroy(p->evPhase);
   if (p->evFork) cudaEventDestroy(p->evFork);
   if (p->evJoin) cudaEventDestroy(p->evJoin);
@@ -1116,6 +1131,8 @@ static int panel_width_class(LuPlan* p, int m) {
 }
 
 static int g_hi_rest = 8192;  // bulk work moves to the high-priority bulk stream once the trailing matrix is this small
+static int g_split = 50;      // two bulk streams while the trailing matrix is large: far part starts at this % of n (0: off)
+void lu_set_split(int on) { g_split = on == 1 ? 50 : on; }
 void lu_set_bulk_hi(int rest) { g_hi_rest = rest; }
 
 static int apply_perm(LuPlan* p, double* A, long long lda, ColMap cm, int k, int nb, int pnl, double* S, double* S2,
@@ -1154,6 +1171,13 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
   } prioGuard;
   cudaStream_t bs = st;    // stream of the bulk work
   int bulkPrio = INT_MIN;
+  // While the trailing matrix is large the bulk columns are split at a fixed column X: the near part
+  // [.., X) stays on the bulk stream (the chain depends on it), the far part [X, n) runs one step behind on
+  // its own low-priority stream, so the latency-bound interchange + TRSM of one part overlaps the other's GEMM.
+  const int npan = wg_cdiv(n, NB);
+  const int X = (look && g_split > 0 && g_split < 100 && p->Sf && n >= 8192) ? NB * ((npan * g_split + 99) / 100) : n;
+  cudaStream_t fs = p->farStream;
+  bool farOn = false;
   bool panelDone = false;  // panel [k, k+nb) already factored by the chain of the previous step
   for (int k = 0, pnl = 0; k < n; k += NB, ++pnl) {
     const int nb = NB < n - k ? NB : n - k;
@@ -1193,6 +1217,18 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
       bs = p->bulkHiStream;
       bulkPrio = p->prioBulkHi;
     }
+    const int R0 = k + nb + nb2;   // first bulk column right of the chain's block
+    const bool useFar = X < n && R0 + 2 * NB <= X;
+    if (farOn && !useFar) {        // the near part is used up: the far columns come back to the bulk stream
+      WG_CUDA(cudaEventRecord(p->evFar, fs));
+      WG_CUDA(cudaStreamWaitEvent(bs, p->evFar, 0));
+      farOn = false;
+    } else if (!farOn && useFar) {
+      WG_CUDA(cudaEventRecord(p->evFar, bs));
+      WG_CUDA(cudaStreamWaitEvent(fs, p->evFar, 0));
+      farOn = true;
+    }
+    const int Xe = farOn ? X : n;  // end of the near part
     // ---- critical chain: columns of the next panel, then the next panel itself
     cudaStream_t cs = p->panelStream;
     WG_CUDA(cudaEventRecord(p->evFork, bs));
@@ -1214,20 +1250,40 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
     WG_CUDA(cudaEventRecord(p->evJoin, cs));
     trace_mark(p, cs, pnl, 4);
     g_wg_launch_prio = bulkPrio;
-    // ---- bulk: every other column
-    rc = apply_perm(p, A, lda, ColMap{n - nb - nb2, k, 0, nb + nb2}, k, nb, pnl, p->S, p->S2, c.vecA, bs);
+    // ---- bulk: right of the chain's block up to Xe; the finished columns left of the panel too unless the
+    //      far stream is on (they are read by the far GEMM of the previous step, so it interchanges them itself)
+    rc = apply_perm(p, A, lda, farOn ? ColMap{Xe - R0, Xe - R0, R0, 0} : ColMap{k + (Xe - R0), k, 0, nb + nb2}, k, nb,
+                    pnl, p->S, p->S2, c.vecA, bs);
     if (rc) return rc;
     trace_mark(p, bs, pnl, 1);
-    rc = trsm_rec(L11, lda, U12 + nb2, lda, nb, rest - nb2, bs);
+    rc = trsm_rec(L11, lda, U12 + nb2, lda, nb, Xe - R0, bs);
     if (rc) return rc;
     trace_mark(p, bs, pnl, 2);
-    prof_mark(p, bs, 2.0 * rest * (double)(rest - nb2) * nb, true);
-    rc = dgemm_sub(C22 + nb2, L21, U12 + nb2, rest, rest - nb2, nb, lda, lda, lda, bs);
+    prof_mark(p, bs, 2.0 * rest * (double)(Xe - R0) * nb, true);
+    rc = dgemm_sub(C22 + nb2, L21, U12 + nb2, rest, Xe - R0, nb, lda, lda, lda, bs);
     if (rc) return rc;
     prof_mark(p, bs, 0.0, false);
     trace_mark(p, bs, pnl, 3);
+    if (farOn) {   // ---- far columns [X, n) and the finished columns [0, k), running behind the near part
+      WG_CUDA(cudaEventRecord(p->evNear, bs));
+      g_wg_launch_prio = INT_MIN;
+      const int off = X - (k + nb);
+      rc = apply_perm(p, A, lda, ColMap{k + (n - X), k, 0, X - k}, k, nb, pnl, p->Sf, p->Sf2, c.vecA, fs);
+      if (rc) return rc;
+      rc = trsm_rec(L11, lda, U12 + off, lda, nb, n - X, fs);
+      if (rc) return rc;
+      rc = dgemm_sub(C22 + off, L21, U12 + off, rest, n - X, nb, lda, lda, lda, fs);
+      if (rc) return rc;
+      WG_CUDA(cudaStreamWaitEvent(fs, p->evJoin, 0));   // its next step needs the next panel ...
+      WG_CUDA(cudaStreamWaitEvent(fs, p->evNear, 0));   // ... and interchanges rows of L21 that this near GEMM reads
+      g_wg_launch_prio = bulkPrio;
+    }
     WG_CUDA(cudaStreamWaitEvent(bs, p->evJoin, 0));
     panelDone = true;
+  }
+  if (farOn) {
+    WG_CUDA(cudaEventRecord(p->evFar, fs));
+    WG_CUDA(cudaStreamWaitEvent(bs, p->evFar, 0));
   }
   if (bs != st) {
     WG_CUDA(cudaEventRecord(p->evPhase, bs));
