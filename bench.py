@@ -338,11 +338,13 @@ def run_b200(a):
     # one more solo factorisation on plain streams (events cannot sit inside the CUDA graph) with every
     # trailing-update GEMM launch bracketed by CUDA events on its launching stream
     lib.wg_set_tuning(a.nb, 0)
+    lib.wg_set_bulk_split(0)     # one trailing-update launch per step, so a launch is timed on its own stream
     lib.wg_profile_gemm(engines[0].h, 1, None, None, None)
     step(engines[0], W)
     torch.cuda.synchronize()
     lib.wg_profile_gemm(engines[0].h, 0, C.byref(gms), C.byref(gfl), C.byref(gcnt))
     lib.wg_set_tuning(a.nb, a.graph)
+    lib.wg_set_bulk_split(1)
     gemm_tf = gfl.value / (gms.value * 1e-3) / 1e12 if gms.value > 0 else float("nan")
     stage = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(4)] for e in evs]).mean(axis=0)
 
@@ -441,7 +443,8 @@ def run_b200(a):
                          "traffic": 4.24e9 if (P, M, N) == (1, 40, 21) else None,
                          "launches_timed": gcnt.value, "ms_timed": gms.value,
                          "algorithmic": "2*M*N*K flops of every trailing-update launch / its CUDA-event duration on the "
-                                        "launching stream, summed over the solo pass (look-ahead panels run beside it); "
+                                        "launching stream, summed over one solo factorisation on plain streams with the "
+                                        "bulk columns unsplit (the look-ahead chain runs beside it); "
                                         "traffic = dram read+write of the first-step launch (15344^2 x 256) from "
                                         "profiles/r01_ncu_full_dgemm_128x64_2cta.csv vs 3.83e9 algorithmic",
                          "peak_source": "measured in this run: torch.matmul (cuBLAS DGEMM) fp64 8192^3 best of 5; "

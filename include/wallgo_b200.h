@@ -48,6 +48,11 @@ int wg_set_lookahead(int on);
  * high-priority stream, so a second system sharing the GPU cannot starve this one's latency-bound tail
  * (default 8192; 0 disables) */
 int wg_set_bulk_priority_rest(int rest);
+/* percent: while the trailing matrix is large (n >= 8192) the bulk columns right of this percentage of n are
+ * updated by a second, low-priority stream that runs one step behind the first, so the latency-bound
+ * interchange + TRSM of one part overlaps the other's GEMM (default 50; 0 disables, 1 = default).  Pure
+ * scheduling: results are bit-identical for every value. */
+int wg_set_bulk_split(int percent);
 
 /* ---- lifecycle : BoltzmannSolver.__init__ + updateParticleList (boltzmann.py:52-139) */
 int wg_create(int P, int M, int N, int device, wg_solver** out);

@@ -137,13 +137,13 @@ def test_lu_near_far_split_is_bit_identical(env):
     try:
         for graph, split in ((1, 1), (1, 0), (0, 1)):
             lib.wg_set_tuning(256, graph)
-            lib.wg_debug_split(split)
+            lib.wg_set_bulk_split(split)
             LU, ipiv, info, _ = _lu(env, A)
             assert info == 0
             outs.append((LU, ipiv))
     finally:
         lib.wg_set_tuning(256, 1)
-        lib.wg_debug_split(1)
+        lib.wg_set_bulk_split(1)
     for LU, ipiv in outs[1:]:
         assert np.array_equal(outs[0][1], ipiv) and np.array_equal(outs[0][0], LU)
     # P A = L U on a sample of rows (the full product at this size is a CPU-minute)

@@ -11,7 +11,7 @@ ap.add_argument("--graph", type=int, default=0); ap.add_argument("--threads", ty
 ap.add_argument("--stagger", type=float, default=0.05)
 a = ap.parse_args()
 lib = _lib.load(); lib.wg_set_tuning(256, a.graph)
-if os.environ.get("WG_SPLIT"): lib.wg_debug_split(int(os.environ["WG_SPLIT"]))
+if os.environ.get("WG_SPLIT"): lib.wg_set_bulk_split(int(os.environ["WG_SPLIT"]))
 grid = synthetic.makeGrid(a.M, a.N); parts = synthetic.makeParticles(a.P)
 s = wb.BoltzmannSolver(grid); s.updateParticleList(parts)
 s.setBackground(synthetic.makeBackground(grid)); s.setCollisionArray(synthetic.makeCollision(grid, parts))

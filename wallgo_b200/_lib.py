@@ -21,6 +21,7 @@ SYMBOLS = {
     "wg_set_tuning": (C.c_int, [C.c_int, C.c_int]),
     "wg_set_lookahead": (C.c_int, [C.c_int]),
     "wg_set_bulk_priority_rest": (C.c_int, [C.c_int]),
+    "wg_set_bulk_split": (C.c_int, [C.c_int]),
     "wg_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
     "wg_destroy": (C.c_int, [_vp]),
     "wg_dims": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -95,9 +95,8 @@ int wg_debug_leaf32(int on) {
   wg::lu_set_leaf32(on);
   return WG_OK;
 }
-/* developer knob (not part of the public header): near/far split of the bulk columns on/off */
-int wg_debug_split(int on) {
-  wg::lu_set_split(on);
+int wg_set_bulk_split(int percent) {
+  wg::lu_set_split(percent);
   return WG_OK;
 }
 int wg_set_lookahead(int on) {
