@@ -44,6 +44,10 @@ raw_page("prof_gemm_r1_v1.ncu-rep", f"{tag}_ncu_full_dgemm_128x64_2cta.csv")
 raw_page("prof_gemm_r1.ncu-rep", f"{tag}_ncu_full_dgemm_128x128_1cta.csv")
 raw_page("prof_assemble_r1.ncu-rep", f"{tag}_ncu_full_assemble.csv")
 raw_page("prof_leaf_r3.ncu-rep", f"{tag}_ncu_full_panel_leaf.csv")
+raw_page("prof_trsm_r1.ncu-rep", f"{tag}_ncu_full_trsm_strip.csv")
+raw_page("prof_trisolve_r1.ncu-rep", f"{tag}_ncu_full_trisolve_step.csv")
+raw_page("prof_moments_r1.ncu-rep", f"{tag}_ncu_full_truncation_moments.csv")
+raw_page("prof_perm_r1.ncu-rep", f"{tag}_ncu_full_perm_gather.csv")
 for f in ("bench_1gpu.json", "leaf_timing.log"):
     if os.path.exists(os.path.join(G, f)): shutil.copy(os.path.join(G, f), os.path.join(P, f"{tag}_{f}"))
 print(sorted(os.listdir(P)))
