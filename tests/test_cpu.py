@@ -288,3 +288,44 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 assert "oracle" not in open(os.path.join(dirpath, f)).read().lower().replace(
                     "c oracle", ""), f"{f} mentions the oracle"
+
+
+def test_tail_decision_equals_polyfit():
+    """The truncation decision is the sign of a least-squares slope (polynomial.py:994-1033); the closed form
+    used on the host path must decide exactly as np.polyfit does, including degenerate spectra."""
+    import warnings
+    from wallgo_b200.spectral import tailConverging
+
+    def reference(coeffs, offset):
+        m = len(coeffs)
+        if m < 2:
+            return False
+        with warnings.catch_warnings(), np.errstate(divide="ignore", invalid="ignore"):
+            warnings.simplefilter("ignore")
+            fit = np.polyfit(np.arange(m) + offset, np.log(np.abs(coeffs)), 1, cov=(m >= 3))
+        slope = fit[0][0] if m >= 3 else fit[0]
+        return bool(slope < 0)
+
+    rng = np.random.default_rng(0)
+    cases = []
+    for _ in range(1500):
+        m = int(rng.integers(1, 14))
+        decay = rng.uniform(-1.5, 1.5)
+        cases.append(np.exp(decay * np.arange(m) + rng.normal(0, rng.uniform(0, 2), m)) * rng.choice([-1, 1], m))
+    cases += [np.ones(6), np.zeros(5), np.array([1.0, 0.0, 1e-3, 1e-6]), np.array([2.0, 2.0]), np.array([1e-300, 1e300]),
+              np.array([1.0, 1.0 + 1e-15, 1.0, 1.0 - 1e-15])]
+    with warnings.catch_warnings(), np.errstate(divide="ignore", invalid="ignore"):
+        warnings.simplefilter("ignore")
+        for c in cases:
+            for off in (0, 7):
+                assert tailConverging(c, off) == reference(c, off), (c, off)
+
+
+def test_auto_concurrency_policy():
+    import wallgo_b200 as wb
+
+    ac = wb.BoltzmannSolver.autoConcurrency
+    assert ac(15600) == 3 and ac(11600) == 4 and ac(8700) == 4 and ac(3800) == 8 and ac(1900) == 32
+    assert ac(31200, freeBytes=20 * 2**30) == 1          # one 7.8 GB operator + workspace in 60 % of 20 GB
+    assert ac(15600, freeBytes=170 * 2**30) == 3
+    assert ac(1900, freeBytes=2**30) >= 1
