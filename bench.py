@@ -305,6 +305,9 @@ def run_b200(a):
     streams = [torch.cuda.Stream(device=dev) for _ in range(C_)]
     own_prof = [e.prof for e in engines]
 
+    # the library's own path (BoltzmannSolver._solveOnDevice): wg_factor + wg_solve
+    fused_now = [False]
+
     def step(e, i, rec=None):
         e.prof = profs[i]
         if rec:
@@ -312,10 +315,19 @@ def run_b200(a):
         e.assemble(vws[i], 1.0)
         if rec:
             rec[1].record()
-        e.factor()
-        if rec:
+        if rec and len(rec) > 5:      # stage breakdown: factorisation and both triangular solves as separate calls
+            e.factor()
             rec[2].record()
-        e.solve()
+            e.solve()
+        elif fused_now[0]:             # alternative entry: forward solve fused into the factorisation
+            e.factor_solve()
+            if rec:
+                rec[2].record()
+        else:
+            e.factor()
+            e.solve()
+            if rec:
+                rec[2].record()
         if rec:
             rec[3].record()
         e.spectra_async(e.S)
@@ -347,7 +359,14 @@ def run_b200(a):
     lib.wg_set_bulk_split(1)
     gemm_tf = gfl.value / (gms.value * 1e-3) / 1e12 if gms.value > 0 else float("nan")
     stage = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(4)] for e in evs]).mean(axis=0)
+    # the same with factorisation and triangular solves as separate calls (comparable with LAPACK getrf / getrs)
+    evu = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+    step(engines[0], W, evu)
+    step(engines[0], W, evu)
+    torch.cuda.synchronize()
+    unfused = [evu[j].elapsed_time(evu[j + 1]) for j in range(4)]
 
+    fused_now[0] = bool(a.fused)
     pm = 4 * P * (M - 1)
     gathered = torch.empty(world * pm, dtype=torch.float64, device=dev) if world > 1 else None
     sampler = ClockSampler(local)
@@ -419,7 +438,7 @@ def run_b200(a):
     if rank == 0:
         hbm_peak, hbm_src = measured_peaks()
         lu_flops = 2.0 / 3.0 * float(n) ** 3
-        lu_tf_solo = lu_flops / (stage[1] * 1e-3) / 1e12
+        lu_tf_solo = lu_flops / (unfused[1] * 1e-3) / 1e12
         lu_tf = K * lu_flops / (ms * 1e-3) / 1e12   # whole-GPU FP64 rate over the timed region (LU flops only)
         asm_gbs = (8.0 * n * n + 8.0 * n) / (stage[0] * 1e-3) / 1e9
         line = {
@@ -433,8 +452,9 @@ def run_b200(a):
                        "lu": {"nb": a.nb, "cuda_graph": bool(a.graph)},
                        "concurrency": f"{C_} independent systems in flight per GPU (staggered streams)",
                        "parallelism": f"{world} x independent systems, no collective inside a solve"},
-            "stages_ms_solo": {"assemble": stage[0], "lu_factor": stage[1], "tri_solve": stage[2],
-                               "spectra_moments": stage[3], "lu_tflops_solo": lu_tf_solo,
+            "stages_ms_solo": {"assemble": stage[0], "lu_factor_and_solves": stage[1],
+                               "spectra_moments": stage[3], "lu_factor": unfused[1],
+                               "tri_solve": unfused[2], "lu_tflops_solo": lu_tf_solo,
                                "note": "one system alone on the GPU, CUDA events around each stage"},
             "latency_ms_sequential_getDeltas": seq_ms,
             "roofline": {"kernel": "dgemm_sub_kernel<128,64,16,2,2,3> (trailing update of the LU, DMMA.8x8x4)",
@@ -494,6 +514,7 @@ def main():
     ap.add_argument("--concurrency", type=int, default=0, help="independent systems in flight per GPU (0: auto)")
     ap.add_argument("--bulk-hi", type=int, default=-1, help="developer knob: wg_set_bulk_priority_rest")
     ap.add_argument("--stagger", type=float, default=-1.0, help="developer knob: seconds between slot starts")
+    ap.add_argument("--fused", type=int, default=0, help="developer knob: 1 = wg_factor_solve, 0 = wg_factor + wg_solve (shipped path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scan-points", type=int, default=256, help="vw-scan points of the secondary metric (0: skip)")
     ap.add_argument("--scan-workload", default="cfg4", choices=sorted(WORKLOADS))

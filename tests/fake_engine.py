@@ -139,6 +139,9 @@ class FakeEngine:
         b.arr[...] = np.linalg.solve(self.A.arr, b.arr)
         return b
 
+    def factor_solve(self, b=None):
+        return self.solve(b)
+
     def info(self):
         return 0
 

@@ -319,3 +319,39 @@ def test_other_baseline_sizes_residual(cuda_device, P, M, N):
         for a, b in zip(seq, out):
             assert np.array_equal(a.deltaF, b.deltaF)
             assert np.array_equal(a.Deltas.Delta00.coefficients, b.Deltas.Delta00.coefficients)
+
+
+@pytest.mark.parametrize("P,M,N", [(1, 6, 5), (2, 12, 7), (1, 20, 11), (3, 30, 11)])
+def test_fused_forward_solve_equals_separate_solves(cuda_device, P, M, N):
+    """wg_factor_solve (forward substitution riding along inside the factorisation, then the backward solve)
+    against wg_factor + wg_solve on the same operator: same factors bit for bit, solutions equal to rounding,
+    and the factors remain usable for a later wg_solve."""
+    import torch
+    import wallgo_b200 as wb
+    from wallgo_b200 import synthetic
+
+    grid = synthetic.makeGrid(M, N)
+    parts = synthetic.makeParticles(P)
+    solver = wb.BoltzmannSolver(grid)
+    solver.updateParticleList(parts)
+    solver.setCollisionArray(synthetic.makeCollision(grid, parts))
+    solver.setBackground(synthetic.makeBackground(grid))
+    eng = solver._getEngine()
+    solver._uploadBackground(eng)
+    vw = float(solver.background.velocityWall)
+    eng.assemble(vw, 1.0)
+    S0 = eng.S.clone()
+    eng.factor()
+    LU_sep = eng.A.clone()
+    eng.solve()
+    x_sep = eng.S.clone()
+    for _ in range(2):                      # second pass replays the cached graphs
+        eng.assemble(vw, 1.0)
+        eng.factor_solve()
+        assert eng.info() == 0
+        assert torch.equal(eng.A, LU_sep)
+        scale = float(torch.max(torch.abs(x_sep)))
+        assert float(torch.max(torch.abs(eng.S - x_sep))) <= 1e-11 * scale
+    b2 = S0.clone()
+    eng.solve(b2)                           # the factors are still a complete LU
+    assert float(torch.max(torch.abs(b2 - x_sep))) <= 1e-11 * float(torch.max(torch.abs(x_sep)))

@@ -34,6 +34,7 @@ SYMBOLS = {
     "wg_set_collision": (C.c_int, [_vp, _vp, C.c_int]),
     "wg_assemble": (C.c_int, [_vp, _dp, C.c_double, C.c_double, C.c_int, _dp, C.c_longlong, _dp, _vp]),
     "wg_factor": (C.c_int, [_vp, _dp, C.c_longlong, _vp]),
+    "wg_factor_solve": (C.c_int, [_vp, _dp, C.c_longlong, _dp, _vp]),
     "wg_solve": (C.c_int, [_vp, _dp, C.c_longlong, _dp, _vp]),
     "wg_assemble_factor_solve_batched": (C.c_int, [C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_double),
                                                    C.POINTER(C.c_double), C.POINTER(_vp), C.POINTER(C.c_longlong),

@@ -309,6 +309,13 @@ int wg_factor(wg_solver* s, double* A_dev, long long lda, void* stream) {
   return wg::lu_factor(s->plan, A_dev, lda, s->ipiv, s->info, (cudaStream_t)stream);
 }
 
+int wg_factor_solve(wg_solver* s, double* A_dev, long long lda, double* b_dev, void* stream) {
+  WG_REQUIRE(s && A_dev && b_dev, "wg_factor_solve: NULL argument");
+  int rc = wg::lu_factor(s->plan, A_dev, lda, s->ipiv, s->info, (cudaStream_t)stream, b_dev);
+  if (rc) return rc;
+  return wg::lu_solve(s->plan, A_dev, lda, b_dev, (cudaStream_t)stream, true);
+}
+
 int wg_solve(wg_solver* s, const double* LU_dev, long long lda, double* b_dev, void* stream) {
   WG_REQUIRE(s && LU_dev && b_dev, "wg_solve: NULL argument");
   return wg::lu_solve(s->plan, LU_dev, lda, b_dev, (cudaStream_t)stream);

@@ -14,8 +14,9 @@ void gemm_set_variant(int v);
 struct LuPlan;
 int lu_plan_create(int n, LuPlan** out);
 void lu_plan_destroy(LuPlan* p);
-int lu_factor(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStream_t st);
-int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st);
+// rhs != nullptr: the forward solve of that right-hand side is fused into the factorisation
+int lu_factor(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStream_t st, double* rhs = nullptr);
+int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st, bool backwardOnly = false);
 void lu_set_tuning(int nb, int use_graph);
 void lu_set_debug(long long* dev_buf, int c0);
 void lu_set_lookahead(int on);

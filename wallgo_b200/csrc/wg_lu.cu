@@ -750,6 +750,25 @@ __global__ void lu_rhs_perm_kernel(double* __restrict__ b, const int* __restrict
   }
 }
 
+// the interchanges of ONE panel applied to the right-hand side (forward solve fused into the factorisation)
+__global__ void lu_rhs_perm_panel_kernel(double* __restrict__ b, const int* __restrict__ srcTop,
+                                         const int* __restrict__ bDst, const int* __restrict__ bSrc,
+                                         const int* __restrict__ nbotPtr, int k, int nb) {
+  const int tid = threadIdx.x;
+  const int nbt = *nbotPtr;
+  double v = 0.0;
+  int dst = -1;
+  if (tid < nb) {
+    v = b[srcTop[k + tid]];
+    dst = k + tid;
+  } else if (tid - nb < nbt) {
+    v = b[bSrc[k + tid - nb]];
+    dst = bDst[k + tid - nb];
+  }
+  __syncthreads();
+  if (dst >= 0) b[dst] = v;
+}
+
 // One step of the blocked triangular solve (BS = 128 rows per block).  Forward (unit lower) visits
 // blocks top-down, backward (upper) bottom-up.  In the step for block [kb, kb+bs):
 //   CTA 0     : applies the previous block's solution x_prev to its own rows, then solves the
@@ -880,6 +899,9 @@ struct LuPlan {
   cudaStream_t farStream = nullptr;    // bulk work of the right-most columns while the trailing matrix is large
   double *Sf = nullptr, *Sf2 = nullptr;
   cudaEvent_t evFar = nullptr, evNear = nullptr;
+  cudaStream_t rhsStream = nullptr;    // fused forward solve of the right-hand side (lowest priority)
+  cudaEvent_t evRhsIn = nullptr, evRhsOut = nullptr;
+  bool rhsPending = false;
   int prioChain = 0, prioBulkHi = 0;
   cudaEvent_t evPhase = nullptr;
   cudaEvent_t evFork = nullptr, evJoin = nullptr;
@@ -898,12 +920,17 @@ struct LuPlan {
   long long glda = 0;
   int* gipiv = nullptr;
   int* ginfo = nullptr;
+  double* grhs = nullptr;
+  // forward-solve state while the factorisation is being enqueued with a fused right-hand side
+  double* rhs = nullptr;
+  int rhsPrev = -1, rhsPrevBs = 0;
   // CUDA-graph cache of the triangular solves for one (factors, right-hand side) pair
   cudaGraphExec_t solveExec = nullptr;
   long long solveLaunches = 0;
   const double* sLU = nullptr;
   long long slda = 0;
   double* sb = nullptr;
+  int sBackOnly = 0;
 };
 
 template <int W, int R>
@@ -962,6 +989,9 @@ int lu_plan_create(int n, LuPlan** out) {
   WG_CUDA(cudaStreamCreateWithPriority(&p->farStream, cudaStreamNonBlocking, prLow));
   WG_CUDA(cudaEventCreateWithFlags(&p->evFar, cudaEventDisableTiming));
   WG_CUDA(cudaEventCreateWithFlags(&p->evNear, cudaEventDisableTiming));
+  WG_CUDA(cudaStreamCreateWithPriority(&p->rhsStream, cudaStreamNonBlocking, prLow));
+  WG_CUDA(cudaEventCreateWithFlags(&p->evRhsIn, cudaEventDisableTiming));
+  WG_CUDA(cudaEventCreateWithFlags(&p->evRhsOut, cudaEventDisableTiming));
   if (n >= 8192) {
     WG_CUDA(cudaMalloc(&p->Sf, sbytes));
     WG_CUDA(cudaMalloc(&p->Sf2, sbytes));
@@ -981,6 +1011,9 @@ void lu_plan_destroy(LuPlan* p) {
   if (p->farStream) cudaStreamDestroy(p->farStream);
   if (p->evFar) cudaEventDestroy(p->evFar);
   if (p->evNear) cudaEventDestroy(p->evNear);
+  if (p->rhsStream) cudaStreamDestroy(p->rhsStream);
+  if (p->evRhsIn) cudaEventDestroy(p->evRhsIn);
+  if (p->evRhsOut) cudaEventDestroy(p->evRhsOut);
   cudaFree(p->Sf);
   cudaFree(p->Sf2);
   if (p->evPhase) cudaEventDestroy(p->evPhase);
@@ -1149,6 +1182,59 @@ static int apply_perm(LuPlan* p, double* A, long long lda, ColMap cm, int k, int
   return WG_OK;
 }
 
+static int trisolve_configure() {
+  static bool configured = false;
+  if (!configured) {
+    const size_t smem = (size_t)(TS_BS * TS_LD + 2 * TS_BS) * sizeof(double);
+    WG_CUDA(cudaFuncSetAttribute(lu_trisolve_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WG_CUDA(cudaFuncSetAttribute(lu_trisolve_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  return WG_OK;
+}
+
+// Forward solve fused into the factorisation: once panel [k, k+nb) is factored and its interchanges have
+// reached the finished columns left of it, the right-hand side takes the same interchanges and the forward
+// substitution advances through the panel's 128-row blocks (the same step kernel as the stand-alone solve).
+// It runs on its own lowest-priority stream, after the stream `after` has interchanged the finished columns
+// for this panel; rhs_wait() orders the NEXT interchange of those columns behind it.  Nothing else depends on
+// it, so it never sits on the critical path.
+static int rhs_wait(LuPlan* p, cudaStream_t st) {
+  if (p->rhs && p->rhsPending) {
+    WG_CUDA(cudaStreamWaitEvent(st, p->evRhsOut, 0));
+    p->rhsPending = false;
+  }
+  return WG_OK;
+}
+
+static int rhs_panel(LuPlan* p, const double* LU, long long lda, int k, int nb, int pnl, cudaStream_t after) {
+  if (!p->rhs) return WG_OK;
+  const int n = p->n;
+  const int savedPrio = g_wg_launch_prio;
+  g_wg_launch_prio = INT_MIN;
+  cudaStream_t st = p->rhsStream;
+  WG_CUDA(cudaEventRecord(p->evRhsIn, after));
+  WG_CUDA(cudaStreamWaitEvent(st, p->evRhsIn, 0));
+  WG_CUDA(launch_prio(lu_rhs_perm_panel_kernel, dim3(1), dim3(1024), 0, st, p->rhs, p->permSrcTop, p->permBDst,
+                      p->permBSrc, p->permNBot + pnl, k, nb));
+  WG_LAUNCH_CHECK();
+  const size_t smem = (size_t)(TS_BS * TS_LD + 2 * TS_BS) * sizeof(double);
+  for (int kb = k; kb < k + nb; kb += TS_BS) {
+    const int bs = TS_BS < k + nb - kb ? TS_BS : k + nb - kb;
+    const int rest = n - kb - bs;
+    const int grid = 1 + ((p->rhsPrev >= 0 && rest > 0) ? wg_cdiv(rest, 8) : 0);
+    WG_CUDA(launch_prio(lu_trisolve_step_kernel<false>, dim3(grid), dim3(256), smem, st, LU, lda, p->rhs, n, p->rhsPrev,
+                        p->rhsPrevBs, kb, bs));
+    WG_LAUNCH_CHECK();
+    p->rhsPrev = kb;
+    p->rhsPrevBs = bs;
+  }
+  WG_CUDA(cudaEventRecord(p->evRhsOut, st));
+  p->rhsPending = true;
+  g_wg_launch_prio = savedPrio;
+  return WG_OK;
+}
+
 // Right-looking blocked LU with a look-ahead critical chain.  After panel k is factored, everything the
 // NEXT panel needs -- the row interchanges, the triangular solve and the update of its own columns, then
 // its factorisation -- runs on the highest-priority "chain" stream; the bulk of step k (interchanges of all
@@ -1169,6 +1255,13 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
   struct PrioGuard {
     ~PrioGuard() { g_wg_launch_prio = INT_MIN; }
   } prioGuard;
+  p->rhsPrev = -1;
+  p->rhsPrevBs = 0;
+  p->rhsPending = false;
+  if (p->rhs) {
+    int rcc = trisolve_configure();
+    if (rcc) return rcc;
+  }
   cudaStream_t bs = st;    // stream of the bulk work
   int bulkPrio = INT_MIN;
   // While the trailing matrix is large the bulk columns are split at a fixed column X: the near part
@@ -1200,7 +1293,11 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
     double* U12 = A + (long long)k * lda + k + nb;
     const double* L11 = A + (long long)k * lda + k;
     if (!(look && rest > nb2)) {
+      rc = rhs_wait(p, bs);
+      if (rc) return rc;
       rc = apply_perm(p, A, lda, ColMap{n - nb, k, 0, nb}, k, nb, pnl, p->S, p->S2, c.vecA, bs);
+      if (rc) return rc;
+      rc = rhs_panel(p, A, lda, k, nb, pnl, bs);
       if (rc) return rc;
       if (rest <= 0) break;
       rc = trsm_rec(L11, lda, U12, lda, nb, rest, bs);
@@ -1252,9 +1349,17 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
     g_wg_launch_prio = bulkPrio;
     // ---- bulk: right of the chain's block up to Xe; the finished columns left of the panel too unless the
     //      far stream is on (they are read by the far GEMM of the previous step, so it interchanges them itself)
+    if (!farOn) {
+      rc = rhs_wait(p, bs);
+      if (rc) return rc;
+    }
     rc = apply_perm(p, A, lda, farOn ? ColMap{Xe - R0, Xe - R0, R0, 0} : ColMap{k + (Xe - R0), k, 0, nb + nb2}, k, nb,
                     pnl, p->S, p->S2, c.vecA, bs);
     if (rc) return rc;
+    if (!farOn) {
+      rc = rhs_panel(p, A, lda, k, nb, pnl, bs);
+      if (rc) return rc;
+    }
     trace_mark(p, bs, pnl, 1);
     rc = trsm_rec(L11, lda, U12 + nb2, lda, nb, Xe - R0, bs);
     if (rc) return rc;
@@ -1268,7 +1373,11 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
       WG_CUDA(cudaEventRecord(p->evNear, bs));
       g_wg_launch_prio = INT_MIN;
       const int off = X - (k + nb);
+      rc = rhs_wait(p, fs);
+      if (rc) return rc;
       rc = apply_perm(p, A, lda, ColMap{k + (n - X), k, 0, X - k}, k, nb, pnl, p->Sf, p->Sf2, c.vecA, fs);
+      if (rc) return rc;
+      rc = rhs_panel(p, A, lda, k, nb, pnl, fs);
       if (rc) return rc;
       rc = trsm_rec(L11, lda, U12 + off, lda, nb, n - X, fs);
       if (rc) return rc;
@@ -1285,6 +1394,10 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
     WG_CUDA(cudaEventRecord(p->evFar, fs));
     WG_CUDA(cudaStreamWaitEvent(bs, p->evFar, 0));
   }
+  {
+    int rcw = rhs_wait(p, bs);
+    if (rcw) return rcw;
+  }
   if (bs != st) {
     WG_CUDA(cudaEventRecord(p->evPhase, bs));
     WG_CUDA(cudaStreamWaitEvent(st, p->evPhase, 0));
@@ -1292,10 +1405,11 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
   return WG_OK;
 }
 
-int lu_factor(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStream_t st) {
+int lu_factor(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStream_t st, double* rhs) {
   WG_REQUIRE(p && A && ipiv && info && lda >= p->n, "lu_factor: bad arguments");
+  p->rhs = rhs;   // non-null: the forward solve L y = P rhs rides along (finish with lu_solve(..., backwardOnly))
   if (!g_use_graph) return factor_enqueue(p, A, lda, ipiv, info, st);
-  if (!p->exec || p->gA != A || p->glda != lda || p->gipiv != ipiv || p->ginfo != info) {
+  if (!p->exec || p->gA != A || p->glda != lda || p->gipiv != ipiv || p->ginfo != info || p->grhs != rhs) {
     if (p->exec) {
       cudaGraphExecDestroy(p->exec);
       p->exec = nullptr;
@@ -1321,18 +1435,19 @@ int lu_factor(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStr
     p->glda = lda;
     p->gipiv = ipiv;
     p->ginfo = info;
+    p->grhs = rhs;
   }
   WG_CUDA(cudaGraphLaunch(p->exec, st));
   g_wg_launches += p->graphLaunches;
   return WG_OK;
 }
 
-static int solve_enqueue(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st);
+static int solve_enqueue(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st, bool backwardOnly);
 
-int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st) {
+int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st, bool backwardOnly) {
   WG_REQUIRE(p && LU && b && lda >= p->n, "lu_solve: bad arguments");
-  if (!g_use_graph) return solve_enqueue(p, LU, lda, b, st);
-  if (!p->solveExec || p->sLU != LU || p->slda != lda || p->sb != b) {
+  if (!g_use_graph) return solve_enqueue(p, LU, lda, b, st, backwardOnly);
+  if (!p->solveExec || p->sLU != LU || p->slda != lda || p->sb != b || p->sBackOnly != (int)backwardOnly) {
     if (p->solveExec) {
       cudaGraphExecDestroy(p->solveExec);
       p->solveExec = nullptr;
@@ -1341,7 +1456,7 @@ int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t
     WG_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
     WG_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
     const long long before = g_wg_launches;
-    int rc = solve_enqueue(p, LU, lda, b, cs);
+    int rc = solve_enqueue(p, LU, lda, b, cs, backwardOnly);
     p->solveLaunches = g_wg_launches - before;
     g_wg_launches = before;
     cudaGraph_t graph = nullptr;
@@ -1357,26 +1472,25 @@ int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t
     p->sLU = LU;
     p->slda = lda;
     p->sb = b;
+    p->sBackOnly = (int)backwardOnly;
   }
   WG_CUDA(cudaGraphLaunch(p->solveExec, st));
   g_wg_launches += p->solveLaunches;
   return WG_OK;
 }
 
-static int solve_enqueue(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st) {
+static int solve_enqueue(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st, bool backwardOnly) {
   const int n = p->n, NB = p->nb;
-  lu_rhs_perm_kernel<<<1, 1024, 0, st>>>(b, p->permSrcTop, p->permBDst, p->permBSrc, p->permNBot, n, NB);
-  WG_LAUNCH_CHECK();
+  int rcc = trisolve_configure();
+  if (rcc) return rcc;
   const size_t smem = (size_t)(TS_BS * TS_LD + 2 * TS_BS) * sizeof(double);
-  static bool configured = false;
-  if (!configured) {
-    WG_CUDA(cudaFuncSetAttribute(lu_trisolve_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    WG_CUDA(cudaFuncSetAttribute(lu_trisolve_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
-  }
   const int nblk = wg_cdiv(n, TS_BS);
   int kprev = -1, bsprev = 0;
-  for (int q = 0; q < nblk; ++q) {
+  if (!backwardOnly) {
+    lu_rhs_perm_kernel<<<1, 1024, 0, st>>>(b, p->permSrcTop, p->permBDst, p->permBSrc, p->permNBot, n, NB);
+    WG_LAUNCH_CHECK();
+  }
+  for (int q = 0; q < nblk && !backwardOnly; ++q) {
     const int kb = q * TS_BS;
     const int bs = TS_BS < n - kb ? TS_BS : n - kb;
     const int rest = n - kb - bs;

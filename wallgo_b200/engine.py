@@ -165,6 +165,13 @@ class BoltzmannEngine:
         A = self._ensure_A()
         check(self.lib.wg_factor(self.h, A.data_ptr(), A.stride(0), self._stream()), "wg_factor")
 
+    def factor_solve(self, b=None):
+        """np.linalg.solve in one call: LU with the forward solve of b riding along, then the backward solve."""
+        b = self.S if b is None else b
+        A = self._ensure_A()
+        check(self.lib.wg_factor_solve(self.h, A.data_ptr(), A.stride(0), b.data_ptr(), self._stream()), "wg_factor_solve")
+        return b
+
     def solve(self, b=None):
         """Triangular solves with the current factors; b (device, n) is overwritten by the solution."""
         b = self.S if b is None else b
