@@ -10,6 +10,8 @@ s = wb.BoltzmannSolver(grid); s.updateParticleList(parts)
 s.setBackground(synthetic.makeBackground(grid)); s.setCollisionArray(synthetic.makeCollision(grid, parts))
 eng = s._getEngine(); s._uploadBackground(eng)
 vw = float(s.background.velocityWall)
+from wallgo_b200 import _lib
+if os.environ.get("WG_ASM_WIDE"): _lib.load().wg_debug_asm_wide(int(os.environ["WG_ASM_WIDE"]))
 for _ in range(3): eng.assemble(vw, 1.0)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

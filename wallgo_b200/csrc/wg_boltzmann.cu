@@ -135,8 +135,18 @@ __global__ void wg_rows_kernel(BzDims d, const double* __restrict__ prof, const 
 // rows of the n x n operator.  The R-row tiles of K1 = Trz(x)Trp, K2 = Drz(x)Trp and of the collision
 // tensor are staged in shared memory with TMA bulk copies; the K1 tile (scaled by the Liouville row
 // weight) then lives in registers and is re-used for all (M-1) z-blocks of the row.
-template <int R>
-__global__ void __launch_bounds__(512) wg_assemble_kernel(BzDims d, const double* __restrict__ K1,
+#ifndef WG_ASM_MINB
+#define WG_ASM_MINB 2
+#endif
+// 32-byte global store (SASS STG.E.ENL2.256): half as many store instructions as double2 for the same bytes
+__device__ __forceinline__ void st_global_v4(double* p, double a, double b, double c, double e) {
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(e) : "memory");
+}
+
+// V = doubles per thread and store: 2 (16-byte stores) or 4 (32-byte stores; needs lda % 4 == 0 and a
+// 32-byte aligned operator)
+template <int R, int V>
+__global__ void __launch_bounds__(512, WG_ASM_MINB) wg_assemble_kernel(BzDims d, const double* __restrict__ K1,
                                                           const double* __restrict__ K2,
                                                           const double* __restrict__ Coll,
                                                           const double* __restrict__ Tchi,
@@ -186,38 +196,42 @@ __global__ void __launch_bounds__(512) wg_assemble_kernel(BzDims d, const double
   __syncthreads();
   mbar_wait(&bar, 0);
 
-  for (int cp = tid; cp < q / 2; cp += blockDim.x) {
-    double2 wk[R];
+  for (int cp = tid; cp < q / V; cp += blockDim.x) {
+    double wk[R][V];
 #pragma unroll
-    for (int rr = 0; rr < R; ++rr) {
-      const double2 kv = *reinterpret_cast<const double2*>(K1s + rr * q + 2 * cp);
-      wk[rr] = make_double2(rw1[rr] * kv.x, rw1[rr] * kv.y);
-    }
+    for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+      for (int v = 0; v < V; ++v) wk[rr][v] = rw1[rr] * K1s[rr * q + V * cp + v];
     for (int b = 0; b < P; ++b) {
       const bool same = (b == a);
-      double* out = A + r0 * lda + (long long)b * M1 * q + 2 * cp;
+      double* out = A + r0 * lda + (long long)b * M1 * q + V * cp;
       for (int i = 0; i < M1; ++i, out += q) {
         const double dv = same ? dch[i] : 0.0;
         const double tx = tch[i];
         if (tx == 0.0) {
 #pragma unroll
-          for (int rr = 0; rr < R; ++rr)
-            *reinterpret_cast<double2*>(out + rr * lda) = make_double2(wk[rr].x * dv, wk[rr].y * dv);
+          for (int rr = 0; rr < R; ++rr) {
+            if constexpr (V == 4)
+              st_global_v4(out + rr * lda, wk[rr][0] * dv, wk[rr][1] * dv, wk[rr][2] * dv, wk[rr][3] * dv);
+            else
+              *reinterpret_cast<double2*>(out + rr * lda) = make_double2(wk[rr][0] * dv, wk[rr][1] * dv);
+          }
         } else {
           const double ctx = ct2 * tx;
 #pragma unroll
           for (int rr = 0; rr < R; ++rr) {
-            const double2 cv = *reinterpret_cast<const double2*>(Cs + ((size_t)rr * P + b) * q + 2 * cp);
-            double vx = wk[rr].x * dv, vy = wk[rr].y * dv;
-            if (same) {
-              const double2 k2 = *reinterpret_cast<const double2*>(K2s + rr * q + 2 * cp);
-              const double c2 = rw2[rr] * tx;
-              vx -= c2 * k2.x;
-              vy -= c2 * k2.y;
+            double val[V];
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              double x = wk[rr][v] * dv;
+              if (same) x -= (rw2[rr] * tx) * K2s[rr * q + V * cp + v];
+              x += ctx * Cs[((size_t)rr * P + b) * q + V * cp + v];
+              val[v] = x;
             }
-            vx += ctx * cv.x;
-            vy += ctx * cv.y;
-            *reinterpret_cast<double2*>(out + rr * lda) = make_double2(vx, vy);
+            if constexpr (V == 4)
+              st_global_v4(out + rr * lda, val[0], val[1], val[2], val[3]);
+            else
+              *reinterpret_cast<double2*>(out + rr * lda) = make_double2(val[0], val[1]);
           }
         }
       }
@@ -437,6 +451,9 @@ int bz_build_kron(const BzDims& d, const double* Trz, const double* Drz, const d
   return WG_OK;
 }
 
+static int g_asm_wide = 1;   // 32-byte stores in the assembly kernel when alignment allows
+void bz_set_asm_wide(int on) { g_asm_wide = on; }
+
 int bz_assemble(const BzDims& d, const BzStatic& s, const double* prof, double vw, double collMult, int parts,
                 double* derivs, double* w1, double* w2, double* cT2, double* A, long long lda, double* S,
                 cudaStream_t st) {
@@ -453,14 +470,24 @@ int bz_assemble(const BzDims& d, const BzStatic& s, const double* prof, double v
   WG_REQUIRE(smem <= 200 * 1024, "assemble: basis tile does not fit in shared memory");
   static size_t configured = 0;
   if (smem > configured) {
-    WG_CUDA(cudaFuncSetAttribute(wg_assemble_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WG_CUDA(cudaFuncSetAttribute(wg_assemble_kernel<R, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WG_CUDA(cudaFuncSetAttribute(wg_assemble_kernel<R, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WG_CUDA(cudaFuncSetAttribute(wg_assemble_kernel<R, 2>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared));
+    WG_CUDA(cudaFuncSetAttribute(wg_assemble_kernel<R, 4>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared));
     configured = smem;
   }
-  int threads = ((d.q / 2 + 31) / 32) * 32;
+  dim3 grid(d.q / R, d.P * d.M1);
+  const bool wide = g_asm_wide && d.q % 4 == 0 && lda % 4 == 0 && reinterpret_cast<uintptr_t>(A) % 32 == 0;
+  const int per = wide ? 4 : 2;
+  int threads = ((d.q / per + 31) / 32) * 32;
   if (threads > 512) threads = 512;
   if (threads < 64) threads = 64;
-  dim3 grid(d.q / R, d.P * d.M1);
-  wg_assemble_kernel<R><<<grid, threads, smem, st>>>(d, s.K1, s.K2, s.Coll, s.Tchi, s.Dchi, w1, w2, cT2, A, lda);
+  if (wide)
+    wg_assemble_kernel<R, 4><<<grid, threads, smem, st>>>(d, s.K1, s.K2, s.Coll, s.Tchi, s.Dchi, w1, w2, cT2, A, lda);
+  else
+    wg_assemble_kernel<R, 2><<<grid, threads, smem, st>>>(d, s.K1, s.K2, s.Coll, s.Tchi, s.Dchi, w1, w2, cT2, A, lda);
   WG_LAUNCH_CHECK();
   return WG_OK;
 }

@@ -26,6 +26,7 @@ int bz_build_basis(const BzDims& d, const double* rz, double* Tchi, double* Dchi
                    double* Trz, double* Drz, double* Trp, cudaStream_t st);
 int bz_build_kron(const BzDims& d, const double* Trz, const double* Drz, const double* Trp, double* K1,
                   double* K2, cudaStream_t st);
+void bz_set_asm_wide(int on);
 int bz_assemble(const BzDims& d, const BzStatic& s, const double* prof, double vw, double collMult, int parts,
                 double* derivs, double* w1, double* w2, double* cT2, double* A, long long lda, double* S,
                 cudaStream_t st);

@@ -99,6 +99,11 @@ int wg_set_bulk_split(int percent) {
   wg::lu_set_split(percent);
   return WG_OK;
 }
+/* developer knob (not part of the public header): 32-byte stores in the assembly kernel on/off */
+int wg_debug_asm_wide(int on) {
+  wg::bz_set_asm_wide(on);
+  return WG_OK;
+}
 int wg_set_lookahead(int on) {
   wg::lu_set_lookahead(on);
   return WG_OK;
