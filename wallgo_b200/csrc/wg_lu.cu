@@ -9,14 +9,20 @@
 //     the DMMA GEMM (wg_gemm.cu);
 //   * leaves (16 or 8 columns) are factored by ONE thread-block cluster that keeps the whole
 //     tall-skinny block register-resident (one or more rows per thread), finds pivots with
-//     warp redux + a DSMEM exchange and one hardware cluster barrier per column, and never
-//     moves rows while factoring (implicit pivoting); at the end it writes rows to their
-//     pivoted positions and moves the rest of those rows inside the panel;
-//   * the permutation of a whole panel is composed once on the device and applied to the
-//     columns left and right of the panel by two fully parallel kernels (gather / write);
+//     warp redux + one st.async push of every CTA's candidate row into every CTA's shared memory
+//     (completion through a transaction mbarrier), and never moves rows while factoring (implicit
+//     pivoting); at the end it writes rows to their pivoted positions and moves the rest of those
+//     rows inside the panel;
+//   * the permutation of a whole panel is composed once on the device and applied to other
+//     columns by two fully parallel kernels (gather / write) that take a two-segment column map;
 //   * U12 = L11^-1 A12 by recursive TRSM (GEMM + register-resident 32-wide base);
 //   * trailing update A22 -= L21 U12 on the FP64 tensor pipe.
-// No host synchronisation anywhere: pivots, permutations and `info` stay on the device.
+// Schedule (factor_enqueue): a highest-priority CHAIN stream does everything the next panel needs
+// (its columns' interchanges, TRSM, update, then its factorisation) while one or two BULK streams
+// update all other columns; optionally a fourth stream carries the forward solve of a right-hand
+// side along.  The whole thing is captured once per buffer set and replayed as a CUDA graph whose
+// kernel nodes keep their priorities.  No host synchronisation anywhere: pivots, permutations and
+// `info` stay on the device.
 #include <limits.h>
 #include <stdarg.h>
 
