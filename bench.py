@@ -478,7 +478,7 @@ def run_b200(a):
                                         "(assembly, solves and moments count as overhead)"},
             "roofline_assembly": {"kernel": "wg_assemble_kernel", "bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak,
                                   "unit": "GB/s", "frac": asm_gbs / hbm_peak,
-                                  "traffic": 1.921e9 if (P, M, N) == (1, 40, 21) else None, "peak_source": hbm_src,
+                                  "traffic": 1.935e9 if (P, M, N) == (1, 40, 21) else None, "peak_source": hbm_src,
                                   "algorithmic": "8n^2+8n bytes written per solve / mean CUDA-event time of wg_assemble"},
             "e2e": {"value": e2e, "unit": "solves/s", "h2d_bytes_per_step": int(nprof * 8),
                     "d2h_bytes_per_step": int((eng.nspec + eng.nout) * 8 + 4)},
