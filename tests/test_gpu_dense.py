@@ -355,3 +355,62 @@ def test_fused_forward_solve_equals_separate_solves(cuda_device, P, M, N):
     b2 = S0.clone()
     eng.solve(b2)                           # the factors are still a complete LU
     assert float(torch.max(torch.abs(b2 - x_sep))) <= 1e-11 * float(torch.max(torch.abs(x_sep)))
+
+
+@pytest.mark.parametrize("kind", ["inf_mid_leaf", "neg_inf_late", "nan_entry", "nan_row", "nan_col", "all_nan", "inf_small"])
+def test_lu_nonfinite_input_does_not_fault(env, kind):
+    """Garbage in, garbage out -- but never an out-of-range access.  An infinite entry turns into NaNs
+    (inf - inf) inside a leaf panel; the pivot search must keep treating those rows as candidates (its integer
+    key of |a| has to stay non-negative for NaN), otherwise an inactive row "wins" and carries an invalid
+    position.  Regression test for exactly that fault."""
+    torch, lib, _ = env
+    n = 64 if kind == "inf_small" else 300
+    rng = np.random.default_rng(1)
+    A = rng.standard_normal((n, n))
+    if kind == "inf_mid_leaf":
+        A[150, 100] = np.inf
+    elif kind == "neg_inf_late":
+        A[280, 270] = -np.inf
+    elif kind == "nan_entry":
+        A[150, 100] = np.nan
+    elif kind == "nan_row":
+        A[150, :] = np.nan
+    elif kind == "nan_col":
+        A[:, 100] = np.nan
+    elif kind == "all_nan":
+        A[:] = np.nan
+    elif kind == "inf_small":
+        A[60, 20] = np.inf
+    LU, ipiv, info, x = _lu(env, A, rng.standard_normal(n))
+    assert ipiv.min() >= 0 and ipiv.max() < n
+    assert np.all(ipiv >= np.arange(n))                  # LAPACK-style pivots: row i swaps with a row at or below it
+    # the context is still healthy: a clean factorisation right after
+    B = rng.standard_normal((n, n))
+    LU2, ipiv2, info2, _ = _lu(env, B)
+    assert info2 == 0
+    _check_factors(B, LU2, ipiv2)
+
+
+def test_unphysical_background_does_not_fault(cuda_device):
+    """A superluminal wall velocity makes the Lorentz factors NaN: the solve must return (NaN) results or raise
+    LinAlgError like the reference would, not fault the device."""
+    import torch
+    import wallgo_b200 as wb
+    from wallgo_b200 import synthetic
+
+    grid = synthetic.makeGrid(12, 7)
+    parts = synthetic.makeParticles(2)
+    solver = wb.BoltzmannSolver(grid)
+    solver.updateParticleList(parts)
+    solver.setCollisionArray(synthetic.makeCollision(grid, parts))
+    with np.errstate(all="ignore"):
+        solver.setBackground(synthetic.makeBackground(grid, velocityMid=-1.02))
+        try:
+            res = solver.getDeltas()
+            assert not np.all(np.isfinite(res.deltaF))
+        except (np.linalg.LinAlgError, ValueError, FloatingPointError):
+            pass
+    torch.cuda.synchronize()
+    solver.setBackground(synthetic.makeBackground(grid, velocityMid=-0.4))
+    good = solver.getDeltas()
+    assert np.all(np.isfinite(good.deltaF))

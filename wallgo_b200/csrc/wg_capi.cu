@@ -1,5 +1,6 @@
 // extern "C" boundary of libwallgo_b200.so (see include/wallgo_b200.h).
 #include <limits.h>
+#include <stdlib.h>
 #include <math.h>
 #include <stdarg.h>
 #include <string.h>
@@ -14,6 +15,7 @@
 static thread_local char g_err[512] = "";
 long long g_wg_launches = 0;
 thread_local int g_wg_launch_prio = INT_MIN;
+int g_wg_sync_every_launch = (getenv("WG_SYNC_EVERY_LAUNCH") != nullptr);
 void wg_set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -104,6 +106,8 @@ int wg_debug_asm_wide(int on) {
   wg::bz_set_asm_wide(on);
   return WG_OK;
 }
+/* developer probe (not part of the public header; built with -DWG_LEAF_CHECKS): first bounds violation in a leaf */
+int wg_debug_leaf_fail(int* out8) { return wg::lu_leaf_fail_read(out8); }
 int wg_set_lookahead(int on) {
   wg::lu_set_lookahead(on);
   return WG_OK;

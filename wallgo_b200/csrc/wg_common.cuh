@@ -30,10 +30,12 @@ extern long long g_wg_launches;  // kernels launched by this library (bench acco
     }                                                            \
   } while (0)
 
-#define WG_LAUNCH_CHECK()               \
-  do {                                  \
-    ++g_wg_launches;                    \
-    WG_CUDA(cudaPeekAtLastError());     \
+extern int g_wg_sync_every_launch;  // developer aid (env WG_SYNC_EVERY_LAUNCH=1): attribute faults to the kernel
+#define WG_LAUNCH_CHECK()                                     \
+  do {                                                        \
+    ++g_wg_launches;                                          \
+    WG_CUDA(cudaPeekAtLastError());                           \
+    if (g_wg_sync_every_launch) WG_CUDA(cudaDeviceSynchronize()); \
   } while (0)
 
 static inline int wg_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -76,6 +76,13 @@ struct PanelArgs {
   long long* dbg;  // optional phase timestamps (developer probe), may be nullptr
 };
 
+// bit pattern of |x| (non-negative as a signed integer for every x, NaN included)
+__device__ __forceinline__ long long abs_bits(double x) {
+  long long r;
+  asm("and.b64 %0, %1, 0x7fffffffffffffff;\n" : "=l"(r) : "l"(__double_as_longlong(x)));
+  return r;
+}
+
 // Lane holding the maximum of (key descending, pos ascending) over the lanes with valid != 0.
 // Fast path: one REDUX on the high word of the key (sign, exponent, top mantissa bits) is almost
 // always decisive; exact ties fall back to the full 64-bit key and then to the smallest position
@@ -128,6 +135,18 @@ struct LeafSmem {
 // thread): the window rotates fully -- the finished entry re-enters at the tail, candidate rows are pushed
 // with their finished tail zeroed so the update leaves it untouched -- and after W steps the registers hold
 // the finished row in column order; the tile only transposes 16 columns at a time.
+#ifdef WG_LEAF_CHECKS
+__device__ int g_leaf_fail[8 + 48];
+#endif
+int lu_leaf_fail_read(int* out) {
+#ifdef WG_LEAF_CHECKS
+  return cudaMemcpyFromSymbol(out, g_leaf_fail, sizeof(int) * 56) == cudaSuccess ? 0 : -2;
+#else
+  for (int i = 0; i < 56; ++i) out[i] = 0;
+  return 0;
+#endif
+}
+
 template <int W, int R>
 __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p) {
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -224,7 +243,11 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       const bool act = pos[k] >= dj;
-      const long long key = act ? __double_as_longlong(fabs(a[k][0])) : -1LL;
+      // |a| as an integer key.  The sign bit is cleared with an opaque integer AND: fabs() -- and equally a C++
+      // `bits & 0x7fff...`, which the compiler rewrites into fabs -- is a DADD on this machine and returns the
+      // canonical NaN 0xFFF8... for a NaN operand; as a signed integer that loses against the -1 of an inactive
+      // row and hands the column an out-of-range "pivot position" (an infinite entry is enough: inf - inf).
+      const long long key = act ? abs_bits(a[k][0]) : -1LL;
       const int pp = act ? pos[k] : INT_MAX;
       if (key > bk || (key == bk && pp < bp)) {
         bk = key;
@@ -282,9 +305,26 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
       urow = sm.cluSlot[par][argmax_lane(k3, p3, lane < (int)CL)];
     }
     const long long mkey = reinterpret_cast<const long long*>(urow)[W];
-    const int mpos = (int)reinterpret_cast<const long long*>(urow)[W + 1];
+    // (a winner that is not an active row -- key < 0 -- cannot happen for any input now that the keys are
+    // non-negative; the guard keeps row positions in range whatever the candidates hold)
+    int mpos = (int)reinterpret_cast<const long long*>(urow)[W + 1];
+    if (mkey < 0) mpos = dj;
     const bool sing = (mkey <= 0);
     const double rinv = sing ? 0.0 : 1.0 / urow[0];
+#ifdef WG_LEAF_CHECKS
+    if ((mpos < dj || mpos >= p.n) && atomicCAS(&g_leaf_fail[0], 0, 1) == 0) {
+      g_leaf_fail[1] = c0; g_leaf_fail[2] = j; g_leaf_fail[3] = mpos; g_leaf_fail[4] = (int)(mkey >> 32);
+      g_leaf_fail[5] = (int)rank; g_leaf_fail[6] = tid; g_leaf_fail[7] = (int)CL;
+      for (int q2 = 0; q2 < PNW; ++q2) {
+        g_leaf_fail[8 + q2] = (int)(reinterpret_cast<const long long*>(sm.warpSlot[q2])[W] >> 32);
+        g_leaf_fail[24 + q2] = (int)reinterpret_cast<const long long*>(sm.warpSlot[q2])[W + 1];
+      }
+      g_leaf_fail[40] = (int)(reinterpret_cast<const long long*>(sm.cluSlot[par][0])[W] >> 32);
+      g_leaf_fail[41] = (int)reinterpret_cast<const long long*>(sm.cluSlot[par][0])[W + 1];
+      g_leaf_fail[42] = par; g_leaf_fail[43] = dj; g_leaf_fail[44] = pos[0]; g_leaf_fail[45] = (int)(bk >> 32); g_leaf_fail[46] = w; g_leaf_fail[47] = m;
+    }
+    if (mpos < dj || mpos >= p.n) mpos = dj;
+#endif
     if (dbgc) p.dbg[30] = clock64() + (rinv == 12345.678 ? 1 : 0);
     // the pivot row comes from below the top block: stage its rest-of-panel columns now
     if (ext > 0) {
@@ -299,6 +339,12 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
         int slot = 0;
         if (lane == L) {
           slot = W + atomicAdd(&sm.moveCount, 1);
+#ifdef WG_LEAF_CHECKS
+          if (slot >= SM::MAXMOVE && atomicCAS(&g_leaf_fail[0], 0, 2) == 0) {
+            g_leaf_fail[1] = c0; g_leaf_fail[2] = j; g_leaf_fail[3] = slot; g_leaf_fail[4] = sp; g_leaf_fail[5] = mpos;
+          }
+          if (slot >= SM::MAXMOVE) slot = SM::MAXMOVE - 1;
+#endif
           sm.moveDst[slot] = dj;
         }
         slot = __shfl_sync(0xffffffffu, slot, L);
@@ -381,6 +427,12 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       const int wbase = k * (int)(CL * PT) + (int)rank * PT + warp * 32;
+#ifdef WG_LEAF_CHECKS
+      if (pos[k] >= p.n) {
+        if (atomicCAS(&g_leaf_fail[0], 0, 3) == 0) { g_leaf_fail[1] = c0; g_leaf_fail[3] = pos[k]; g_leaf_fail[4] = spos[k]; g_leaf_fail[6] = tid; }
+        pos[k] = spos[k];
+      }
+#endif
       const bool moved = pos[k] >= 0 && pos[k] != spos[k];
       if (p.vec) {
         const unsigned movedMask = __ballot_sync(0xffffffffu, moved);
@@ -431,6 +483,12 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
       if (s < W && (rank != 0 || s >= w || s >= m)) continue;
       const int d = sm.moveDst[s];
       if (d < 0) continue;
+#ifdef WG_LEAF_CHECKS
+      if (d >= p.n) {
+        if (lane == 0 && atomicCAS(&g_leaf_fail[0], 0, 4) == 0) { g_leaf_fail[1] = c0; g_leaf_fail[2] = s; g_leaf_fail[3] = d; g_leaf_fail[4] = cnt; }
+        continue;
+      }
+#endif
       double* drow = A + (long long)d * lda;
       for (int e = lane; e < ext; e += 32) {
         const int col = e < nLeft ? p.pc0 + e : c0 + w + (e - nLeft);
@@ -474,7 +532,7 @@ static int launch_leaf(const PanelArgs& pa, int CL, cudaStream_t st) {
     cfg.numAttrs = 2;
   }
   WG_CUDA(cudaLaunchKernelEx(&cfg, kern, pa));
-  ++g_wg_launches;
+  WG_LAUNCH_CHECK();
   return WG_OK;
 }
 
