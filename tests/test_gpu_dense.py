@@ -414,3 +414,80 @@ def test_unphysical_background_does_not_fault(cuda_device):
     solver.setBackground(synthetic.makeBackground(grid, velocityMid=-0.4))
     good = solver.getDeltas()
     assert np.all(np.isfinite(good.deltaF))
+
+
+def test_lu_singular_large(env):
+    """Zero matrix, a zero column deep inside a panel and inside the second panel: info is the 1-based index of
+    the first exact zero pivot (LAPACK dgetrf), the factorisation carries on, nothing faults."""
+    torch, lib, _ = env
+    n = 600
+    rng = np.random.default_rng(2)
+    _, ipiv, info, _ = _lu(env, np.zeros((n, n)))
+    assert info == 1 and np.array_equal(ipiv, np.arange(n))
+    for col in (100, 299, 300, 599):
+        A = rng.standard_normal((n, n))
+        A[:, col] = 0.0
+        _, ipiv, info, _ = _lu(env, A)
+        assert info == col + 1, (col, info)
+        assert ipiv.min() >= 0 and ipiv.max() < n
+
+
+def test_lu_unaligned_operator(env):
+    """An operator that starts 8 bytes off a 16-byte boundary with an odd leading dimension takes the scalar
+    (non-vectorised) load/store paths of every kernel: same pivots, factors equal to rounding."""
+    torch, lib, _lib = env
+    n, lda = 700, 703
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((n, n))
+    b = rng.standard_normal(n)
+    LU0, ipiv0, info0, x0 = _lu(env, A, b)
+    big = torch.zeros(n * lda + 1, dtype=torch.float64, device="cuda")
+    view = big[1:].view(n, lda)                      # data_ptr is 8 (mod 16)
+    assert view.data_ptr() % 16 == 8
+    view[:, :n] = torch.from_numpy(A).cuda()
+    ipiv = torch.zeros(n, dtype=torch.int32, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    bd = torch.from_numpy(b.copy()).cuda()
+    plan = C.c_void_p()
+    _lib.check(lib.wg_lu_create(n, 0, C.byref(plan)), "wg_lu_create")
+    try:
+        _lib.check(lib.wg_lu_factor(plan, view.data_ptr(), lda, ipiv.data_ptr(), info.data_ptr(), _stream(torch)), "factor")
+        _lib.check(lib.wg_lu_solve(plan, view.data_ptr(), lda, bd.data_ptr(), _stream(torch)), "solve")
+        torch.cuda.synchronize()
+    finally:
+        lib.wg_lu_destroy(plan)
+    assert int(info.item()) == 0
+    assert np.array_equal(ipiv.cpu().numpy(), ipiv0)
+    LU1 = view[:, :n].cpu().numpy()
+    assert np.max(np.abs(LU1 - LU0)) / np.max(np.abs(LU0)) < 1e-12
+    assert np.max(np.abs(bd.cpu().numpy() - x0)) / np.max(np.abs(x0)) < 1e-10
+
+
+def test_lu_plan_reused_with_alternating_buffers(env):
+    """One plan, two operators in turn: the cached CUDA graphs are rebuilt when the buffers change and replayed
+    when they come back; results match fresh plans bit for bit."""
+    torch, lib, _lib = env
+    n = 900
+    rng = np.random.default_rng(4)
+    mats = [rng.standard_normal((n, n)) for _ in range(2)]
+    rhs = [rng.standard_normal(n) for _ in range(2)]
+    ref = [_lu(env, m, r) for m, r in zip(mats, rhs)]
+    dev = [torch.empty((n, n), dtype=torch.float64, device="cuda") for _ in range(2)]
+    bd = [torch.empty(n, dtype=torch.float64, device="cuda") for _ in range(2)]
+    ipiv = torch.zeros(n, dtype=torch.int32, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    plan = C.c_void_p()
+    _lib.check(lib.wg_lu_create(n, 0, C.byref(plan)), "wg_lu_create")
+    try:
+        for turn in (0, 1, 0, 0, 1):
+            dev[turn].copy_(torch.from_numpy(mats[turn]))
+            bd[turn].copy_(torch.from_numpy(rhs[turn]))
+            _lib.check(lib.wg_lu_factor(plan, dev[turn].data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), _stream(torch)), "factor")
+            _lib.check(lib.wg_lu_solve(plan, dev[turn].data_ptr(), n, bd[turn].data_ptr(), _stream(torch)), "solve")
+            torch.cuda.synchronize()
+            assert int(info.item()) == 0
+            assert np.array_equal(dev[turn].cpu().numpy(), ref[turn][0])
+            assert np.array_equal(ipiv.cpu().numpy(), ref[turn][1])
+            assert np.array_equal(bd[turn].cpu().numpy(), ref[turn][3])
+    finally:
+        lib.wg_lu_destroy(plan)
