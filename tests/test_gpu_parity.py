@@ -288,3 +288,37 @@ def test_batched_c_abi_equals_single_calls(cuda_device):
     for eng, ref in zip(engines, single):
         assert eng.info() == 0
         assert torch.equal(eng.S, ref)
+
+
+def test_overflow_guard_matches_oracle(cuda_device, oracle):
+    """A cold plasma (T ~ 0.5 on a momentum grid scaled for T = 100) drives E/T beyond MAX_EXPONENT ~ 709.78 on
+    part of the grid: the equilibrium-distribution guard of boltzmann.py:864-886 must act on the same points
+    (source exactly -0 there) and the solve must agree with the oracle."""
+    import wallgo_b200 as wb
+    from conftest import FixtureBackground, FixtureGrid
+
+    P, M, N = 2, 8, 7
+    pb = oracle.synthetic_problem(P, M, N, seed=9)
+    pb.T = pb.T / 200.0
+    rq = oracle.row_quantities(pb)
+    x = rq["Epl"] / rq["T"]
+    assert np.any(x > 709.782712893384) and np.any(x < 700.0)      # the guard is exercised, and not everywhere
+    g = dict(P=P, M=M, N=N, chi=pb.tab.chi, rz=pb.tab.rz, rp=pb.tab.rp, pz=pb.pz, pp=pb.pp,
+             dxidchi=pb.xi_dxidchi, dpzdrz=pb.dpzdrz, dppdrp=pb.dppdrp, vw=pb.vw, v=pb.v, T=pb.T, msq=pb.msq)
+    grid = FixtureGrid(g)
+    parts = [wb.Particle(f"p{a}", a, (lambda f, a=a: f.msq[a]), None,
+                         "Fermion" if pb.statistics[a] < 0 else "Boson", 12) for a in range(P)]
+    solver = wb.BoltzmannSolver(grid)
+    solver.updateParticleList(parts)
+    solver.setBackground(FixtureBackground(g))
+    solver.setCollisionArray(wb.CollisionArray(grid, "Chebyshev", parts, pb.collision))
+    op_ref, src_ref = oracle.assemble(pb)
+    op, src, _, _ = solver.buildLinearEquations()
+    assert np.all(np.isfinite(src)) and np.all(np.isfinite(op))
+    assert relmax(src, src_ref) < 1e-12
+    assert np.array_equal(src == 0.0, src_ref == 0.0)
+    assert relmax(op, op_ref) < 1e-12
+    ref = oracle.get_deltas(pb, None, "AUTO")
+    res = solver.getDeltas()
+    assert tuple(res.truncatedTail) == tuple(ref["truncatedTail"])
+    assert relmax(res.deltaF, ref["deltaF"]) < TOL
