@@ -491,3 +491,17 @@ def test_lu_plan_reused_with_alternating_buffers(env):
             assert np.array_equal(bd[turn].cpu().numpy(), ref[turn][3])
     finally:
         lib.wg_lu_destroy(plan)
+
+
+@pytest.mark.parametrize("n,rows", [(64, (3, 40)), (600, (5, 100, 599)), (2600, (700, 1300, 2500)), (9000, (4500, 8999, 600))])
+def test_lu_first_maximal_entry_wins_ties(env, n, rows):
+    """LAPACK's idamax takes the FIRST row of maximal |a|: exact ties that sit in different warps, CTAs of the
+    cluster and with either sign must resolve to the smallest row index."""
+    rng = np.random.default_rng(n)
+    A = rng.uniform(-0.5, 0.5, size=(n, n))
+    for i, r in enumerate(rows):
+        A[r, 0] = 7.25 if i % 2 == 0 else -7.25
+    LU, ipiv, info, _ = _lu(env, A)
+    assert info == 0
+    assert ipiv[0] == min(rows)
+    assert abs(LU[0, 0]) == 7.25
