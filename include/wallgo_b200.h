@@ -117,7 +117,7 @@ int wg_info(wg_solver* s, void* stream, int* info_host);
  * solver) and spectra_dev[(M-1)+2(N-1)] = sum|c| along (chi | pz | pp). */
 int wg_spectra(wg_solver* s, const double* deltaF_dev, double* spectra_dev, void* stream);
 /* second half + estimateTruncationError + getDeltas quadrature (boltzmann.py:296-351, 431-491, 182-238):
- * keep* = number of coefficients kept per axis; roundtrip = 0 returns the input deltaF unchanged
+ * keep* = number of coefficients kept per axis (0 zeroes the axis); roundtrip = 0 returns the input deltaF unchanged
  * (ETruncationOption.NONE).  Outputs: deltaF_out_dev[n], deltas_dev[4*P*(M-1)] (Delta00,02,20,11),
  * err_dev[4*P] (sum|c| kept, and on the last kept chi/pz/pp slice, per species). */
 int wg_moments(wg_solver* s, const double* deltaF_dev, const double* profiles_dev, int keepM, int keepPz,

@@ -329,3 +329,37 @@ def test_auto_concurrency_policy():
     assert ac(31200, freeBytes=20 * 2**30) == 1          # one 7.8 GB operator + workspace in 60 % of 20 GB
     assert ac(15600, freeBytes=170 * 2**30) == 3
     assert ac(1900, freeBytes=2**30) >= 1
+
+
+@pytest.mark.parametrize("M,N,option", [(3, 7, "AUTO"), (3, 7, "THIRD"), (8, 3, "AUTO"), (8, 3, "THIRD"), (3, 3, "THIRD"),
+                                        (3, 3, "NONE"), (4, 5, "AUTO")])
+def test_truncation_on_grids_with_fewer_than_three_coefficients(M, N, option):
+    """With fewer than three coefficients along an axis the reference's cut is 0 and its slice `[-0:]` is the
+    whole axis: a truncation zeroes everything along it while the reported shape does not change
+    (boltzmann.py:400-446).  The host decision must tell the device to keep 0 coefficients there and report the
+    reference's shape; checked against the oracle's restatement of the same lines."""
+    import wallgo_b200 as wb
+    from oracle import boltzmann_oracle as bo
+    from conftest import FixtureGrid
+
+    rng = np.random.default_rng(M * 100 + N)
+    P = 2
+    pb = bo.synthetic_problem(P, M, N, seed=1)
+    dF = rng.standard_normal((P, M - 1, N - 1, N - 1)) * np.exp(0.3 * np.arange(M - 1))[None, :, None, None]
+    ref_dF, ref_shape, ref_peaks = bo.check_spectral_convergence(dF, pb.tab, option)
+    c = np.abs(bo.to_chebyshev(dF, pb.tab))
+    spectra = np.concatenate([c.sum(axis=(0, 2, 3)), c.sum(axis=(0, 1, 3)), c.sum(axis=(0, 1, 2))])
+    g = dict(P=P, M=M, N=N, chi=pb.tab.chi, rz=pb.tab.rz, rp=pb.tab.rp, pz=pb.pz, pp=pb.pp,
+             dxidchi=pb.xi_dxidchi, dpzdrz=pb.dpzdrz, dppdrp=pb.dppdrp)
+    solver = wb.BoltzmannSolver(FixtureGrid(g), truncationOption=getattr(wb.ETruncationOption, option))
+    keep, peaks = solver._decideTruncation(spectra)
+    assert tuple(keep) == tuple(ref_shape[1:])
+    assert tuple(peaks) == tuple(ref_peaks)
+    # what the device is told to keep reproduces the oracle's truncated coefficients
+    cc = bo.to_chebyshev(dF, pb.tab).copy()
+    cc[:, keep.dev[0]:, :, :] = 0
+    cc[:, :, keep.dev[1]:, :] = 0
+    cc[:, :, :, keep.dev[2]:] = 0
+    ref_c = bo.to_chebyshev(ref_dF, pb.tab) if option != "NONE" else bo.to_chebyshev(dF, pb.tab)
+    if option != "NONE":
+        assert np.max(np.abs(cc - ref_c)) <= 1e-12 * max(1.0, np.max(np.abs(ref_c)))

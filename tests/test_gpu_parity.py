@@ -5,6 +5,8 @@ Tolerances (BASELINE.json north_star): deltaF and the four Delta moments <= 1e-1
 (to the max-norm of the quantity); integer outputs (truncation flags, kept shapes, spectral
 peaks) must be equal.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -322,3 +324,18 @@ def test_overflow_guard_matches_oracle(cuda_device, oracle):
     res = solver.getDeltas()
     assert tuple(res.truncatedTail) == tuple(ref["truncatedTail"])
     assert relmax(res.deltaF, ref["deltaF"]) < TOL
+
+
+@pytest.mark.parametrize("tool,args", [("parity_fuzz.py", ("20", "11")), ("lu_fuzz.py", ("44", "5"))])
+def test_fuzz_subsets(cuda_device, tool, args):
+    """Seeded subsets of the two fuzzers: random sizes / bases / derivative and truncation options against the
+    oracle (1e-10, equal truncation flags and peaks), and structured matrices (sparse, low rank, duplicated rows,
+    300 orders of magnitude, integer ties, zero blocks, non-finite entries) against LAPACK."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", tool), *args], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " 0 bad" in r.stdout.splitlines()[-1]

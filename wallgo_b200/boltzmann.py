@@ -28,6 +28,14 @@ class _OwnTypes:
     BoltzmannResults = _own.BoltzmannResults
 
 
+class _Keep(list):
+    """Truncated shape per axis as the reference reports it, plus `.dev`: what the device keeps."""
+
+    def __init__(self, sizes):
+        super().__init__(sizes)
+        self.dev = list(sizes)
+
+
 class BoltzmannSolverB200Mixin:
     """Implementation shared by the standalone class below and the WallGo drop-in subclass."""
 
@@ -192,29 +200,31 @@ class BoltzmannSolverB200Mixin:
         return operator, source, liouville, collision
 
     def _decideTruncation(self, spectra):
-        """Host half of checkSpectralConvergence (boltzmann.py:399-483) on device-reduced spectra."""
+        """Host half of checkSpectralConvergence (boltzmann.py:399-483) on device-reduced spectra.
+
+        Returns (keep, peaks): keep[axis] is the truncated shape the reference reports; keep.dev[axis] is the
+        number of coefficients the device actually retains.  They differ only on grids with fewer than three
+        coefficients along an axis: there the reference's cut is `-(size // 3) == 0`, its slice `[-0:]` is the
+        WHOLE axis, so a truncation zeroes everything while the reported shape stays unchanged
+        (boltzmann.py:400-446) -- reproduced here for drop-in fidelity."""
         g = self.grid
         M1, N1 = g.M - 1, g.N - 1
         sChi, sPz, sPp = spectra[:M1], spectra[M1:M1 + N1], spectra[M1 + N1:]
         cutM, cutN = M1 // 3, N1 // 3
-        # (for grids with fewer than 3 coefficients per axis the reference's `[-0:]` slice is the
-        # whole axis; such grids are only used by its residual test, never with getDeltas)
-        conv = (tailConverging(sChi[M1 - cutM:], M1 - cutM),
-                tailConverging(sPz[N1 - cutN:], N1 - cutN),
-                tailConverging(sPp[N1 - cutN:], N1 - cutN))
-        keep = [M1, N1, N1]
+        conv = (tailConverging(sChi[M1 - cutM:] if cutM else sChi, M1 - cutM),
+                tailConverging(sPz[N1 - cutN:] if cutN else sPz, N1 - cutN),
+                tailConverging(sPp[N1 - cutN:] if cutN else sPp, N1 - cutN))
+        keep = _Keep([M1, N1, N1])
         if self.truncationOption == ETruncationOption.AUTO or self.truncationOption.name == "AUTO":
             cut = [not c for c in conv]
         elif self.truncationOption.name == "THIRD":
             cut = [True, True, True]
         else:
             cut = [False, False, False]
-        if cut[0]:
-            keep[0] = M1 - cutM
-        if cut[1]:
-            keep[1] = N1 - cutN
-        if cut[2]:
-            keep[2] = N1 - cutN
+        for axis, (size, c) in enumerate(((M1, cutM), (N1, cutN), (N1, cutN))):
+            if cut[axis]:
+                keep[axis] = size - c
+                keep.dev[axis] = size - c if c > 0 else 0
         peaks = (spectralPeak(sChi[:keep[0]], 0), spectralPeak(sPz[:keep[1]], 1),
                  spectralPeak(sPp[:keep[2]], 2))
         return keep, peaks
@@ -230,7 +240,7 @@ class BoltzmannSolverB200Mixin:
         spectra = eng.spectra_to_host()
         keep, peaks = self._decideTruncation(spectra)
         roundtrip = self.truncationOption.name != "NONE"
-        eng.moments_async(dFdev, keep, roundtrip)
+        eng.moments_async(dFdev, keep.dev, roundtrip)
         dF, deltas, err = eng.results_to_host()
         return dF, deltas, err, keep, peaks
 
@@ -376,7 +386,7 @@ class BoltzmannSolverB200Mixin:
             if phase == 0:
                 keep, peaks = s_._decideTruncation(eng.spectra_host.numpy().copy())
                 with torch.cuda.stream(s_._stream):
-                    eng.moments_async(eng.S, keep, s_.truncationOption.name != "NONE")
+                    eng.moments_async(eng.S, keep.dev, s_.truncationOption.name != "NONE")
                     eng.out_host.copy_(eng.out, non_blocking=True)
                     ev2 = torch.cuda.Event()
                     ev2.record(s_._stream)

@@ -406,7 +406,9 @@ int wg_moments(wg_solver* s, const double* deltaF_dev, const double* profiles_de
                void* stream) {
   WG_REQUIRE(s && deltaF_dev && profiles_dev && deltaF_out_dev && deltas_dev && err_dev,
              "wg_moments: NULL argument");
-  WG_REQUIRE(keepM >= 1 && keepM <= s->d.M1 && keepPz >= 1 && keepPz <= s->d.N1 && keepPp >= 1 &&
+  // 0 is allowed: on grids with fewer than three coefficients along an axis the reference's truncation
+  // zeroes the whole axis (boltzmann.py:400-446, the slice [-0:])
+  WG_REQUIRE(keepM >= 0 && keepM <= s->d.M1 && keepPz >= 0 && keepPz <= s->d.N1 && keepPp >= 0 &&
                  keepPp <= s->d.N1,
              "wg_moments: keep counts out of range");
   WG_REQUIRE(s->haveGrid, "wg_moments: grid not set");
