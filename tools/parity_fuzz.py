@@ -40,6 +40,31 @@ for case in range(ncases):
     ed = max(relmax(D[i], ref["Deltas"][i]) for i in range(4))
     same = tuple(res.truncatedTail) == tuple(ref["truncatedTail"]) and tuple(res.spectralPeaks) == tuple(ref["spectralPeaks"])
     worst = max(worst, e, ed)
+    # operator / source, the spectral queries on a foreign deltaF, and the linearisation criteria
+    extra = []
+    if case % 2 == 0:
+        op_ref, src_ref = bo.assemble(pb)
+        op, src, _, _ = solver.buildLinearEquations()
+        if relmax(op, op_ref) > 1e-12 or relmax(src, src_ref) > 1e-12:
+            extra.append(f"operator {relmax(op, op_ref):.1e} source {relmax(src, src_ref):.1e}")
+        dFx = rng.standard_normal(ref["deltaF"].shape) * np.exp(rng.uniform(-0.5, 0.5) * np.arange(M - 1))[None, :, None, None]
+        r_dF, r_shape, r_peaks = bo.check_spectral_convergence(dFx, pb.tab, option)
+        g_dF, g_shape, g_peaks = solver.checkSpectralConvergence(dFx)
+        if tuple(g_shape) != tuple(r_shape) or tuple(g_peaks) != tuple(r_peaks) or relmax(g_dF, r_dF) > 1e-11:
+            extra.append(f"checkSpectralConvergence shape {g_shape} vs {r_shape} peaks {g_peaks} vs {r_peaks} dF {relmax(g_dF, r_dF):.1e}")
+        with np.errstate(all="ignore"):
+            te_ref = bo.estimate_truncation_error(r_dF, r_shape, pb.tab)
+            te = solver.estimateTruncationError(g_dF, g_shape)
+        if np.isfinite(te_ref) and abs(te - te_ref) > 1e-9 * max(abs(te_ref), 1e-300):
+            extra.append(f"estimateTruncationError {te} vs {te_ref}")
+    if case % 3 == 0 and min(M, N) >= 5:
+        c_ref = bo.check_linearization(pb)
+        c_gpu = solver.checkLinearization()
+        if any(abs(a - b) > 1e-7 * abs(b) for a, b in zip(c_gpu, c_ref)):
+            extra.append(f"checkLinearization {c_gpu} vs {c_ref}")
+    for msg in extra:
+        bad += 1
+        print("  MISMATCH", msg)
     if not same or e > 1e-10 or ed > 1e-10:
         bad += 1
         print(f"  MISMATCH deltaF {e:.2e} Deltas {ed:.2e} flags {res.truncatedTail} vs {ref['truncatedTail']} peaks {res.spectralPeaks} vs {ref['spectralPeaks']}")
