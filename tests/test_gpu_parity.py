@@ -339,3 +339,37 @@ def test_fuzz_subsets(cuda_device, tool, args):
                        timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert " 0 bad" in r.stdout.splitlines()[-1]
+
+
+def test_two_solvers_interleaved(cuda_device):
+    """Two solvers of different sizes used alternately in one process (each with its own handle, LU plan and
+    cached graphs) give what each gives alone."""
+    import wallgo_b200 as wb
+    from wallgo_b200 import synthetic
+
+    def make(P, M, N):
+        grid = synthetic.makeGrid(M, N)
+        parts = synthetic.makeParticles(P)
+        s = wb.BoltzmannSolver(grid)
+        s.updateParticleList(parts)
+        s.setCollisionArray(synthetic.makeCollision(grid, parts))
+        return s, grid
+
+    a, ga = make(1, 8, 5)
+    b, gb = make(2, 10, 7)
+    vms = (-0.3, -0.45, -0.6)
+    alone_a, alone_b = [], []
+    for vm in vms:
+        a.setBackground(synthetic.makeBackground(ga, velocityMid=vm))
+        alone_a.append(a.getDeltas())
+    for vm in vms:
+        b.setBackground(synthetic.makeBackground(gb, velocityMid=vm))
+        alone_b.append(b.getDeltas())
+    for i, vm in enumerate(vms):
+        a.setBackground(synthetic.makeBackground(ga, velocityMid=vm))
+        b.setBackground(synthetic.makeBackground(gb, velocityMid=vm))
+        rb = b.getDeltas()
+        ra = a.getDeltas()
+        assert np.array_equal(ra.deltaF, alone_a[i].deltaF) and np.array_equal(rb.deltaF, alone_b[i].deltaF)
+        assert np.array_equal(ra.Deltas.Delta20.coefficients, alone_a[i].Deltas.Delta20.coefficients)
+        assert np.array_equal(rb.Deltas.Delta11.coefficients, alone_b[i].Deltas.Delta11.coefficients)
