@@ -505,3 +505,55 @@ def test_lu_first_maximal_entry_wins_ties(env, n, rows):
     assert info == 0
     assert ipiv[0] == min(rows)
     assert abs(LU[0, 0]) == 7.25
+
+
+def test_lu_beyond_32768_rows(env):
+    """Panels taller than 32768 rows use 8 rows x 4 columns per thread in the leaf cluster (capacity 65536):
+    a 33 280-row system (8.9 GB) is factored and solved on the device, the solution satisfies the system."""
+    torch, lib, _lib = env
+    n = 33280
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    A = torch.randn(n, n, dtype=torch.float64, device="cuda", generator=gen)
+    A0 = A.clone()
+    b = torch.randn(n, dtype=torch.float64, device="cuda", generator=gen)
+    x = b.clone()
+    ipiv = torch.zeros(n, dtype=torch.int32, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    plan = C.c_void_p()
+    _lib.check(lib.wg_lu_create(n, 0, C.byref(plan)), "wg_lu_create")
+    try:
+        _lib.check(lib.wg_lu_factor(plan, A.data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), _stream(torch)), "factor")
+        _lib.check(lib.wg_lu_solve(plan, A.data_ptr(), n, x.data_ptr(), _stream(torch)), "solve")
+        torch.cuda.synchronize()
+    finally:
+        lib.wg_lu_destroy(plan)
+    assert int(info.item()) == 0
+    p = ipiv.cpu().numpy()
+    assert np.all(p >= np.arange(n)) and p.max() < n
+    r = torch.mv(A0, x) - b
+    rel = float(torch.linalg.norm(r) / (torch.linalg.norm(A0) * torch.linalg.norm(x)))
+    assert rel < 1e-14, rel
+    assert float(torch.max(torch.abs(torch.tril(A, -1)))) <= 1.0 + 1e-12      # partial pivoting bounds the multipliers
+
+
+@pytest.mark.parametrize("wb", [4, 8])
+def test_lu_tall_panel_leaf_variants_at_small_size(env, wb):
+    """The leaf variants meant for very tall panels (8 columns x up to 4 rows per thread beyond 16384 rows,
+    4 columns x 8 rows beyond 32768) forced on a small matrix: same pivots as the default blocking, factors
+    equal to rounding (the blocking differs, so not bit for bit)."""
+    torch, lib, _ = env
+    n = 700
+    rng = np.random.default_rng(17)
+    A = rng.standard_normal((n, n))
+    b = rng.standard_normal(n)
+    LU0, ipiv0, info0, x0 = _lu(env, A, b)
+    try:
+        lib.wg_debug_force_wb(wb)
+        LU1, ipiv1, info1, x1 = _lu(env, A, b)
+    finally:
+        lib.wg_debug_force_wb(0)
+    assert info0 == info1 == 0
+    assert np.array_equal(ipiv0, ipiv1)
+    assert np.max(np.abs(LU0 - LU1)) / np.max(np.abs(LU0)) < 1e-11
+    assert np.max(np.abs(x0 - x1)) / np.max(np.abs(x0)) < 1e-9
+    _check_factors(A, LU1, ipiv1)

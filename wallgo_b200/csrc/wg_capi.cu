@@ -108,6 +108,11 @@ int wg_debug_asm_wide(int on) {
 }
 /* developer probe (not part of the public header; built with -DWG_LEAF_CHECKS): first bounds violation in a leaf */
 int wg_debug_leaf_fail(int* out8) { return wg::lu_leaf_fail_read(out8); }
+/* developer knob (not part of the public header): force the leaf width class of the LU panels */
+int wg_debug_force_wb(int wb) {
+  wg::lu_set_force_wb(wb);
+  return WG_OK;
+}
 int wg_set_lookahead(int on) {
   wg::lu_set_lookahead(on);
   return WG_OK;

@@ -24,6 +24,7 @@ void lu_set_profile(int on);
 int lu_profile_read(LuPlan* p, double* ms, double* flops, int* count);
 void lu_set_trace(int on);
 void lu_set_leaf32(int on);
+void lu_set_force_wb(int wb);
 int lu_leaf_fail_read(int* out);
 void lu_set_split(int on);
 void lu_set_bulk_hi(int rest);
