@@ -271,10 +271,12 @@ def test_full_size_properties(cuda_device):
     assert np.all(np.isfinite(res1.Deltas.Delta11.coefficients))
 
 
-@pytest.mark.parametrize("P,M,N", [(3, 30, 11), (4, 30, 11), (2, 40, 21)])
+@pytest.mark.parametrize("P,M,N", [(3, 30, 11), (4, 30, 11), (2, 40, 21), (4, 8, 31), (4, 64, 15)])
 def test_other_baseline_sizes_residual(cuda_device, P, M, N):
-    """BASELINE configs 3, 4 and the two-species reading of config 2 (n = 8700, 11600, 31200) through the
-    public class: the solution satisfies the assembled system, the factors reproduce the operator row sums,
+    """BASELINE configs 3, 4 and the two-species reading of config 2 (n = 8700, 11600, 31200), and the two
+    reductions of config 5 (4 species, M=64, N=31: 411 GB, does not fit) that do fit one B200 -- its momentum grid
+    N=31 with 4 species at M=8 (n = 25200) and its spatial grid M=64 with 4 species at N=15 (n = 49392, 19.5 GB,
+    beyond 32768 rows) -- through the public class: the solution satisfies the assembled system, the factors reproduce the operator row sums,
     and several systems in flight return exactly what one at a time returns."""
     import torch
     import wallgo_b200 as wb
