@@ -271,12 +271,13 @@ def test_full_size_properties(cuda_device):
     assert np.all(np.isfinite(res1.Deltas.Delta11.coefficients))
 
 
-@pytest.mark.parametrize("P,M,N", [(3, 30, 11), (4, 30, 11), (2, 40, 21), (4, 8, 31), (4, 64, 15)])
+@pytest.mark.parametrize("P,M,N", [(3, 30, 11), (4, 30, 11), (2, 40, 21), (4, 8, 31), (4, 64, 15), (4, 64, 21)])
 def test_other_baseline_sizes_residual(cuda_device, P, M, N):
     """BASELINE configs 3, 4 and the two-species reading of config 2 (n = 8700, 11600, 31200), and the two
     reductions of config 5 (4 species, M=64, N=31: 411 GB, does not fit) that do fit one B200 -- its momentum grid
     N=31 with 4 species at M=8 (n = 25200) and its spatial grid M=64 with 4 species at N=15 (n = 49392, 19.5 GB,
-    beyond 32768 rows) -- through the public class: the solution satisfies the assembled system, the factors reproduce the operator row sums,
+    beyond 32768 rows) and at N=21 (n = 100800, an 81 GB operator: the largest of the family that fits 180 GB) --
+    through the public class: the solution satisfies the assembled system, the factors reproduce the operator row sums,
     and several systems in flight return exactly what one at a time returns."""
     import torch
     import wallgo_b200 as wb
@@ -538,7 +539,7 @@ def test_lu_beyond_32768_rows(env):
     assert float(torch.max(torch.abs(torch.tril(A, -1)))) <= 1.0 + 1e-12      # partial pivoting bounds the multipliers
 
 
-@pytest.mark.parametrize("wb", [4, 8])
+@pytest.mark.parametrize("wb", [2, 4, 8])
 def test_lu_tall_panel_leaf_variants_at_small_size(env, wb):
     """The leaf variants meant for very tall panels (8 columns x up to 4 rows per thread beyond 16384 rows,
     4 columns x 8 rows beyond 32768) forced on a small matrix: same pivots as the default blocking, factors

@@ -36,7 +36,7 @@ namespace wg {
 constexpr int PT = 512;       // threads per leaf-panel CTA
 constexpr int PNW = PT / 32;  // warps per leaf-panel CTA
 constexpr int MAXCL = 16;     // largest cluster
-constexpr int MAXEXT = 252;   // widest "rest of the panel" a leaf has to move (NB - 4, the narrowest leaf)
+constexpr int MAXEXT = 254;   // widest "rest of the panel" a leaf has to move (NB - 2, the narrowest leaf)
 
 static long long* g_dbg_buf = nullptr;  // developer probe: timestamps of the leaf starting at column g_dbg_c0
 static int g_dbg_c0 = -1;
@@ -1138,6 +1138,7 @@ static int leaf(FactorCtx& c, int c0, int w, int pc0, int pc1) {
     if (m <= c.p->maxCL * PT) return launch_leaf<16, 1>(pa, pick_cl(PT), c.st);
     return launch_leaf<16, 2>(pa, pick_cl(PT * 2), c.st);
   }
+  if (c.wb == 2) return launch_leaf<2, 16>(pa, pick_cl(PT * 16), c.st);  // up to 131072 rows: 16 rows x 2 columns per thread
   if (c.wb == 4) return launch_leaf<4, 8>(pa, pick_cl(PT * 8), c.st);   // up to 65536 rows: 8 rows x 4 columns per thread
   if (m <= c.p->maxCL * PT) return launch_leaf<8, 1>(pa, pick_cl(PT), c.st);
   if (m <= c.p->maxCL * PT * 2) return launch_leaf<8, 2>(pa, pick_cl(PT * 2), c.st);
@@ -1225,12 +1226,14 @@ static int g_force_wb = 0;  // developer knob: force the leaf width class (4: th
 void lu_set_force_wb(int wb) { g_force_wb = wb; }
 
 static int panel_width_class(LuPlan* p, int m) {
+  if (g_force_wb == 2 && m <= p->maxCL * PT * 16) return 2;
   if (g_force_wb == 4 && m <= p->maxCL * PT * 8) return 4;
   if (g_force_wb == 8 && m <= p->maxCL * PT * 4) return 8;
   if (g_leaf32 && m <= p->maxCL * PT) return 32;
   if (m <= p->maxCL * PT * 2) return 16;
   if (m <= p->maxCL * PT * 4) return 8;
   if (m <= p->maxCL * PT * 8) return 4;
+  if (m <= p->maxCL * PT * 16) return 2;
   return 0;
 }
 
@@ -1320,7 +1323,7 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
   WG_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
   if (panel_width_class(p, n) == 0) {
     wg_set_error("lu_factor: n=%d exceeds the leaf-panel capacity (%d rows) of this build", n,
-                 p->maxCL * PT * 8);
+                 p->maxCL * PT * 16);
     return WG_ERR_UNSUPPORTED;
   }
   struct PrioGuard {
