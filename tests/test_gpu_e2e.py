@@ -1,0 +1,93 @@
+"""End-to-end gate with the CUDA engine in the loop (BASELINE.json north star: final wall velocity and
+widths within 1e-6 relative).
+
+The UNMODIFIED reference `WallGoManager.solveWall` (manager.py:484-511 -> equationOfMotion.py:408-784) is run
+twice on the same manager in the same job: once with the reference's own `BoltzmannSolver` (NumPy/LAPACK on
+the host) and once with `wallgo_b200.dropin` installed at the construction site (manager.py:605-611), i.e.
+with every Boltzmann solve, the finite-difference re-solve (equationOfMotion.py:2129-2143) and
+`checkLinearization` (:647) on the B200.  The reference is the pure-Python copy under oracle/_ref
+(oracle/fetch_ref.sh); collision tensors are the in-memory relaxation-time tensor for both arms (the shipped
+.hdf5 files are Git-LFS pointers).  StandardModel and InertDoublet take minutes on the host arm: WG_SLOW=1.
+"""
+import os
+import time
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+CASES = [("yukawa", 20, 11, False), ("singlet", 20, 11, False), ("sm", 30, 11, True), ("idm", 30, 11, True)]
+
+
+@pytest.fixture(scope="module")
+def rd():
+    from oracle import ref_drivers
+    if ref_drivers.reference_root() is None:
+        pytest.skip("reference copy not present (oracle/fetch_ref.sh fills oracle/_ref in the build container)")
+    return ref_drivers
+
+
+def _run_pair(rd, name, M, N, log):
+    WallGo = rd.load_reference()
+    import WallGo.manager as mgr
+    from wallgo_b200 import _lib, dropin
+
+    refCls = WallGo.boltzmann.BoltzmannSolver
+    manager, settings, _ = rd.build_manager(name, M, N)
+    saved = mgr.BoltzmannSolver
+    origRef = rd.patch_load_collisions(refCls)
+    cls = dropin.makeDropInClass()
+    origNew = rd.patch_load_collisions(cls)
+    try:
+        mgr.BoltzmannSolver = refCls
+        t0 = time.perf_counter()
+        rRef = manager.solveWall(settings)
+        tRef = time.perf_counter() - t0
+        mgr.BoltzmannSolver = cls
+        lib = _lib.load()
+        l0 = lib.wg_launch_count()
+        t0 = time.perf_counter()
+        rNew = manager.solveWall(settings)
+        tNew = time.perf_counter() - t0
+        launches = lib.wg_launch_count() - l0
+    finally:
+        mgr.BoltzmannSolver = saved
+        refCls.loadCollisions = origRef
+        if origNew is None:
+            del cls.loadCollisions
+        else:
+            cls.loadCollisions = origNew
+    log.append(f"{name} M={M} N={N}: reference {tRef:.1f}s, B200 drop-in {tNew:.1f}s, {launches} kernels; "
+               f"vw ref {rRef.wallVelocity!r} new {rNew.wallVelocity!r}")
+    return rRef, rNew, launches
+
+
+@pytest.mark.parametrize("name,M,N,slow", CASES)
+def test_solveWall_gate(cuda_device, rd, name, M, N, slow):
+    if slow and not os.environ.get("WG_SLOW"):
+        pytest.skip("minutes of host time on the reference arm: set WG_SLOW=1")
+    log = []
+    rRef, rNew, launches = _run_pair(rd, name, M, N, log)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "e2e_gate.log"), "a") as f:
+        f.write("\n".join(log) + "\n")
+    assert launches > 0, "the CUDA engine was not in the loop"
+    assert rRef.success and rNew.success and rRef.solutionType == rNew.solutionType
+    vRef, vNew = rd.result_vector(rRef), rd.result_vector(rNew)
+    assert np.allclose(vNew, vRef, rtol=1e-6, atol=1e-12), (vNew, vRef)
+    assert abs(rNew.wallVelocity - rRef.wallVelocity) <= 1e-6 * abs(rRef.wallVelocity)
+    # the solution the wall solver returns: deltaF, moments, error estimates, linearisation criteria
+    scale = np.max(np.abs(rRef.deltaF))
+    assert np.max(np.abs(rNew.deltaF - rRef.deltaF)) <= 1e-6 * scale
+    assert np.allclose(rd.deltas_table(rNew), rd.deltas_table(rRef), rtol=0,
+                       atol=1e-6 * np.max(np.abs(rd.deltas_table(rRef))))
+    assert np.allclose(rNew.temperatureProfile, rRef.temperatureProfile, rtol=1e-6)
+    assert np.allclose(rNew.velocityProfile, rRef.velocityProfile, rtol=1e-6, atol=1e-12)
+    assert abs(rNew.linearizationCriterion1 - rRef.linearizationCriterion1) <= 1e-5 * abs(rRef.linearizationCriterion1)
+    assert abs(rNew.linearizationCriterion2 - rRef.linearizationCriterion2) <= 1e-5 * abs(rRef.linearizationCriterion2)
+    sFD = np.max(np.abs(rRef.deltaFFiniteDifference))
+    assert np.max(np.abs(rNew.deltaFFiniteDifference - rRef.deltaFFiniteDifference)) <= 1e-6 * sFD
+    assert abs(rNew.wallVelocityError - rRef.wallVelocityError) <= 1e-4 * abs(rRef.wallVelocityError) + 1e-12
