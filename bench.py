@@ -141,6 +141,41 @@ def cpu_port_one_solve(grid, particles, coll, bg):
     return dict(assemble_s=t1 - t0, dgesv_s=t2 - t1, moments_s=t3 - t2, total_s=t3 - t0), out
 
 
+def reference_available():
+    from oracle import ref_drivers as rd
+    return rd.reference_root() is not None
+
+
+def reference_one_solve(P, M, N, velocityMid, want_solver=False):
+    """The UNMODIFIED reference class (WallGo.BoltzmannSolver from oracle/_ref, pure Python: NumPy broadcasting
+    + LAPACK dgesv through np.linalg.solve) on the host cores: one full solve of the synthetic system of
+    SURVEY.md section 8(d), the stages timed as the reference runs them (boltzmann.py:141-294, 628-820)."""
+    from oracle import ref_drivers as rd
+
+    try:
+        from threadpoolctl import threadpool_limits
+        limiter = threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        limiter = None
+    try:
+        solver, grid, bg, particles = rd.synthetic_solver(P, M, N, velocityMid=velocityMid)
+        t0 = time.perf_counter()
+        op, src, _, _ = solver.buildLinearEquations()
+        t1 = time.perf_counter()
+        dF = np.linalg.solve(op, src).reshape(P, M - 1, N - 1, N - 1)       # boltzmann.py:283
+        t2 = time.perf_counter()
+        del op
+        res = solver.getDeltas(dF)
+        t3 = time.perf_counter()
+    finally:
+        if limiter is not None:
+            limiter.restore_original_limits()
+    t = dict(assemble_s=t1 - t0, dgesv_s=t2 - t1, moments_s=t3 - t2, total_s=t3 - t0)
+    if want_solver:
+        return t, res, (solver, grid, bg, particles)
+    return t, res
+
+
 def blas_info():
     try:
         from threadpoolctl import threadpool_info, threadpool_limits
@@ -156,19 +191,26 @@ def run_reference(a):
     if rank != 0:
         return
     P, M, N = WORKLOADS[a.workload]
+    real = reference_available()
     grid, particles, coll, bgs = build_inputs(P, M, N, a.steps + a.warmup, 0)
     budget = float(a.ref_budget_s)
+
+    def one(i):
+        if real:     # same wall velocities as the b200 arm's steps (build_inputs)
+            return reference_one_solve(P, M, N, -0.3 - 0.4 * (i % 97) / 97.0)
+        return cpu_port_one_solve(grid, particles, coll, bgs[i])
+
     for i in range(min(a.warmup, 1)):
-        cpu_port_one_solve(grid, particles, coll, bgs[i])
+        one(i)
     t0 = time.perf_counter()
     done, parts = 0, []
     for i in range(a.steps):
-        t, _ = cpu_port_one_solve(grid, particles, coll, bgs[a.warmup + i])
+        t, _ = one(a.warmup + i)
         parts.append(t)
         done += 1
         if time.perf_counter() - t0 > budget:
             break
-    el = time.perf_counter() - t0
+    el = sum(p_["total_s"] for p_ in parts)     # the hot path only: building the synthetic inputs is not a step
     val = done / el
     n = P * (M - 1) * (N - 1) ** 2
     sample = (f"{done} of {a.steps} requested full solves (assemble+dgesv+moments) at P={P},M={M},N={N}, "
@@ -179,16 +221,135 @@ def run_reference(a):
             "steps": done, "warmup": min(a.warmup, 1), "ms_per_step": 1e3 * el / done, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{a.workload}: P={P} M={M} N={N} n={n}, synthetic collision tensor",
-                       "note": "reference is pure Python and cannot travel to the GPU box; this arm runs the "
-                               "oracle port (NumPy broadcasting + LAPACK dgesv) of the same path"},
-            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": os.cpu_count(), "kind": "port",
-                             "sample": sample},
+                       "note": ("the unmodified reference class WallGo.BoltzmannSolver (pure Python copy under "
+                                "oracle/_ref): buildLinearEquations + np.linalg.solve + getDeltas" if real else
+                                "oracle/_ref absent on this machine: the oracle port (NumPy broadcasting + LAPACK "
+                                "dgesv) of the same path")},
+            "cpu_baseline": {"value": val, "unit": "solves/s", "cores": os.cpu_count(),
+                             "kind": "reference" if real else "port", "sample": sample},
             "e2e": {"value": val, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if a.scan_points > 0 and real and a.ref_scan_points > 0:
+        try:
+            import contextlib
+            with contextlib.redirect_stdout(sys.stderr):      # the reference prints its phase tracing to stdout
+                line["scan"] = reference_scan(a)
+        except Exception as exc:  # the main line must survive a failure of the secondary metric
+            line["scan"] = {"error": repr(exc)[:300]}
     print(json.dumps(line), flush=True)
 
 
+SCAN_MODELS = {"idm": (4, 30, 11), "yukawa": (2, 20, 11), "singlet": (1, 20, 11), "sm": (3, 30, 11)}
+
+
+def scan_velocities(manager, npts):
+    """256 wall velocities uniformly in [vMin, 0.53] for the InertDoublet driver (vJ = 0.5333): the valid
+    deflagration range of equationOfMotion.py:186-187."""
+    hyd = manager.hydrodynamics
+    hi = min(0.53, 0.995 * hyd.vJ)
+    lo = max(float(hyd.vMin), 0.01)
+    return np.linspace(lo, hi, npts)
+
+
+def reference_scan(a):
+    """CPU anchor of the scan metric: the unmodified reference (its own BoltzmannSolver on the host) on a
+    bounded sample of the same scan points."""
+    from oracle import ref_drivers as rd
+
+    WallGo = rd.load_reference()
+    P, M, N = SCAN_MODELS[a.scan_model]
+    rd.patch_load_collisions(WallGo.boltzmann.BoltzmannSolver)
+    t0 = time.perf_counter()
+    manager, settings, _ = rd.build_manager(a.scan_model, M, N)
+    setup = time.perf_counter() - t0
+    vws = scan_velocities(manager, a.scan_points)
+    ws = manager.setupWallSolver(settings)
+    eom = ws.eom
+    eom.pressAbsErrTol = 1e-8
+    wp0 = WallGo.WallParams(widths=ws.initialWallThickness * np.ones(eom.nbrFields), offsets=np.zeros(eom.nbrFields))
+    idx = list(np.linspace(0, len(vws) - 1, a.ref_scan_points).astype(int))
+    t0 = time.perf_counter()
+    press = []
+    for i in idx:
+        out = eom.wallPressure(float(vws[i]), wp0, boltzmannResultsInput=None)
+        press.append(float(out[0]))
+    el = time.perf_counter() - t0
+    return {"metric": "vw scan pts/sec", "value": len(idx) / el, "unit": "points/s", "points": len(idx),
+            "seconds": el, "setup_seconds": setup, "point_indices": [int(i) for i in idx], "pressures": press,
+            "workload": f"{a.scan_model}: P={P} M={M} N={N}, EOM.wallPressure(vw_i, wallParams0, None), "
+                        f"{len(idx)} of the {a.scan_points} scan points, host cores {os.cpu_count()}"}
+
+
 def run_scan(a, world, rank, local):
-    """Second half of the BASELINE metric: wall-velocity scan points/s.  256 independent vw points of the
+    """Second half of the BASELINE metric: wall-velocity scan points/s, a point being what SURVEY.md section
+    8(d)(2) defines: one `EOM.wallPressure(vw_i, wallParams0, boltzmannResultsInput=None)` of the UNMODIFIED
+    reference wall solver (equationOfMotion.py:786-1131; ~4 Boltzmann solves + host loop) on the InertDoublet
+    driver (P=4, M=30, N=11, n=11600), 256 vw in [vMin, 0.53], strong scaling: ranks take points round-robin,
+    each rank with its own WallGoManager / EOM / Grid3Scales, Boltzmann solves on the rank's GPU through
+    wallgo_b200.dropin (vectoriseEOM=True), pressures + wall parameters + moments gathered by ONE all_gather.
+    Needs the reference copy under oracle/_ref; without it the Boltzmann-only sweep below is reported."""
+    import contextlib
+
+    import torch
+    import torch.distributed as dist
+
+    from oracle import ref_drivers as rd
+    if rd.reference_root() is None:
+        return run_scan_boltzmann_only(a, world, rank, local)
+    with contextlib.redirect_stdout(sys.stderr):
+        WallGo = rd.load_reference()
+        from wallgo_b200 import _lib, dropin, vwscan
+
+        P, M, N = SCAN_MODELS[a.scan_model]
+        cls = dropin.install(vectoriseEOM=True)
+        rd.patch_load_collisions(cls)      # shipped .hdf5 are Git-LFS pointers: relaxation-time tensor, both arms
+        t0 = time.perf_counter()
+        manager, settings, _ = rd.build_manager(a.scan_model, M, N)
+        setup = time.perf_counter() - t0
+        vws = scan_velocities(manager, a.scan_points)
+        workers = vwscan.defaultWorkers(world) if a.scan_workers < 0 else a.scan_workers
+        # warm-up: engines, buffers and CUDA graphs of every slot; forks nothing
+        vwscan.scanLocal(manager, settings, vws, [rank % len(vws)], workers=0)
+        lib = _lib.load()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0 = lib.wg_launch_count()
+        stats = {}
+        t0 = time.perf_counter()
+        table = vwscan.scanWallPressure(manager, settings, vws, workers=workers, stats=stats)
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        launches = lib.wg_launch_count() - l0
+    mine = len(range(rank, len(vws), world))
+    agg = torch.tensor([el, stats.get("host_s", 0.0), float(stats.get("solves", 0)), float(launches)],
+                       dtype=torch.float64, device=torch.device("cuda", local))
+    if world > 1:
+        mx = agg.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        el = float(mx[0].item())
+    hostTotal, solves, launches = float(agg[1].item()), int(agg[2].item()), int(agg[3].item())
+    nF = (table.shape[1] - 2 - 4 * P * (M - 1)) // 2
+    assert np.all(np.isfinite(table))
+    n = P * (M - 1) * (N - 1) ** 2
+    return {"metric": "vw scan pts/sec", "value": len(vws) / el, "unit": "points/s", "points": len(vws),
+            "seconds": el, "scaling": "strong", "setup_seconds_per_rank": setup,
+            "workload": f"{a.scan_model}: P={P} M={M} N={N} n={n}, vw in [{vws[0]:.3f}, {vws[-1]:.3f}], "
+                        "relaxation-time collision tensor",
+            "point": "EOM.wallPressure(vw_i, wallParams0, None) of the unmodified reference wall solver, Boltzmann "
+                     "solves on the GPU via wallgo_b200.dropin (vectoriseEOM); one all_gather of the result rows",
+            "host_workers_per_rank": int(workers), "points_per_rank": mine,
+            "boltzmann_solves": solves, "solves_per_point": solves / max(1, len(vws)),
+            "host_seconds_per_point": hostTotal / max(1, len(vws)),
+            "host_note": "wall time a point spends in the reference's host loop + waiting for its solves, summed "
+                         "over the host workers; the GPU time of one solve at this size is ~0.05 s",
+            "gpu_launches": launches,
+            "checksum": float(np.sum(table[:, 0])), "checksum_moments": float(np.sum(table[:, 2 + 2 * nF:])),
+            "pressure_first_last": [float(table[0, 0]), float(table[-1, 0])]}
+
+
+def run_scan_boltzmann_only(a, world, rank, local):
+    """Fallback when the reference copy is absent: Boltzmann-only sweep.  256 independent vw points of the
     cfg4-sized system (P=4, M=30, N=11, n=11600) sharded round-robin over the ranks (strong scaling), every
     point one full assemble+LU+moments through the public class with host buffers, one NCCL all_gather of
     the moment tables at the end.  A point here is ONE Boltzmann solve at that vw: the EOM pressure
@@ -436,7 +597,14 @@ def run_b200(a):
     assert np.all(np.isfinite(res.Deltas.Delta00.coefficients))
     eng = engines[0]
 
-    scan_line = run_scan(a, world, rank, local) if a.scan_points > 0 else None
+    scan_line = None
+    if a.scan_points > 0:
+        try:
+            scan_line = run_scan(a, world, rank, local)
+        except Exception as exc:   # the secondary metric must not take the headline line down with it
+            import traceback
+            traceback.print_exc()
+            scan_line = {"metric": "vw scan pts/sec", "error": repr(exc)[:300]}
     if rank == 0:
         hbm_peak, hbm_src = measured_peaks()
         lu_flops = 2.0 / 3.0 * float(n) ** 3
@@ -490,15 +658,60 @@ def run_b200(a):
             line["scan"] = scan_line
         if world == 1 and not a.no_cpu_baseline and 8.0 * n * n > 24e9:
             line["cpu_baseline"] = {"value": None, "unit": "solves/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": "skipped: the NumPy port needs several copies of the operator in host RAM"}
+                                    "sample": "skipped: the NumPy path needs several copies of the operator in host RAM"}
+        elif world == 1 and not a.no_cpu_baseline and reference_available():
+            # the reference itself on the host cores, and the SAME system through the CUDA path: parity block
+            try:
+                import contextlib
+                vmid = -0.3 - 0.4 * (W % 97) / 97.0
+                with contextlib.redirect_stdout(sys.stderr):
+                    t, rres, (rsolver, rgrid, rbg, rparts) = reference_one_solve(P, M, N, vmid, want_solver=True)
+                    from oracle import ref_drivers as rd
+                    from wallgo_b200 import dropin
+                    new = dropin.makeDropInClass()(rgrid, rsolver.basisM, rsolver.basisN, rsolver.derivatives,
+                                                   rsolver.collisionMultiplier, rsolver.truncationOption, device=local)
+                    new.updateParticleList(rparts)
+                    new.setBackground(rbg)
+                    new.setCollisionArray(rsolver.collisionArray)
+                    gres = new.getDeltas()
+                    Dr, Dg = rd.deltas_table(rres), rd.deltas_table(gres)
+                line["cpu_baseline"] = {
+                    "value": 1.0 / t["total_s"], "unit": "solves/s", "cores": os.cpu_count(), "kind": "reference",
+                    "sample": f"1 full solve of the same workload by the unmodified reference class (oracle/_ref): "
+                              f"buildLinearEquations {t['assemble_s']:.2f}s + np.linalg.solve (LAPACK dgesv) "
+                              f"{t['dgesv_s']:.2f}s + getDeltas(deltaF) {t['moments_s']:.2f}s, NumPy {np.__version__}, "
+                              f"BLAS {blas_info()}"}
+                line["parity"] = {
+                    "against": "the same system (reference grid / background / collision array objects) solved by the "
+                               "reference class on the host and by the CUDA path, full size",
+                    "max_rel_deltaF": float(np.max(np.abs(gres.deltaF - rres.deltaF)) / np.max(np.abs(rres.deltaF))),
+                    "max_rel_Deltas": float(max(np.max(np.abs(Dg[i] - Dr[i])) / np.max(np.abs(Dr[i])) for i in range(4))),
+                    "flags_equal": bool(tuple(gres.truncatedTail) == tuple(rres.truncatedTail)
+                                        and tuple(gres.spectralPeaks) == tuple(rres.spectralPeaks)),
+                    "truncatedTail": [bool(x) for x in gres.truncatedTail],
+                    "spectralPeaks": [int(x) for x in gres.spectralPeaks], "tolerance": 1e-10}
+                del new, rsolver
+            except MemoryError:
+                line["cpu_baseline"] = {"value": None, "unit": "solves/s", "cores": os.cpu_count(), "kind": "reference",
+                                        "sample": "skipped: operator does not fit host RAM"}
         elif world == 1 and not a.no_cpu_baseline:
             try:
-                t, _ = cpu_port_one_solve(grid, particles, coll, bgs[W])
+                t, ores = cpu_port_one_solve(grid, particles, coll, bgs[W])
+                solver.setBackground(bgs[W])
+                gres = solver.getDeltas()
+                Dg = np.stack([gres.Deltas.Delta00.coefficients, gres.Deltas.Delta02.coefficients,
+                               gres.Deltas.Delta20.coefficients, gres.Deltas.Delta11.coefficients])
                 line["cpu_baseline"] = {
                     "value": 1.0 / t["total_s"], "unit": "solves/s", "cores": os.cpu_count(), "kind": "port",
                     "sample": f"1 full solve of the same workload (assemble {t['assemble_s']:.2f}s + LAPACK dgesv "
                               f"{t['dgesv_s']:.2f}s + moments {t['moments_s']:.2f}s), NumPy {np.__version__}, "
                               f"BLAS {blas_info()}"}
+                line["parity"] = {
+                    "against": "the oracle port on the same system (oracle/_ref absent on this machine)",
+                    "max_rel_deltaF": float(np.max(np.abs(gres.deltaF - ores["deltaF"])) / np.max(np.abs(ores["deltaF"]))),
+                    "max_rel_Deltas": float(max(np.max(np.abs(Dg[i] - ores["Deltas"][i])) / np.max(np.abs(ores["Deltas"][i]))
+                                                for i in range(4))),
+                    "flags_equal": bool(tuple(gres.truncatedTail) == tuple(ores["truncatedTail"])), "tolerance": 1e-10}
             except MemoryError:
                 line["cpu_baseline"] = {"value": None, "unit": "solves/s", "cores": os.cpu_count(), "kind": "port",
                                         "sample": "skipped: operator does not fit host RAM"}
@@ -523,6 +736,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scan-points", type=int, default=256, help="vw-scan points of the secondary metric (0: skip)")
     ap.add_argument("--scan-workload", default="cfg4", choices=sorted(WORKLOADS))
+    ap.add_argument("--scan-model", default="idm", choices=sorted(SCAN_MODELS))
+    ap.add_argument("--scan-workers", type=int, default=-1, help="host processes per rank for the scan (-1: auto, 0: in-process)")
+    ap.add_argument("--ref-scan-points", type=int, default=2, help="scan points the reference arm times (0: skip)")
     ap.add_argument("--ref-budget-s", type=float, default=150.0)
     a = ap.parse_args()
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup

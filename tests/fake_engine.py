@@ -32,14 +32,49 @@ class _NP:
 
 
 class _FakeStream:
+    cuda_stream = 0
+
+    def __init__(self, device=None):
+        pass
+
     def synchronize(self):
         pass
 
 
+class _FakeEvent:
+    def record(self, stream=None):
+        pass
+
+    def query(self):
+        return True
+
+    def synchronize(self):
+        pass
+
+
+class _FakeStreamCtx:
+    def __init__(self, stream):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
 class _FakeCuda:
+    Stream = _FakeStream
+    Event = _FakeEvent
+    stream = _FakeStreamCtx
+
     @staticmethod
     def current_stream(dev=None):
         return _FakeStream()
+
+    @staticmethod
+    def mem_get_info(dev=None):
+        return (64 << 30, 128 << 30)
 
 
 class _FakeTorch:
@@ -68,6 +103,39 @@ class FakeEngine:
         self.launches = 0
         self.dev = None
         self.mats = [None] * 9
+        self.stream_ptr = None
+
+    # the slot pool (BoltzmannSolver.slotPool) reads results through these pinned-buffer stand-ins
+    @property
+    def spectra(self):
+        return _NP(self._spectra)
+
+    @property
+    def spectra_host(self):
+        return _NP(self._spectra.copy())
+
+    @property
+    def out(self):
+        return self.out_host
+
+    @property
+    def out_host(self):
+        dF, deltas, err = self._out
+        return _NP(np.concatenate([np.ravel(dF), np.ravel(deltas), np.ravel(err)]))
+
+    def tmunu_out(self, deltas, msqInterior, velocityMid):
+        d = np.asarray(deltas, dtype=float).reshape(4, self.P, self.M1)
+        msq = np.asarray(msqInterior, dtype=float).reshape(self.P, self.M1)
+        u0 = np.sqrt(1.0 / (1.0 - velocityMid**2))
+        u3 = u0 * velocityMid
+        ub0, ub3 = u3, u0
+        a1 = 3 * d[2] - d[1] - msq * d[0]
+        a2 = 3 * d[1] - d[2] + msq * d[0]
+        dof = self.dofs[:, None]
+        t30 = np.sum(dof * (a1 * u3 * u0 + a2 * ub3 * ub0 + 2 * d[3] * (u3 * ub0 + ub3 * u0)) / 2.0, axis=0)
+        t33 = np.sum(dof * ((a1 * u3 * u3 + a2 * ub3 * ub3 + 4 * d[3] * u3 * ub3) / 2.0
+                            - (msq * d[0] + d[1] - d[2]) / 2.0), axis=0)
+        return t30, t33
 
     def close(self):
         pass

@@ -41,6 +41,25 @@ def _run_pair(rd, name, M, N, log):
     origRef = rd.patch_load_collisions(refCls)
     cls = dropin.makeDropInClass()
     origNew = rd.patch_load_collisions(cls)
+    traces = {}
+
+    def traced(klass, key):
+        """record every getDeltas() of the wall solver: wall velocity, inputs checksum, outputs"""
+        orig = klass.getDeltas
+        traces[key] = []
+
+        def getDeltas(self, deltaF=None):
+            res = orig(self, deltaF)
+            if deltaF is None:
+                bg = self.background
+                traces[key].append((float(bg.velocityWall), float(np.sum(bg.temperatureProfile)),
+                                    rd.deltas_table(res).copy(), tuple(res.truncatedTail), tuple(res.spectralPeaks),
+                                    self.derivatives))
+            return res
+        klass.getDeltas = getDeltas
+        return orig
+
+    origGetRef, origGetNew = traced(refCls, "ref"), traced(cls, "new")
     try:
         mgr.BoltzmannSolver = refCls
         t0 = time.perf_counter()
@@ -55,6 +74,8 @@ def _run_pair(rd, name, M, N, log):
         launches = lib.wg_launch_count() - l0
     finally:
         mgr.BoltzmannSolver = saved
+        refCls.getDeltas = origGetRef
+        cls.getDeltas = origGetNew
         refCls.loadCollisions = origRef
         if origNew is None:
             del cls.loadCollisions
@@ -62,6 +83,16 @@ def _run_pair(rd, name, M, N, log):
             cls.loadCollisions = origNew
     log.append(f"{name} M={M} N={N}: reference {tRef:.1f}s, B200 drop-in {tNew:.1f}s, {launches} kernels; "
                f"vw ref {rRef.wallVelocity!r} new {rNew.wallVelocity!r}")
+    a, b = traces["ref"], traces["new"]
+    log.append(f"  getDeltas calls: reference {len(a)}, drop-in {len(b)}")
+    worst = 0.0
+    for k, (x, y) in enumerate(zip(a, b)):
+        dD = float(np.max(np.abs(x[2] - y[2])) / max(np.max(np.abs(x[2])), 1e-300))
+        dT = abs(x[1] - y[1]) / abs(x[1])
+        flag = "" if (x[3] == y[3] and x[4] == y[4]) else f"  TRUNCATION DIFFERS ref {x[3]} {x[4]} new {y[3]} {y[4]}"
+        if dD > 10 * worst or flag:
+            log.append(f"  call {k} ({x[5]}): vw {x[0]:.9f}/{y[0]:.9f} input dT {dT:.1e} Deltas rel diff {dD:.2e}{flag}")
+        worst = max(worst, dD)
     return rRef, rNew, launches
 
 

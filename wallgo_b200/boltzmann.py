@@ -36,6 +36,96 @@ class _Keep(list):
         self.dev = list(sizes)
 
 
+class _SlotPool:
+    """Slots of independent systems in flight on one GPU (see BoltzmannSolverB200Mixin.slotPool)."""
+
+    def __init__(self, solver, count):
+        import ctypes
+
+        self.sibs = solver._siblings(count)
+        self.torch = self.sibs[0]._getEngine().torch
+        for s_ in self.sibs:
+            eng = s_._getEngine()
+            if getattr(s_, "_stream", None) is None:
+                s_._stream = self.torch.cuda.Stream(device=eng.dev)
+            eng.stream_ptr = ctypes.c_void_p(s_._stream.cuda_stream)   # pinned while the pool is open
+        self.state = [None] * count      # per slot: (token, phase, event[, keep, peaks])
+
+    def close(self):
+        for s_ in self.sibs:
+            if s_._engine is not None:
+                s_._engine.stream_ptr = None
+
+    def freeSlots(self) -> int:
+        return sum(1 for st in self.state if st is None)
+
+    def busy(self) -> bool:
+        return any(st is not None for st in self.state)
+
+    def submit(self, token, background=None, raw=None) -> bool:
+        """Enqueue one system (a BoltzmannBackground, or raw = (T, v, msq, dxidchi, vw)) on a free slot.
+        Returns False when every slot is busy."""
+        for slot, st in enumerate(self.state):
+            if st is None:
+                break
+        else:
+            return False
+        s_ = self.sibs[slot]
+        torch = self.torch
+        with torch.cuda.stream(s_._stream):
+            if raw is None:
+                s_.setBackground(background)
+                eng = s_._solveOnDevice()
+            else:
+                eng = s_._solveRawOnDevice(*raw)
+            eng.spectra_async(eng.S)
+            eng.spectra_host.copy_(eng.spectra, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(s_._stream)
+        self.state[slot] = (token, 0, ev)
+        return True
+
+    def _advance(self, slot, finished):
+        token, phase = self.state[slot][0], self.state[slot][1]
+        s_ = self.sibs[slot]
+        eng = s_._engine
+        torch = self.torch
+        if phase == 0:
+            keep, peaks = s_._decideTruncation(eng.spectra_host.numpy().copy())
+            with torch.cuda.stream(s_._stream):
+                eng.moments_async(eng.S, keep.dev, s_.truncationOption.name != "NONE")
+                eng.out_host.copy_(eng.out, non_blocking=True)
+                ev2 = torch.cuda.Event()
+                ev2.record(s_._stream)
+            self.state[slot] = (token, 1, ev2, keep, peaks)
+            return
+        _, _, _, keep, peaks = self.state[slot]
+        if eng.info() != 0:
+            raise np.linalg.LinAlgError("Singular matrix")
+        h = eng.out_host.numpy()
+        pm = 4 * eng.P * eng.M1
+        dF = h[:eng.n].reshape(eng.P, eng.M1, eng.N1, eng.N1).copy()
+        deltas = h[eng.n:eng.n + pm].reshape(4, eng.P, eng.M1).copy()
+        err = h[eng.n + pm:].reshape(eng.P, 4).copy()
+        self.state[slot] = None
+        finished.append((token, (dF, deltas, err, keep, peaks) if self.rawResults else
+                         s_._wrapResults(dF, deltas, err, keep, peaks)))
+
+    rawResults = False   # True: poll() returns the (dF, deltas, err, keep, peaks) tuples instead of BoltzmannResults
+
+    def poll(self):
+        finished = []
+        for slot, st in enumerate(self.state):
+            if st is not None and st[2].query():
+                self._advance(slot, finished)
+        return finished
+
+    def waitOldest(self):
+        live = [(st[0] if isinstance(st[0], int) else k, k) for k, st in enumerate(self.state) if st is not None]
+        if live:
+            self.state[min(live)[1]][2].synchronize()
+
+
 class BoltzmannSolverB200Mixin:
     """Implementation shared by the standalone class below and the WallGo drop-in subclass."""
 
@@ -154,6 +244,18 @@ class BoltzmannSolverB200Mixin:
         msq = self._msq(bg.fieldProfiles)
         eng.upload_profiles(np.asarray(bg.temperatureProfile, dtype=np.float64),
                             np.asarray(bg.velocityProfile, dtype=np.float64), msq, dxidchi)
+
+    def _solveRawOnDevice(self, T, v, msq, dxidchi, vw):
+        """assemble + LU + solves from already evaluated profiles (boosted T, v on the M+1 nodes, m^2 of every
+        species there, dxi/dchi of the caller's own grid mapping): the form the scan server receives from its
+        host workers, whose grids differ per wall velocity (equationOfMotion.py:1457-1503)."""
+        eng = self._getEngine()
+        eng.upload_profiles(np.asarray(T, dtype=np.float64), np.asarray(v, dtype=np.float64),
+                            np.asarray(msq, dtype=np.float64), np.asarray(dxidchi, dtype=np.float64))
+        eng.assemble(float(vw), float(self.collisionMultiplier))
+        eng.factor()
+        eng.solve()
+        return eng
 
     def _solveOnDevice(self, fused: bool = False):
         """assemble + LU + triangular solves; leaves deltaF in eng.S (device).  fused=True uses wg_factor_solve
@@ -297,6 +399,16 @@ class BoltzmannSolverB200Mixin:
         t30, t33, pot, dv = eng.feedback(dmsq, float(bg.velocityMid))
         return dict(T30=t30, T33=t33, potentialOut=pot, dVout=dv)
 
+    def tmunuOut(self, offEquilDeltas, fields, velocityMid: float):
+        """(T30_out, T33_out) on all interior z nodes for an arbitrary BoltzmannDeltas (EOM.deltaToTmunu,
+        equationOfMotion.py:2021-2127, which the reference evaluates point by point): one wg_feedback launch.
+        `fields` are the M-1 interior field points the EOM hands to findPlasmaProfile."""
+        eng = self._getEngine()
+        d = offEquilDeltas
+        table = np.stack([np.asarray(d.Delta00.coefficients), np.asarray(d.Delta02.coefficients),
+                          np.asarray(d.Delta20.coefficients), np.asarray(d.Delta11.coefficients)])
+        return eng.tmunu_out(table, self._msq(fields), float(velocityMid))
+
     # ------------------------------------------------------------------ batches of independent systems
     def _siblings(self, count):
         """This solver plus (count-1) shallow clones, each with its own engine, operator buffer and CUDA
@@ -328,6 +440,26 @@ class BoltzmannSolverB200Mixin:
             c = max(1, min(c, int(0.6 * freeBytes) // perSlot))
         return c
 
+    def _autoSlotCount(self) -> int:
+        eng0 = self._getEngine()
+        if getattr(self, "_autoSlots", None) is None or self._autoSlots[0] != eng0.n:
+            free = eng0.torch.cuda.mem_get_info(eng0.dev)[0]      # ~30 ms: asked once per system size
+            have = sum(8 * eng0.n * eng0.n for s_ in (getattr(self, "_sibs", None) or [self])
+                       if s_._engine is not None and s_._engine.A is not None)
+            self._autoSlots = (eng0.n, self.autoConcurrency(eng0.n, free + have))
+        return self._autoSlots[1]
+
+    def slotPool(self, concurrency: int | None = None):
+        """Asynchronous form of getDeltas() for many independent systems: `concurrency` slots (None:
+        autoConcurrency), each with its own engine, operator buffer, CUDA stream and captured graphs.
+        submit() enqueues one system on a free slot without waiting; poll() advances the slots whose device
+        work has finished (host half of the truncation, moments, result download) and returns the
+        (token, BoltzmannResults) pairs that completed.  getDeltasBatch() and the wall-velocity scan server
+        (wallgo_b200.vwscan) are built on it."""
+        if concurrency is None or int(concurrency) <= 0:
+            concurrency = self._autoSlotCount()
+        return _SlotPool(self, max(1, int(concurrency)))
+
     def getDeltasBatch(self, backgrounds, concurrency: int | None = None):
         """getDeltas() for a list of independent backgrounds (wall-velocity scan points, parameter points),
         `concurrency` systems in flight on this GPU (None: autoConcurrency).  Each system is solved exactly
@@ -340,87 +472,33 @@ class BoltzmannSolverB200Mixin:
         if nItems == 0:
             return []
         if concurrency is None or int(concurrency) <= 0:
-            eng0 = self._getEngine()
-            if getattr(self, "_autoSlots", None) is None or self._autoSlots[0] != eng0.n:
-                free = eng0.torch.cuda.mem_get_info(eng0.dev)[0]      # ~30 ms: asked once per system size
-                have = sum(8 * eng0.n * eng0.n for s_ in (getattr(self, "_sibs", None) or [self])
-                           if s_._engine is not None and s_._engine.A is not None)
-                self._autoSlots = (eng0.n, self.autoConcurrency(eng0.n, free + have))
-            concurrency = self._autoSlots[1]
+            concurrency = self._autoSlotCount()
         C = max(1, min(int(concurrency), nItems))
-        sibs = self._siblings(C)
-        torch = sibs[0]._getEngine().torch
-        import ctypes
-        for s_ in sibs:
-            eng = s_._getEngine()
-            if getattr(s_, "_stream", None) is None:
-                s_._stream = torch.cuda.Stream(device=eng.dev)
-            eng.stream_ptr = ctypes.c_void_p(s_._stream.cuda_stream)   # pinned for the duration of the batch
+        pool = self.slotPool(C)
         results = [None] * nItems
-        n = sibs[0]._getEngine().n
+        n = self._getEngine().n
         stagger = (2.0 / 3.0) * float(n) ** 3 / 20e12 / C   # rough LU time / C
         nextItem = 0
-        state = [None] * C       # per slot: (item, phase, event, aux)
-
-        def start(slot):
-            nonlocal nextItem
-            if nextItem >= nItems:
-                state[slot] = None
-                return
-            it = nextItem
-            nextItem += 1
-            s_ = sibs[slot]
-            with torch.cuda.stream(s_._stream):
-                s_.setBackground(backgrounds[it])
-                eng = s_._solveOnDevice()
-                eng.spectra_async(eng.S)
-                eng.spectra_host.copy_(eng.spectra, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(s_._stream)
-            state[slot] = (it, 0, ev)
-
-        def advance(slot):
-            it, phase = state[slot][0], state[slot][1]
-            s_ = sibs[slot]
-            eng = s_._engine
-            if phase == 0:
-                keep, peaks = s_._decideTruncation(eng.spectra_host.numpy().copy())
-                with torch.cuda.stream(s_._stream):
-                    eng.moments_async(eng.S, keep.dev, s_.truncationOption.name != "NONE")
-                    eng.out_host.copy_(eng.out, non_blocking=True)
-                    ev2 = torch.cuda.Event()
-                    ev2.record(s_._stream)
-                state[slot] = (it, 1, ev2, keep, peaks)
-            else:
-                _, _, _, keep, peaks = state[slot]
-                if eng.info() != 0:
-                    raise np.linalg.LinAlgError("Singular matrix")
-                h = eng.out_host.numpy()
-                pm = 4 * eng.P * eng.M1
-                dF = h[:eng.n].reshape(eng.P, eng.M1, eng.N1, eng.N1).copy()
-                deltas = h[eng.n:eng.n + pm].reshape(4, eng.P, eng.M1).copy()
-                err = h[eng.n + pm:].reshape(eng.P, 4).copy()
-                results[it] = s_._wrapResults(dF, deltas, err, keep, peaks)
-                start(slot)
-
         try:
-            for slot in range(C):
-                if slot > 0 and stagger > 1e-3:
+            while nextItem < min(C, nItems):
+                if nextItem > 0 and stagger > 1e-3:
                     time.sleep(stagger)
-                start(slot)
-            while any(st is not None for st in state):
-                progressed = False
-                for slot in range(C):
-                    if state[slot] is not None and state[slot][2].query():
-                        advance(slot)
-                        progressed = True
-                if not progressed:
-                    oldest = min((st[0], k) for k, st in enumerate(state) if st is not None)[1]
-                    state[oldest][2].synchronize()
+                pool.submit(nextItem, background=backgrounds[nextItem])
+                nextItem += 1
+            done = 0
+            while done < nItems:
+                finished = pool.poll()
+                if not finished:
+                    pool.waitOldest()
+                    continue
+                for token, res in finished:
+                    results[token] = res
+                    done += 1
+                    if nextItem < nItems:
+                        pool.submit(nextItem, background=backgrounds[nextItem])
+                        nextItem += 1
         finally:
-            for s_ in sibs:
-                if s_._engine is not None:
-                    s_._engine.stream_ptr = None
+            pool.close()
         return results
 
     def _wrapResults(self, dF, deltas, err, keep, peaks):

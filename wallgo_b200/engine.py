@@ -75,6 +75,15 @@ class BoltzmannEngine:
             return self.stream_ptr
         return C.c_void_p(self.torch.cuda.current_stream(self.dev).cuda_stream)
 
+    def _onEngineStream(self):
+        """Context in which torch copies / synchronisation use the same stream as the kernels: the pinned
+        slot stream while a batch runs (stream_ptr), torch's current stream otherwise."""
+        import contextlib
+
+        if self.stream_ptr is None:
+            return contextlib.nullcontext()
+        return self.torch.cuda.stream(self.torch.cuda.ExternalStream(int(self.stream_ptr.value), device=self.dev))
+
     def _ensure_A(self):
         if self.A is None:
             self.A = self.torch.empty((self.n, self.n), dtype=self.torch.float64, device=self.dev)
@@ -107,11 +116,38 @@ class BoltzmannEngine:
         if F:
             d = torch.from_numpy(np.ascontiguousarray(dmsq, dtype=np.float64).reshape(self.P, self.M1, F)).to(self.dev)
             dptr = d.data_ptr()
-        check(self.lib.wg_feedback(self.h, self.out[n:].data_ptr(), self.prof.data_ptr(), dptr, F,
-                                   float(velocityMid), out.data_ptr(), self._stream()), "wg_feedback")
-        h = out.cpu().numpy()
+        with self._onEngineStream():
+            check(self.lib.wg_feedback(self.h, self.out[n:].data_ptr(), self.prof.data_ptr(), dptr, F,
+                                       float(velocityMid), out.data_ptr(), self._stream()), "wg_feedback")
+            h = out.cpu().numpy()
         M1 = self.M1
         return h[:M1].copy(), h[M1:2 * M1].copy(), h[2 * M1:3 * M1].copy(), h[3 * M1:].reshape(M1, F).copy()
+
+    def tmunu_out(self, deltas, msqInterior, velocityMid: float):
+        """T30_out, T33_out [M-1] (EOM.deltaToTmunu for all interior z at once) from HOST moment tables: the wall
+        EOM mixes the moments of successive solves on the host (under-relaxation, equationOfMotion.py:1352-1355)
+        before it asks for the plasma profile, so the table is uploaded (4 P (M-1) doubles), wg_feedback runs
+        once and 2 (M-1) doubles come back."""
+        torch = self.torch
+        pm, L, M1 = 4 * self.P * self.M1, self.M + 1, self.M1
+        if getattr(self, "_fb_host", None) is None:
+            self._fb_host = torch.zeros(pm + self.nprof, dtype=torch.float64).pin_memory()
+            self._fb_dev = torch.empty(pm + self.nprof, dtype=torch.float64, device=self.dev)
+            self._fb_out = torch.empty(3 * M1, dtype=torch.float64, device=self.dev)
+            self._fb_out_host = torch.empty(3 * M1, dtype=torch.float64).pin_memory()
+        h = self._fb_host.numpy()
+        h[:pm] = np.asarray(deltas, dtype=np.float64).reshape(-1)
+        msq = np.asarray(msqInterior, dtype=np.float64).reshape(self.P, M1)
+        for a in range(self.P):
+            h[pm + (2 + a) * L + 1: pm + (2 + a) * L + 1 + M1] = msq[a]
+        with self._onEngineStream():
+            self._fb_dev.copy_(self._fb_host, non_blocking=True)
+            check(self.lib.wg_feedback(self.h, self._fb_dev.data_ptr(), self._fb_dev[pm:].data_ptr(), 0, 0,
+                                       float(velocityMid), self._fb_out.data_ptr(), self._stream()), "wg_feedback")
+            self._fb_out_host.copy_(self._fb_out, non_blocking=True)
+            torch.cuda.current_stream(self.dev).synchronize()
+        o = self._fb_out_host.numpy()
+        return o[:M1].copy(), o[M1:2 * M1].copy()
 
     def build_basis(self):
         check(self.lib.wg_build_basis(self.h), "wg_build_basis")
@@ -152,7 +188,8 @@ class BoltzmannEngine:
         ph[L:2 * L] = v
         ph[2 * L:(2 + self.P) * L] = np.asarray(msq, dtype=np.float64).reshape(-1)
         ph[(2 + self.P) * L:] = dxidchi
-        self.prof.copy_(self.prof_host, non_blocking=True)
+        with self._onEngineStream():
+            self.prof.copy_(self.prof_host, non_blocking=True)
 
     def assemble(self, vw: float, collisionMultiplier: float = 1.0, parts: int = 3, A=None):
         A = self._ensure_A() if A is None else A
@@ -188,8 +225,9 @@ class BoltzmannEngine:
         check(self.lib.wg_spectra(self.h, dF.data_ptr(), self.spectra.data_ptr(), self._stream()), "wg_spectra")
 
     def spectra_to_host(self):
-        self.spectra_host.copy_(self.spectra, non_blocking=True)
-        self.torch.cuda.current_stream(self.dev).synchronize()
+        with self._onEngineStream():
+            self.spectra_host.copy_(self.spectra, non_blocking=True)
+            self.torch.cuda.current_stream(self.dev).synchronize()
         return self.spectra_host.numpy().copy()
 
     def moments_async(self, dF, keep, roundtrip: bool):
@@ -201,8 +239,9 @@ class BoltzmannEngine:
 
     def results_to_host(self):
         """One device -> host copy: (deltaF (P,M-1,N-1,N-1), Deltas (4,P,M-1), err (P,4))."""
-        self.out_host.copy_(self.out, non_blocking=True)
-        self.torch.cuda.current_stream(self.dev).synchronize()
+        with self._onEngineStream():
+            self.out_host.copy_(self.out, non_blocking=True)
+            self.torch.cuda.current_stream(self.dev).synchronize()
         h = self.out_host.numpy()
         n, pm = self.n, 4 * self.P * self.M1
         dF = h[:n].reshape(self.P, self.M1, self.N1, self.N1).copy()

@@ -204,15 +204,46 @@ class _ProfileProblem:
         return (-enthalpy + np.sqrt(4 * self.s1**2 + enthalpy**2)) / (2 * self.s1)
 
 
+def deltaToTmunuVec(particles, fields, velocityMid, offEquilDeltas):
+    """EOM.deltaToTmunu (equationOfMotion.py:2021-2127) on all grid points at once, host NumPy: returns
+    (T30_out, T33_out) with one entry per point of `fields`.  Same arithmetic order as the scalar routine."""
+    u0 = np.sqrt(1.0 / (1.0 - velocityMid * velocityMid))
+    u3 = u0 * velocityMid
+    ub0, ub3 = u3, u0
+    npts = np.asarray(offEquilDeltas.Delta00.coefficients).shape[1]
+    t30 = np.zeros(npts)
+    t33 = np.zeros(npts)
+    for i, particle in enumerate(particles):
+        d00 = np.asarray(offEquilDeltas.Delta00.coefficients)[i]
+        d02 = np.asarray(offEquilDeltas.Delta02.coefficients)[i]
+        d20 = np.asarray(offEquilDeltas.Delta20.coefficients)[i]
+        d11 = np.asarray(offEquilDeltas.Delta11.coefficients)[i]
+        msq = np.asarray(particle.msqVacuum(fields), dtype=np.float64).reshape(npts)
+        a1 = 3 * d20 - d02 - msq * d00
+        a2 = 3 * d02 - d20 + msq * d00
+        t30 = t30 + particle.totalDOFs * (a1 * u3 * u0 + a2 * ub3 * ub0 + 2 * d11 * (u3 * ub0 + ub3 * u0)) / 2.0
+        t33 = t33 + particle.totalDOFs * ((a1 * u3 * u3 + a2 * ub3 * ub3 + 4 * d11 * u3 * ub3) / 2.0
+                                          - (msq * d00 + d02 - d20) / 2.0)
+    return t30, t33
+
+
+def _tmunuOut(eom, fields, velocityMid, offEquilDeltas):
+    """Out-of-equilibrium T30, T33 for every interior z: the device kernel (wg_feedback, one launch) when the
+    EOM's Boltzmann solver owns a GPU engine, the host vector form in the scan's host workers."""
+    solver = getattr(eom, "boltzmannSolver", None)
+    if solver is not None and getattr(solver, "_engine", None) is not None and hasattr(solver, "tmunuOut"):
+        return solver.tmunuOut(offEquilDeltas, fields, velocityMid)
+    return deltaToTmunuVec(eom.particles, fields, velocityMid, offEquilDeltas)
+
+
 def findPlasmaProfile(eom, c1, c2, velocityMid, fields, dPhidz, offEquilDeltas, Tplus, Tminus):
     """Vector form of EOM.findPlasmaProfile (equationOfMotion.py:1764-1941); same arguments after `eom`,
     same return value (temperatureProfile, velocityProfile) and the same success flags on `eom`."""
     npts = len(eom.grid.xiValues)
-    # out-of-equilibrium part of T^{30}, T^{33}: the reference's own per-point routine (cheap, exact)
-    tout = np.array([eom.deltaToTmunu(i, fields.getFieldPoint(i), velocityMid, offEquilDeltas) for i in range(npts)],
-                    dtype=np.float64).reshape(npts, 2)
-    s1 = c1 - tout[:, 0]
-    s2 = c2 - tout[:, 1]
+    # out-of-equilibrium part of T^{30}, T^{33} on all points at once (the reference: M-1 calls of deltaToTmunu)
+    t30, t33 = _tmunuOut(eom, fields, velocityMid, offEquilDeltas)
+    s1 = c1 - t30
+    s2 = c2 - t33
     pb = _ProfileProblem(eom, fields, dPhidz, s1, s2)
     upper = 2 * max(Tplus, Tminus)
     tMin, _, _ = minimizeBoundedVec(pb.lhs, np.zeros(npts), np.full(npts, upper))

@@ -1,0 +1,267 @@
+"""Wall-velocity scan: `EOM.wallPressure(vw_i, wallParams0, boltzmannResultsInput=None)` for many vw
+(/root/reference/src/WallGo/equationOfMotion.py:786-1131), the second half of the BASELINE metric.
+
+A scan point is the reference's own, unmodified pressure iteration: ~4 Boltzmann solves interleaved with
+host work that only the reference's control plane can do (hydrodynamic matching, the per-z temperature
+root finds that call the user's effective potential, the Nelder-Mead minimisation of the action).  After
+the Boltzmann solve has moved to the GPU that host work is >90 % of a point, so one Python process per GPU
+cannot keep a B200 busy.  Layout per rank (one process per GPU, as everywhere in this package):
+
+  * the rank process owns the GPU and acts as a SOLVE SERVER: a slot pool of independent systems in flight
+    (BoltzmannSolver.slotPool: one engine, operator buffer, stream and captured CUDA graphs per slot);
+  * `workers` forked host processes each run the unmodified `EOM.wallPressure` on their own
+    EOM / Grid3Scales (the grid is re-mapped per vw, equationOfMotion.py:1457-1503) with a
+    `WallGo.BoltzmannSolver` subclass whose getDeltas() ships the O(P*M) boosted background numbers to the
+    server over a pipe and receives deltaF, the four moments and the truncation outputs back (127 KB);
+  * points are handed out dynamically (the iteration count varies per vw); ranks take points round-robin
+    and one all_gather of the per-point rows ends the scan (wallgo_b200.scan.gatherPoints).
+
+Every point starts from the same (wallParams0, deltaF = 0), and the device path is batch-invariant, so the
+table is identical for any number of workers and GPUs (checked by a checksum in bench.py and by the tests).
+`workers=0` runs the points sequentially in the rank process through the plain drop-in class.
+
+Needs WallGo (the reference) importable, like wallgo_b200.dropin.
+"""
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+
+
+def rowWidth(nFields: int, P: int, M: int) -> int:
+    """[pressure, widths (nFields), offsets (nFields), iterations, Delta00|02|20|11 (4*P*(M-1))]"""
+    return 2 + 2 * nFields + 4 * P * (M - 1)
+
+
+def _row(out, nSolves):
+    pressure, wallParams, res = out[0], out[1], out[2]
+    d = res.Deltas
+    return np.concatenate([[float(pressure)], np.ravel(wallParams.widths), np.ravel(wallParams.offsets),
+                           [float(nSolves)], d.Delta00.coefficients.ravel(), d.Delta02.coefficients.ravel(),
+                           d.Delta20.coefficients.ravel(), d.Delta11.coefficients.ravel()])
+
+
+def _initialWallParams(WallGo, ws):
+    eom = ws.eom
+    eom.pressAbsErrTol = 1e-8          # EOM.solveWall sets this before its first wallPressure (:474)
+    return WallGo.WallParams(widths=ws.initialWallThickness * np.ones(eom.nbrFields),
+                             offsets=np.zeros(eom.nbrFields))
+
+
+def makeRemoteClass(conn):
+    """Subclass of WallGo.BoltzmannSolver for the host workers: setBackground as the reference, getDeltas()
+    by remote procedure call to the rank's solve server."""
+    import WallGo  # pylint: disable=import-outside-toplevel
+    import WallGo.results  # noqa: F401  pylint: disable=import-outside-toplevel
+    from WallGo.boltzmann import BoltzmannSolver as _RefSolver  # pylint: disable=import-outside-toplevel
+
+    from .boltzmann import BoltzmannSolverB200Mixin
+
+    class _WallGoTypes:
+        Polynomial = WallGo.Polynomial
+        BoltzmannDeltas = WallGo.BoltzmannDeltas
+        BoltzmannResults = WallGo.results.BoltzmannResults
+
+    class RemoteBoltzmannSolver(BoltzmannSolverB200Mixin, _RefSolver):
+        _types = _WallGoTypes
+        nSolves = 0
+
+        def __init__(self, grid, basisM="Cardinal", basisN="Chebyshev", derivatives="Spectral",
+                     collisionMultiplier=1.0, truncationOption=None, device=None):
+            from WallGo.boltzmann import ETruncationOption  # pylint: disable=import-outside-toplevel
+            self._initB200(grid, basisM, basisN, derivatives, collisionMultiplier,
+                           ETruncationOption.AUTO if truncationOption is None else truncationOption, device)
+
+        def loadCollisions(self, directoryPath):     # the server holds the tensor
+            pass
+
+        def _getEngine(self):
+            raise RuntimeError("host worker: the GPU belongs to the rank's solve server")
+
+        def getDeltas(self, deltaF=None):
+            assert deltaF is None, "host workers only forward full solves"
+            bg = self.background
+            dxidchi, _, _ = self.grid.getCompactificationDerivatives()
+            conn.send(("solve", np.asarray(bg.temperatureProfile, dtype=np.float64),
+                       np.asarray(bg.velocityProfile, dtype=np.float64), self._msq(bg.fieldProfiles),
+                       np.asarray(dxidchi, dtype=np.float64), float(bg.velocityWall)))
+            kind, payload = conn.recv()
+            if kind == "error":
+                raise np.linalg.LinAlgError(payload)
+            dF, deltas, err, keepList, peaks = payload
+            type(self).nSolves += 1
+            return self._wrapResults(dF, deltas, err, keepList, peaks)
+
+    return RemoteBoltzmannSolver
+
+
+def _workerMain(conn, manager, settings):
+    """Host worker: unmodified EOM.wallPressure, Boltzmann solves forwarded to the server."""
+    import WallGo  # pylint: disable=import-outside-toplevel
+    import WallGo.manager as _manager  # pylint: disable=import-outside-toplevel
+
+    try:
+        try:      # one core per host worker: the EOM's NumPy calls are small, BLAS threads would only collide
+            from threadpoolctl import threadpool_limits  # pylint: disable=import-outside-toplevel
+            threadpool_limits(limits=1)
+        except Exception:  # pylint: disable=broad-except
+            pass
+        cls = makeRemoteClass(conn)
+        _manager.BoltzmannSolver = cls
+        ws = manager.setupWallSolver(settings)
+        wp0 = _initialWallParams(WallGo, ws)
+        conn.send(("ready",))
+        while True:
+            msg = conn.recv()
+            if msg[0] == "stop":
+                break
+            _, idx, vw = msg
+            before = cls.nSolves
+            t0 = time.perf_counter()
+            out = ws.eom.wallPressure(float(vw), wp0, boltzmannResultsInput=None)
+            conn.send(("done", idx, _row(out, cls.nSolves - before), time.perf_counter() - t0))
+    except BaseException as exc:  # pylint: disable=broad-except
+        import traceback
+        try:
+            conn.send(("crash", traceback.format_exc()))
+        except Exception:  # pylint: disable=broad-except
+            pass
+        raise exc
+    finally:
+        conn.close()
+
+
+def defaultWorkers(worldSize: int = 1) -> int:
+    """Host processes per rank: the node's cores are divided evenly among its GPUs (so the per-GPU host budget
+    does not depend on how many ranks a run uses), one core stays with the rank process, at most 8."""
+    try:
+        import torch  # pylint: disable=import-outside-toplevel
+        gpus = max(1, torch.cuda.device_count())
+    except Exception:  # pylint: disable=broad-except
+        gpus = 1
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return max(1, min(8, cores // max(gpus, worldSize) - 1))
+
+
+def scanLocal(manager, settings, vws, indices, workers=None, concurrency=None, stats=None):
+    """The points `indices` of `vws` on this process' GPU.  Returns [len(indices), width] rows in the order
+    of `indices`.  `manager` is a WallGoManager after setupThermodynamicsHydrodynamics with
+    wallgo_b200.dropin installed (dropin.install()); `settings` its WallSolverSettings."""
+    import multiprocessing as mp
+    from multiprocessing.connection import wait as mpWait
+
+    import WallGo  # pylint: disable=import-outside-toplevel
+
+    indices = list(indices)
+    stats = {} if stats is None else stats
+    ws = manager.setupWallSolver(settings)          # the server's solver: holds the collision tensor
+    solver = ws.boltzmannSolver
+    nF, P, M = ws.eom.nbrFields, len(solver.offEqParticles), solver.grid.M
+    rows = np.zeros((len(indices), rowWidth(nF, P, M)))
+    if workers is None:
+        workers = defaultWorkers()
+    workers = min(int(workers), len(indices))
+    stats.update(workers=workers, host_s=0.0, solves=0)
+    if not indices:
+        return rows
+    if workers <= 0:
+        wp0 = _initialWallParams(WallGo, ws)
+        for k, i in enumerate(indices):
+            t0 = time.perf_counter()
+            calls = [0]
+            orig = solver.getDeltas
+
+            def counted(deltaF=None, _o=orig, _c=calls):
+                _c[0] += 1
+                return _o(deltaF)
+
+            solver.getDeltas = counted
+            try:
+                out = ws.eom.wallPressure(float(vws[i]), wp0, boltzmannResultsInput=None)
+            finally:
+                del solver.getDeltas
+            rows[k] = _row(out, calls[0])
+            stats["host_s"] += time.perf_counter() - t0
+            stats["solves"] += calls[0]
+        return rows
+
+    # ---- solve server + forked host workers
+    ctx = mp.get_context("fork")
+    conns, procs = [], []
+    for _ in range(workers):
+        parent, child = ctx.Pipe(duplex=True)
+        pr = ctx.Process(target=_workerMain, args=(child, manager, settings), daemon=True)
+        pr.start()
+        child.close()
+        conns.append(parent)
+        procs.append(pr)
+    pool = solver.slotPool(concurrency)
+    pool.rawResults = True
+    todo = list(enumerate(indices))[::-1]
+    waiting = []                      # solve requests that found no free slot: (conn, raw)
+    done = 0
+    tServerBusy = 0.0
+    try:
+        live = set(conns)
+        while done < len(indices):
+            ready = mpWait(list(live), timeout=0.0004 if (pool.busy() or waiting) else 0.05)
+            for c in ready:
+                msg = c.recv()
+                kind = msg[0]
+                if kind == "solve":
+                    if not pool.submit(c, raw=msg[1:]):
+                        waiting.append((c, msg[1:]))
+                elif kind in ("ready", "done"):
+                    if kind == "done":
+                        _, k, row, secs = msg
+                        rows[k] = row
+                        stats["host_s"] += secs
+                        stats["solves"] += int(row[1 + 2 * nF])
+                        done += 1
+                    if todo:
+                        k, i = todo.pop()
+                        c.send(("point", k, float(vws[i])))
+                    else:
+                        c.send(("stop",))
+                        live.discard(c)
+                elif kind == "crash":
+                    raise RuntimeError("scan worker failed:\n" + msg[1])
+            t0 = time.perf_counter()
+            for c, payload in pool.poll():
+                dF, deltas, err, keep, peaks = payload
+                c.send(("result", (dF, deltas, err, list(keep), peaks)))
+            while waiting and pool.freeSlots():
+                c, raw = waiting.pop(0)
+                pool.submit(c, raw=raw)
+            tServerBusy += time.perf_counter() - t0
+    finally:
+        pool.close()
+        for c in conns:
+            try:
+                c.close()
+            except Exception:  # pylint: disable=broad-except
+                pass
+        for pr in procs:
+            pr.join(timeout=5)
+            if pr.is_alive():
+                pr.terminate()
+    stats["server_s"] = tServerBusy
+    return rows
+
+
+def scanWallPressure(manager, settings, vws, workers=None, concurrency=None, stats=None):
+    """All points of `vws`, sharded round-robin over the ranks of the default process group (one per GPU),
+    gathered with ONE all_gather.  Every rank returns the full [len(vws), width] table."""
+    import torch.distributed as dist  # pylint: disable=import-outside-toplevel
+
+    from . import scan  # pylint: disable=import-outside-toplevel
+
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    mine = scan.shardPoints(len(vws), rank, world)
+    if workers is None:
+        workers = defaultWorkers(world)
+    rows = scanLocal(manager, settings, vws, mine, workers=workers, concurrency=concurrency, stats=stats)
+    return scan.gatherPoints(rows, len(vws), rows.shape[1])
