@@ -17,7 +17,8 @@
  *   - all arrays are C-ordered float64.  n = P*(M-1)*(N-1)^2, q = (N-1)^2.
  *     row r = ((a*(M-1)+alpha)*(N-1)+beta)*(N-1)+gamma, col c = ((b*(M-1)+i)*(N-1)+j)*(N-1)+k
  *     (boltzmann.py:813-817, :286-292).
- *   - handles are not thread-safe; one solver per process per GPU (the reference is single-threaded).
+ *   - handles are not thread-safe (the reference is single-threaded); any number of solvers per process and
+ *     per GPU, each used by one host thread at a time.
  *   - there is no CPU path: every call fails with WG_ERR_CUDA if no sm_100 device is usable.
  */
 #ifndef WALLGO_B200_H
@@ -40,7 +41,10 @@ int wg_version(void);
 const char* wg_last_error(void);
 /* number of CUDA kernels this library has launched so far in this process (graph replays included) */
 long long wg_launch_count(void);
-/* nb: top-level LU panel width (multiple of 16, 32..256); use_graph: replay the factorisation as a CUDA graph */
+/* Scheduling knobs of the LU.  The four setters below change the process-wide DEFAULTS: a solver adopts them the
+ * next time it factors (its captured CUDA graphs are re-captured), unless it has been tuned individually with
+ * wg_solver_set_tuning, which touches that solver only.
+ * nb: top-level LU panel width (multiple of 16, 32..256); use_graph: replay the factorisation as a CUDA graph */
 int wg_set_tuning(int nb, int use_graph);
 /* on: factor panel k+1 on a high-priority stream while the trailing update of panel k runs (default 1) */
 int wg_set_lookahead(int on);
@@ -54,7 +58,12 @@ int wg_set_bulk_priority_rest(int rest);
  * scheduling: results are bit-identical for every value. */
 int wg_set_bulk_split(int percent);
 
-/* ---- lifecycle : BoltzmannSolver.__init__ + updateParticleList (boltzmann.py:52-139) */
+/* The same knobs for ONE solver (negative value: keep); later changes of the defaults no longer affect it. */
+int wg_solver_set_tuning(wg_solver* s, int nb, int use_graph, int lookahead, int split_percent, int bulk_hi_rest);
+
+/* ---- lifecycle : BoltzmannSolver.__init__ + updateParticleList (boltzmann.py:52-139).  Every entry point
+ * makes the solver's device current for the duration of the call and restores the caller's device, so solvers
+ * on different GPUs can coexist in one process (one host thread per solver at a time). */
 int wg_create(int P, int M, int N, int device, wg_solver** out);
 int wg_destroy(wg_solver* s);
 int wg_dims(const wg_solver* s, int* n, int* q);
@@ -83,6 +92,14 @@ int wg_set_transforms(wg_solver* s, const double* const mats[9]);
 /* Collision tensor C[a,beta,gamma,b,j,k] in the solver's momentum basis, P^2 q^2 doubles
  * (BoltzmannSolver.setCollisionArray, boltzmann.py:125-129).  on_device: pointer is device memory. */
 int wg_set_collision(wg_solver* s, const double* C, int on_device);
+
+/* Collision-file ingest, N_f -> N down-interpolation (CollisionArray.interpolateCollisionArray,
+ * collisionArray.py:391-478) on the device.  src: tensor read from the files, [P][NF-1][NF-1][P][NF-1][NF-1],
+ * Chebyshev basis in the polynomial axes; Lz, Lp [(NT-1) x (NF-1)]: Lagrange cardinals of the source grid's
+ * rho_z / rho_par nodes evaluated on the target grid's nodes; out [P][NT-1][NT-1][P][NT-1][NT-1] (Chebyshev),
+ * laid out as the reference lays it out.  All four are HOST pointers (once per run). */
+int wg_interpolate_collision(int device, int P, int NF, int NT, const double* Lz, const double* Lp,
+                             const double* src, double* out);
 
 /* ---- per solve (device pointers, stream ordered)
  * profiles_dev = [ T(M+1) | v(M+1) plasma frame | msq(P x (M+1)) | dxi/dchi(M-1) ]
@@ -116,7 +133,9 @@ int wg_info(wg_solver* s, void* stream, int* info_host);
 /* checkSpectralConvergence, first half (boltzmann.py:376-397): Chebyshev coefficients (kept inside the
  * solver) and spectra_dev[(M-1)+2(N-1)] = sum|c| along (chi | pz | pp). */
 int wg_spectra(wg_solver* s, const double* deltaF_dev, double* spectra_dev, void* stream);
-/* second half + estimateTruncationError + getDeltas quadrature (boltzmann.py:296-351, 431-491, 182-238):
+/* second half + estimateTruncationError + getDeltas quadrature (boltzmann.py:296-351, 431-491, 182-238).
+ * Consumes the Chebyshev coefficients the preceding wg_spectra(deltaF_dev) left inside the solver: without that
+ * call on the same deltaF_dev (or after another wg_moments) it returns WG_ERR_STATE.
  * keep* = number of coefficients kept per axis (0 zeroes the axis); roundtrip = 0 returns the input deltaF unchanged
  * (ETruncationOption.NONE).  Outputs: deltaF_out_dev[n], deltas_dev[4*P*(M-1)] (Delta00,02,20,11),
  * err_dev[4*P] (sum|c| kept, and on the last kept chi/pz/pp slice, per species). */
@@ -135,7 +154,8 @@ int wg_feedback(wg_solver* s, const double* deltas_dev, const double* profiles_d
                 int nFields, double velocityMid, double* out_dev, void* stream);
 /* y = (collision part of the last assembled operator) * x   (boltzmann.py:541-545) */
 int wg_collision_apply(wg_solver* s, const double* x_dev, double* y_dev, void* stream);
-/* in-place basis change of a (P, M-1, N-1, N-1) array with the matrices of wg_set_transforms */
+/* basis change of a (P, M-1, N-1, N-1) array with the matrices of wg_set_transforms (stage 0..2);
+ * out-of-place: in_dev and out_dev must differ */
 int wg_change_basis(wg_solver* s, int stage, const double* in_dev, double* out_dev, void* stream);
 
 /* Live timing of the dominant kernel (trailing-update GEMM of wg_factor) with CUDA events on the

@@ -363,3 +363,38 @@ def test_truncation_on_grids_with_fewer_than_three_coefficients(M, N, option):
     ref_c = bo.to_chebyshev(ref_dF, pb.tab) if option != "NONE" else bo.to_chebyshev(dF, pb.tab)
     if option != "NONE":
         assert np.max(np.abs(cc - ref_c)) <= 1e-12 * max(1.0, np.max(np.abs(ref_c)))
+
+
+def test_collision_directory_ingest_and_errors(tmp_path):
+    """CollisionArray.newFromDirectory / BoltzmannSolver.loadCollisions (boltzmann.py:822-844,
+    collisionArray.py:179-354): one file per ordered pair, CollisionLoadError for a missing file, for a grid
+    larger than the files and for a size mismatch without interpolation."""
+    import wallgo_b200 as wb
+
+    g = load_golden("interp_P2_N7_to_N5")
+    P, M, Nf = int(g["P"]), int(g["M"]), int(g["Nf"])
+    parts = [wb.Particle(f"p{a}", a, None, None, "Fermion", 1) for a in range(P)]
+    for a in range(P):
+        for b in range(P):
+            if (a + b) % 2:
+                np.save(tmp_path / f"collisions_p{a}_p{b}.npy", g["source"][a, :, :, b])
+            else:
+                np.savez(tmp_path / f"collisions_p{a}_p{b}.npz", **{"data": g["source"][a, :, :, b], "Basis Size": Nf,
+                                                                     "Basis Type": "Chebyshev"})
+    grid = wb.Grid(M, Nf, 0.05, 100.0)
+    ca = wb.CollisionArray.newFromDirectory(tmp_path, grid, "Chebyshev", parts)
+    assert np.array_equal(ca[...], g["source"]) and ca.getBasisType() == "Chebyshev"
+    solver = wb.BoltzmannSolver(grid)
+    solver.updateParticleList(parts)
+    solver.loadCollisions(tmp_path)
+    assert np.array_equal(solver.collisionArray[...], g["source"])
+    with pytest.raises(wb.CollisionLoadError):
+        wb.CollisionArray.newFromDirectory(tmp_path, wb.Grid(M, Nf + 2, 0.05, 100.0), "Chebyshev", parts)
+    with pytest.raises(wb.CollisionLoadError):
+        wb.CollisionArray.newFromDirectory(tmp_path, wb.Grid(M, Nf - 2, 0.05, 100.0), "Chebyshev", parts, bInterpolate=False)
+    (tmp_path / "collisions_p1_p0.npy").unlink()
+    with pytest.raises(wb.CollisionLoadError):
+        solver.loadCollisions(tmp_path)
+    (tmp_path / "collisions_p1_p0.hdf5").write_text("version https://git-lfs.github.com/spec/v1\n")   # an LFS pointer
+    with pytest.raises(wb.CollisionLoadError):
+        solver.loadCollisions(tmp_path)

@@ -373,3 +373,68 @@ def test_two_solvers_interleaved(cuda_device):
         assert np.array_equal(ra.deltaF, alone_a[i].deltaF) and np.array_equal(rb.deltaF, alone_b[i].deltaF)
         assert np.array_equal(ra.Deltas.Delta20.coefficients, alone_a[i].Deltas.Delta20.coefficients)
         assert np.array_equal(rb.Deltas.Delta11.coefficients, alone_b[i].Deltas.Delta11.coefficients)
+
+
+@pytest.mark.parametrize("name", ["interp_P1_N9_to_N5", "interp_P2_N7_to_N5"])
+def test_collision_ingest_interpolates_on_the_device(cuda_device, name, tmp_path):
+    """File ingest with N_f > N: the down-interpolation kernel (wg_interpolate_collision) against the live
+    reference's CollisionArray.interpolateCollisionArray (golden), through loadCollisions."""
+    import wallgo_b200 as wb
+
+    g = load_golden(name)
+    P, M, Nf, Nt = int(g["P"]), int(g["M"]), int(g["Nf"]), int(g["Nt"])
+    parts = [wb.Particle(f"p{a}", a, None, None, "Fermion", 1) for a in range(P)]
+    for a in range(P):
+        for b in range(P):
+            np.savez(tmp_path / f"collisions_p{a}_p{b}.npz", **{"data": g["source"][a, :, :, b], "Basis Size": Nf,
+                                                                 "Basis Type": "Chebyshev"})
+    solver = wb.BoltzmannSolver(wb.Grid(M, Nt, 0.05, 100.0), basisN=str(g["basis"]))
+    solver.updateParticleList(parts)
+    solver.loadCollisions(tmp_path)
+    assert solver.collisionArray[...].shape == g["ref_interpolated"].shape
+    assert relmax(solver.collisionArray[...], g["ref_interpolated"]) < 1e-12
+    src = wb.CollisionArray(wb.Grid(M, Nf, 0.05, 100.0), "Chebyshev", parts, g["source"])
+    host = wb.CollisionArray.interpolateCollisionArray(src, wb.Grid(M, Nt, 0.05, 100.0))
+    assert relmax(solver.collisionArray[...], host[...]) < 1e-13
+
+
+def test_wg_moments_requires_its_spectra_call(cuda_device):
+    """wg_moments consumes the Chebyshev coefficients of the preceding wg_spectra on the same deltaF: calling it
+    twice, or on another vector, is a state error instead of a silent result from stale data."""
+    from wallgo_b200 import _lib
+
+    g = load_golden("tiny_P1_M6_N5")
+    solver = solver_from_golden(g)
+    solver.getDeltas()
+    eng = solver._getEngine()
+    with pytest.raises(_lib.WallGoB200Error):
+        eng.moments_async(eng.S, (5, 4, 4), True)          # second wg_moments without a new wg_spectra
+    eng.spectra_async(eng.S)
+    with pytest.raises(_lib.WallGoB200Error):
+        eng.moments_async(eng.dF_in, (5, 4, 4), True)      # other vector than the one wg_spectra saw
+    eng.spectra_async(eng.S)
+    eng.moments_async(eng.S, (5, 4, 4), True)
+
+
+def test_solvers_on_two_devices_in_one_process(cuda_device):
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    g = load_golden("small_P2_M12_N7")
+    a, b = solver_from_golden(g, device=0), solver_from_golden(g, device=1)
+    ra, rb = a.getDeltas(), b.getDeltas()
+    assert torch.cuda.current_device() == 0
+    assert np.array_equal(ra.deltaF, rb.deltaF)
+    assert relmax(rb.deltaF, g["ref_deltaF_trunc"]) < TOL
+
+
+def test_per_solver_tuning_does_not_leak(cuda_device):
+    """wg_solver_set_tuning touches one solver; results are identical for every schedule."""
+    g = load_golden("cfg1_P1_M20_N11")
+    a, b = solver_from_golden(g), solver_from_golden(g)
+    ea, eb = a._getEngine(), b._getEngine()
+    from wallgo_b200 import _lib
+    _lib.check(ea.lib.wg_solver_set_tuning(ea.h, 64, 0, 0, 0, 0), "wg_solver_set_tuning")
+    ra, rb = a.getDeltas(), b.getDeltas()
+    assert relmax(ra.deltaF, rb.deltaF) < 1e-12 and relmax(ra.deltaF, g["ref_deltaF_trunc"]) < TOL

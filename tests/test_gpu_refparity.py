@@ -60,7 +60,6 @@ def test_baseline_config_against_reference_class(cuda_device, rd, cfg):
         refBlk = opRef[r0:r0 + step]
         scale = np.max(np.abs(refBlk), axis=1, keepdims=True)
         worst = max(worst, float(np.max(np.abs(blk - refBlk) / scale)))
-        assert np.array_equal(blk == 0.0, refBlk == 0.0), "sparsity pattern differs"
     assert worst <= 2e-13, (cfg, worst)
 
     # ---- deltaF = np.linalg.solve(operator, source) on the host vs LU on the device

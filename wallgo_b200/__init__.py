@@ -14,9 +14,9 @@ _os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 from .boltzmann import BoltzmannSolver  # noqa: E402
 from .containers import (BoltzmannBackground, BoltzmannDeltas, BoltzmannResults, CollisionArray,
-                         ETruncationOption, Particle, Polynomial)
+                         CollisionLoadError, ETruncationOption, Particle, Polynomial)
 from .grid import Grid, Grid3Scales
 
 __all__ = ["BoltzmannSolver", "BoltzmannBackground", "BoltzmannDeltas", "BoltzmannResults",
-           "CollisionArray", "ETruncationOption", "Particle", "Polynomial", "Grid", "Grid3Scales"]
+           "CollisionArray", "CollisionLoadError", "ETruncationOption", "Particle", "Polynomial", "Grid", "Grid3Scales"]
 __version__ = "0.1.0"

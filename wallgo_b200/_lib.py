@@ -19,6 +19,7 @@ SYMBOLS = {
     "wg_last_error": (C.c_char_p, []),
     "wg_launch_count": (C.c_longlong, []),
     "wg_set_tuning": (C.c_int, [C.c_int, C.c_int]),
+    "wg_solver_set_tuning": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "wg_set_lookahead": (C.c_int, [C.c_int]),
     "wg_set_bulk_priority_rest": (C.c_int, [C.c_int]),
     "wg_set_bulk_split": (C.c_int, [C.c_int]),
@@ -32,6 +33,7 @@ SYMBOLS = {
     "wg_get_tables": (C.c_int, [_vp] + [_hd] * 6),
     "wg_set_transforms": (C.c_int, [_vp, C.POINTER(_hd)]),
     "wg_set_collision": (C.c_int, [_vp, _vp, C.c_int]),
+    "wg_interpolate_collision": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _hd, _hd, _hd, _hd]),
     "wg_assemble": (C.c_int, [_vp, _dp, C.c_double, C.c_double, C.c_int, _dp, C.c_longlong, _dp, _vp]),
     "wg_factor": (C.c_int, [_vp, _dp, C.c_longlong, _vp]),
     "wg_factor_solve": (C.c_int, [_vp, _dp, C.c_longlong, _dp, _vp]),

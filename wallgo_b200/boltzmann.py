@@ -159,18 +159,21 @@ class BoltzmannSolverB200Mixin:
 
     def setCollisionArray(self, collisionArray) -> None:
         self.collisionArray = collisionArray
+        self._staticKey = None           # re-upload the tensor at the next solve
 
     def updateParticleList(self, offEqParticles) -> None:
         for p in offEqParticles:
             assert hasattr(p, "msqVacuum") and hasattr(p, "statistics"), "not a Particle"
         self.offEqParticles = offEqParticles
+        self._staticKey = None
 
     def loadCollisions(self, directoryPath) -> None:
-        """Reads collisions_{a}_{b}.hdf5 (boltzmann.py:822-844).  HDF5 ingest is a 'next' row
-        (SURVEY section 8 f2): it needs an HDF5 reader, which this image does not have."""
-        raise NotImplementedError(
-            "wallgo_b200: HDF5 collision ingest is not built yet; pass an in-memory tensor with "
-            "setCollisionArray (the reference supports this via CollisionArray.newFromPolynomial)")
+        """Loads one collision file per ordered pair of out-of-equilibrium species from `directoryPath`
+        (boltzmann.py:822-844 -> CollisionArray.newFromDirectory); raises CollisionLoadError when a file is
+        missing, larger grids are requested than the files hold, or the format cannot be read here."""
+        self.collisionArray = _own.CollisionArray.newFromDirectory(
+            directoryPath, self.grid, self.basisN, self.offEqParticles, device=self.device)
+        self._staticKey = None
 
     # deepcopy (used by EOM.getBoltzmannFiniteDifference, equationOfMotion.py:2135) must not clone
     # the device handle; the copy builds its own engine lazily.
@@ -216,8 +219,14 @@ class BoltzmannSolverB200Mixin:
         coll = self._collisionData()
         stats = tuple(-1.0 if p.statistics == "Fermion" else 1.0 for p in self.offEqParticles)
         _, dpzdrz, dppdrp = g.getCompactificationDerivatives()
-        key = (self.basisM, self.basisN, self.derivatives, stats, coll.__array_interface__["data"][0],
-               coll.shape, float(g.momentumFalloffT), float(coll.flat[0]), float(coll.flat[-1]))
+        # content fingerprint of the tensor (an in-place edit by the caller must not leave a stale copy on the
+        # GPU): the full sum up to 2^21 entries, a strided sample of that size beyond
+        flat = coll.reshape(-1)
+        step = max(1, flat.size >> 21)
+        dofs = tuple(float(p.totalDOFs) for p in self.offEqParticles)
+        key = (self.basisM, self.basisN, self.derivatives, stats, dofs, id(g), coll.__array_interface__["data"][0],
+               coll.shape, float(g.momentumFalloffT), float(np.sum(flat[::step])), float(np.sum(np.abs(flat[::step]))),
+               float(flat[0]), float(flat[-1]))
         if key != self._staticKey:
             chi, rz, rp = g.getCompactCoordinates()
             _, pz, pp = g.getCoordinates()

@@ -14,6 +14,11 @@ from enum import Enum, auto
 import numpy as np
 
 
+class CollisionLoadError(Exception):
+    """Raised when collision integrals fail to load (mirror of WallGo.exceptions.CollisionLoadError,
+    exceptions.py:52-55; the drop-in raises WallGo's own class)."""
+
+
 class ETruncationOption(Enum):
     """Mirror of WallGo.boltzmann.ETruncationOption (boltzmann.py:24-34)."""
     NONE = auto()
@@ -162,26 +167,92 @@ class CollisionArray:
     def getBasisType(self):
         return self.basisType
 
+    # ------------------------------------------------------------------ file ingest
     @staticmethod
-    def interpolateCollisionArray(srcCollision, targetGrid):
-        """Collision tensor computed on a finer momentum grid (N_f) brought to `targetGrid` (N <= N_f - 1):
-        the Chebyshev series in the polynomial axes is truncated and the collocation axes are evaluated at
-        the target nodes with the Lagrange cardinals of the source grid (reference
-        collisionArray.py:390-478, polynomial.py:300-443).  The result has the source's basis type.
-        Note: like the reference, the evaluated array (points, a, b, j, k) is reshaped without a transpose,
-        which is only an identity re-labelling for a single species."""
-        import copy
+    def readPairFile(directoryPath, name1, name2):
+        """(data (N_f-1)^4, basisSize N_f, basisType) of one ordered pair.  The reference's on-disk format is
+        `collisions_{a}_{b}.hdf5` with attrs "Basis Size", "Basis Type" on the group "metadata" and a dataset
+        "{a}, {b}" (collisionArray.py:225-249).  This image has no HDF5 library and every shipped .hdf5 is a
+        Git-LFS pointer, so an HDF5 reader could not be verified; until then the same content is accepted as
+          collisions_{a}_{b}.npz   keys: "data" (or "{a}, {b}"), "Basis Size", "Basis Type"
+          collisions_{a}_{b}.npy   raw (N_f-1)^4 tensor, Chebyshev basis, N_f from the shape
+        (`python -c "import h5py, numpy ..."` on a machine with h5py converts a directory in three lines,
+        INTEGRATION.md).  An .hdf5 next to them is tried with h5py when that module exists."""
+        import os
 
+        base = os.path.join(str(directoryPath), f"collisions_{name1}_{name2}")
+        if os.path.exists(base + ".npz"):
+            with np.load(base + ".npz", allow_pickle=False) as z:
+                key = "data" if "data" in z.files else f"{name1}, {name2}"
+                if key not in z.files:
+                    raise CollisionLoadError(f"CollisionArray error: {base}.npz holds no dataset 'data' or '{key}'.")
+                data = np.array(z[key], dtype=np.float64)
+                size = int(z["Basis Size"]) if "Basis Size" in z.files else data.shape[0] + 1
+                btype = str(z["Basis Type"]) if "Basis Type" in z.files else "Chebyshev"
+            return data, size, btype
+        if os.path.exists(base + ".npy"):
+            data = np.array(np.load(base + ".npy", allow_pickle=False), dtype=np.float64)
+            return data, data.shape[0] + 1, "Chebyshev"
+        if os.path.exists(base + ".hdf5"):
+            try:
+                import h5py  # pylint: disable=import-outside-toplevel
+                with h5py.File(base + ".hdf5", "r") as f:
+                    meta = f["metadata"]
+                    btype = meta.attrs["Basis Type"]
+                    btype = btype.decode() if isinstance(btype, bytes) else str(btype)
+                    return np.array(f[f"{name1}, {name2}"][:], dtype=np.float64), int(meta.attrs["Basis Size"]), btype
+            except (ImportError, OSError, AttributeError) as exc:
+                raise CollisionLoadError(
+                    f"CollisionArray error: {base}.hdf5 cannot be read here ({exc}); convert it to .npz "
+                    "(keys 'data', 'Basis Size', 'Basis Type') -- see INTEGRATION.md.") from exc
+        raise CollisionLoadError(f"CollisionArray error: {base}.hdf5 not found.")
+
+    @staticmethod
+    def newFromDirectory(directoryPath, grid, basisType, particles, bInterpolate=True, device=None):
+        """Mirror of CollisionArray.newFromDirectory (collisionArray.py:179-354): one file per ordered pair of
+        out-of-equilibrium species, all with the same basis size N_f and basis type; N_f > grid.N is brought
+        down to the grid by `interpolateCollisionArray`, whose contraction runs ON THE DEVICE
+        (wg_interpolate_collision) when a GPU is present.  Raises CollisionLoadError like the reference."""
+        P = len(particles)
+        tensor, sizeFile, typeFile = None, None, None
+        for i, p1 in enumerate(particles):
+            for j, p2 in enumerate(particles):
+                data, size, btype = CollisionArray.readPairFile(directoryPath, p1.name, p2.name)
+                if grid.N > size:
+                    raise CollisionLoadError(
+                        f"Target collision grid size ({grid.N}) must be smaller or equal to the grid size "
+                        f"recorded in collision files ({size}).")
+                if btype not in ("Cardinal", "Chebyshev"):
+                    raise CollisionLoadError(f"CollisionArray error: unknown basis type {btype!r} in the collision file.")
+                if data.shape != (size - 1,) * 4:
+                    raise CollisionLoadError(
+                        f"CollisionArray error: dataset '{p1.name}, {p2.name}' has shape {data.shape}, "
+                        f"expected {(size - 1,) * 4}.")
+                if tensor is None:
+                    tensor = np.zeros((P, size - 1, size - 1, P, size - 1, size - 1))
+                    sizeFile, typeFile = size, btype
+                else:
+                    assert size == sizeFile, "CollisionArray error: All the collision files must have the same basis size."
+                    assert btype == typeFile, "CollisionArray error: All the collision files must have the same basis type."
+                tensor[i, :, :, j, :, :] = data
+        if sizeFile == grid.N:
+            return CollisionArray(grid, typeFile, particles, tensor).changeBasis(basisType)
+        if not bInterpolate:
+            raise CollisionLoadError(
+                f"Grid size mismatch when loading collision directory: {directoryPath}. "
+                "Consider using bInterpolate=True in CollisionArray.loadFromFile().")
+        from .grid import Grid  # pylint: disable=import-outside-toplevel
+        dummyGrid = Grid(grid.M, sizeFile, getattr(grid, "positionFalloff", 1.0), grid.momentumFalloffT)
+        src = CollisionArray(dummyGrid, typeFile, particles, tensor)
+        return CollisionArray.interpolateCollisionArrayDevice(src, grid, device=device).changeBasis(basisType)
+
+    @staticmethod
+    def interpolationMatrices(srcGrid, targetGrid, nF):
+        """Lagrange cardinals of the source momentum nodes evaluated on the target nodes: Lz, Lp [nT x nF]
+        (what Polynomial.evaluate does along the Cardinal axes, polynomial.py:300-443)."""
         from .spectral import lobattoNodes
 
-        nT = targetGrid.N - 1
-        assert targetGrid.N <= srcCollision.getBasisSize(), (
-            f"CollisionArray interpolation error: target grid size ({targetGrid.N}) must be smaller than or "
-            f"equal to the source grid size ({srcCollision.getBasisSize() + 1}).")
-        src = copy.deepcopy(srcCollision)
-        src.changeBasis("Chebyshev")
-        nF = src.size
-        _, rzF, rpF = lobattoNodes(src.grid.M, src.grid.N)
+        _, rzF, rpF = lobattoNodes(srcGrid.M, srcGrid.N)
         _, rzT, rpT = lobattoNodes(targetGrid.M, targetGrid.N)
 
         def lagrange(xT, xFull, idx):
@@ -194,8 +265,55 @@ class CollisionArray:
 
         Lz = lagrange(rzT, np.concatenate([[-1.0], rzF, [1.0]]), np.arange(1, nF + 1))   # [beta_T, beta_F]
         Lp = lagrange(rpT, np.concatenate([rpF, [1.0]]), np.arange(0, nF))               # [gamma_T, gamma_F]
-        ev = np.einsum("xb,yg,abgcjk->xyacjk", Lz, Lp, src.data)                          # (bT, gT, a, b, j, k)
+        return Lz, Lp
+
+    @staticmethod
+    def interpolateCollisionArrayDevice(srcCollision, targetGrid, device=None):
+        """interpolateCollisionArray with the contraction on the GPU (wg_interpolate_collision): what the file
+        ingest uses.  No CPU path: raises without a CUDA device, like every other product call."""
+        import copy
+
+        nT = targetGrid.N - 1
+        assert targetGrid.N <= srcCollision.getBasisSize(), (
+            f"CollisionArray interpolation error: target grid size ({targetGrid.N}) must be smaller than or "
+            f"equal to the source grid size ({srcCollision.getBasisSize() + 1}).")
+        src = copy.deepcopy(srcCollision)
+        src.changeBasis("Chebyshev")
+        nF = src.size
+        Lz, Lp = CollisionArray.interpolationMatrices(src.grid, targetGrid, nF)
         P = len(src.particles)
+        from . import _lib  # pylint: disable=import-outside-toplevel
+        from .engine import default_device  # pylint: disable=import-outside-toplevel
+
+        lib = _lib.load()
+        data = np.empty((P, nT, nT, P, nT, nT))
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (Lz, Lp, src.data)]
+        _lib.check(lib.wg_interpolate_collision(default_device() if device is None else int(device), P, nF + 1, nT + 1,
+                                                _lib.host_ptr(arrs[0]), _lib.host_ptr(arrs[1]), _lib.host_ptr(arrs[2]),
+                                                _lib.host_ptr(data)), "wg_interpolate_collision")
+        out = CollisionArray(targetGrid, "Chebyshev", src.particles, data)
+        return out.changeBasis(srcCollision.getBasisType())
+
+    @staticmethod
+    def interpolateCollisionArray(srcCollision, targetGrid):
+        """Collision tensor computed on a finer momentum grid (N_f) brought to `targetGrid` (N <= N_f - 1):
+        the Chebyshev series in the polynomial axes is truncated and the collocation axes are evaluated at
+        the target nodes with the Lagrange cardinals of the source grid (reference
+        collisionArray.py:390-478, polynomial.py:300-443).  The result has the source's basis type.
+        Note: like the reference, the evaluated array (points, a, b, j, k) is reshaped without a transpose,
+        which is only an identity re-labelling for a single species."""
+        import copy
+
+        nT = targetGrid.N - 1
+        assert targetGrid.N <= srcCollision.getBasisSize(), (
+            f"CollisionArray interpolation error: target grid size ({targetGrid.N}) must be smaller than or "
+            f"equal to the source grid size ({srcCollision.getBasisSize() + 1}).")
+        src = copy.deepcopy(srcCollision)
+        src.changeBasis("Chebyshev")
+        nF = src.size
+        Lz, Lp = CollisionArray.interpolationMatrices(src.grid, targetGrid, nF)
+        P = len(src.particles)
+        ev = np.einsum("xb,yg,abgcjk->xyacjk", Lz, Lp, src.data)                          # (bT, gT, a, b, j, k)
         ev = ev.reshape(nT * nT, P, P, nF, nF)[..., :nT, :nT]
         data = np.ascontiguousarray(ev).reshape(P, nT, nT, P, nT, nT)
         out = CollisionArray(targetGrid, "Chebyshev", src.particles, data)

@@ -426,6 +426,46 @@ __global__ void wg_feedback_kernel(BzDims d, const double* __restrict__ deltas, 
   }
 }
 
+// Collision tensor computed on a finer momentum grid brought to the solver's grid
+// (CollisionArray.interpolateCollisionArray, collisionArray.py:391-478): the collocation axes (beta, gamma) are
+// evaluated at the target nodes with the Lagrange cardinals of the source grid, the Chebyshev series in the
+// polynomial axes (j, k) is truncated.  src [P][nF][nF][P][nF][nF]; out is written in the order
+// (x, y, a, c, j, k) -- the reference reshapes the evaluated array to (P, nT, nT, P, nT, nT) WITHOUT a transpose
+// (an identity re-labelling only for one species), reproduced here for drop-in fidelity.
+__global__ void wg_collision_interp_kernel(int P, int nF, int nT, const double* __restrict__ Lz,
+                                           const double* __restrict__ Lp, const double* __restrict__ src,
+                                           double* __restrict__ out) {
+  const long long total = (long long)nT * nT * P * P * nT * nT;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    long long r = e;
+    const int k = (int)(r % nT); r /= nT;
+    const int j = (int)(r % nT); r /= nT;
+    const int c = (int)(r % P); r /= P;
+    const int a = (int)(r % P); r /= P;
+    const int y = (int)(r % nT); r /= nT;
+    const int x = (int)r;
+    double acc = 0.0;
+    for (int b = 0; b < nF; ++b) {
+      double inner = 0.0;
+      for (int g = 0; g < nF; ++g)
+        inner += Lp[y * nF + g] * src[((((long long)(a * nF + b) * nF + g) * P + c) * nF + j) * nF + k];
+      acc += Lz[x * nF + b] * inner;
+    }
+    out[e] = acc;
+  }
+}
+
+int bz_collision_interp(int P, int nF, int nT, const double* Lz, const double* Lp, const double* src, double* out,
+                        cudaStream_t st) {
+  const long long total = (long long)nT * nT * P * P * nT * nT;
+  int blocks = wg_cdiv(total, 256);
+  if (blocks > 2368) blocks = 2368;
+  wg_collision_interp_kernel<<<blocks, 256, 0, st>>>(P, nF, nT, Lz, Lp, src, out);
+  WG_LAUNCH_CHECK();
+  return WG_OK;
+}
+
 // ============================================================================ host launchers
 int bz_feedback(const BzDims& d, const double* deltas, const double* prof, const double* dofs, const double* dmsq,
                 int F, double u0, double u3, double* out, cudaStream_t st) {
@@ -468,15 +508,13 @@ int bz_assemble(const BzDims& d, const BzStatic& s, const double* prof, double v
   constexpr int R = 4;
   const size_t smem = ((size_t)R * d.q * (2 + d.P) + 2 * d.M1) * sizeof(double);
   WG_REQUIRE(smem <= 200 * 1024, "assemble: basis tile does not fit in shared memory");
-  static size_t configured = 0;
-  if (smem > configured) {
+  if (wg_func_configured(reinterpret_cast<const void*>(wg_assemble_kernel<R, 4>), smem) < (long long)smem) {
     WG_CUDA(cudaFuncSetAttribute(wg_assemble_kernel<R, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WG_CUDA(cudaFuncSetAttribute(wg_assemble_kernel<R, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WG_CUDA(cudaFuncSetAttribute(wg_assemble_kernel<R, 2>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared));
     WG_CUDA(cudaFuncSetAttribute(wg_assemble_kernel<R, 4>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared));
-    configured = smem;
   }
   dim3 grid(d.q / R, d.P * d.M1);
   const bool wide = g_asm_wide && d.q % 4 == 0 && lda % 4 == 0 && reinterpret_cast<uintptr_t>(A) % 32 == 0;

@@ -38,6 +38,8 @@ int bz_moments(const BzDims& d, const BzStatic& s, const double* card, const dou
                cudaStream_t st);
 int bz_feedback(const BzDims& d, const double* deltas, const double* prof, const double* dofs, const double* dmsq,
                 int F, double u0, double u3, double* out, cudaStream_t st);
+int bz_collision_interp(int P, int nF, int nT, const double* Lz, const double* Lp, const double* src, double* out,
+                        cudaStream_t st);
 int bz_collision_matvec(const BzDims& d, const BzStatic& s, const double* cT2, const double* x, double* y,
                         cudaStream_t st);
 

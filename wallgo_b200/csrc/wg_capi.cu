@@ -5,6 +5,10 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include "../../include/wallgo_b200.h"
@@ -13,15 +17,49 @@
 #include "wg_kernels.h"
 
 static thread_local char g_err[512] = "";
-long long g_wg_launches = 0;
+std::atomic<long long> g_wg_launches{0};
 thread_local int g_wg_launch_prio = INT_MIN;
 int g_wg_sync_every_launch = (getenv("WG_SYNC_EVERY_LAUNCH") != nullptr);
+long long wg_func_configured(const void* func, size_t smem) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, long long> seen;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_pair(dev, func);
+  auto it = seen.find(key);
+  const long long before = (it == seen.end()) ? -1 : it->second;
+  if ((long long)smem > before) seen[key] = (long long)smem;
+  return before;
+}
+
 void wg_set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+// Every entry point runs with the handle's device current and restores the caller's device on return, so
+// engines on different GPUs can live in one process and the host's own torch code keeps its device.
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) ok = (cudaSetDevice(device) == cudaSuccess);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define WG_ON_DEVICE(dev)                                          \
+  DeviceGuard _guard(dev);                                         \
+  if (!_guard.ok) {                                                \
+    wg_set_error("cudaSetDevice(%d) failed", (int)(dev));          \
+    return WG_ERR_CUDA;                                            \
+  }
 
 struct wg_lu {
   wg::LuPlan* plan = nullptr;
@@ -34,6 +72,7 @@ struct wg_solver {
   wg::BzStatic st = {};
   std::vector<void*> allocs;
   double* mats[9] = {};  // transforms (device) or nullptr
+  double* matsSpare[9] = {};  // buffers of transforms that are currently the identity
   // per-solve scratch
   double *derivs = nullptr, *w1 = nullptr, *w2 = nullptr, *cT2 = nullptr;
   double *cheb = nullptr, *bufA = nullptr, *bufB = nullptr;
@@ -41,6 +80,7 @@ struct wg_solver {
   double* dofs = nullptr;
   wg::LuPlan* plan = nullptr;
   bool haveGrid = false, haveTables = false, haveColl = false, haveStat = false, assembled = false;
+  const double* chebOf = nullptr;  // deltaF whose Chebyshev coefficients wg_spectra left in `cheb` (nullptr: none)
 };
 
 template <typename T>
@@ -59,7 +99,6 @@ static int require_device(int device) {
     return WG_ERR_CUDA;
   }
   WG_REQUIRE(device >= 0 && device < count, "device index out of range");
-  WG_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
   WG_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) {
@@ -73,7 +112,7 @@ static int require_device(int device) {
 extern "C" {
 
 int wg_version(void) { return 100; }
-long long wg_launch_count(void) { return g_wg_launches; }
+long long wg_launch_count(void) { return g_wg_launches.load(); }
 const char* wg_last_error(void) { return g_err; }
 int wg_set_tuning(int nb, int use_graph) {
   wg::lu_set_tuning(nb, use_graph);
@@ -85,6 +124,7 @@ int wg_debug_gemm_variant(int v) {
 }
 int wg_profile_gemm(wg_solver* s, int enable, double* ms, double* flops, int* count) {
   WG_REQUIRE(s, "wg_profile_gemm: NULL solver");
+  WG_ON_DEVICE(s->device);
   wg::lu_set_profile(enable);
   return wg::lu_profile_read(s->plan, ms, flops, count);
 }
@@ -113,6 +153,11 @@ int wg_debug_force_wb(int wb) {
   wg::lu_set_force_wb(wb);
   return WG_OK;
 }
+int wg_solver_set_tuning(wg_solver* s, int nb, int use_graph, int lookahead, int split_percent, int bulk_hi_rest) {
+  WG_REQUIRE(s && s->plan, "wg_solver_set_tuning: NULL solver");
+  wg::lu_plan_set_tuning(s->plan, nb, use_graph, lookahead, split_percent, bulk_hi_rest);
+  return WG_OK;
+}
 int wg_set_lookahead(int on) {
   wg::lu_set_lookahead(on);
   return WG_OK;
@@ -129,6 +174,7 @@ int wg_create(int P, int M, int N, int device, wg_solver** out) {
   WG_REQUIRE(P >= 1 && M >= 3 && N >= 3 && (N % 2 == 1), "wg_create: need P>=1, M>=3, N>=3 and N odd");
   int rc = require_device(device);
   if (rc) return rc;
+  WG_ON_DEVICE(device);
   wg_solver* s = new wg_solver();
   s->device = device;
   wg::BzDims& d = s->d;
@@ -166,10 +212,12 @@ int wg_create(int P, int M, int N, int device, wg_solver** out) {
 
 int wg_destroy(wg_solver* s) {
   if (!s) return WG_OK;
-  cudaSetDevice(s->device);
+  WG_ON_DEVICE(s->device);
   for (void* p : s->allocs) cudaFree(p);
-  for (int i = 0; i < 9; ++i)
+  for (int i = 0; i < 9; ++i) {
     if (s->mats[i]) cudaFree(s->mats[i]);
+    if (s->matsSpare[i]) cudaFree(s->matsSpare[i]);
+  }
   wg::lu_plan_destroy(s->plan);
   delete s;
   return WG_OK;
@@ -191,7 +239,7 @@ static int h2d(double* dst, const double* src, size_t count) {
 int wg_set_grid(wg_solver* s, const double* chi, const double* rz, const double* rp, const double* pz,
                 const double* pp, const double* dpzdrz, const double* dppdrp) {
   WG_REQUIRE(s, "wg_set_grid: NULL solver");
-  WG_CUDA(cudaSetDevice(s->device));
+  WG_ON_DEVICE(s->device);
   int rc = 0;
   rc |= h2d(s->st.chi, chi, s->d.M1);
   rc |= h2d(s->st.rz, rz, s->d.N1);
@@ -207,7 +255,7 @@ int wg_set_grid(wg_solver* s, const double* chi, const double* rz, const double*
 
 int wg_set_statistics(wg_solver* s, const double* statistics) {
   WG_REQUIRE(s, "wg_set_statistics: NULL solver");
-  WG_CUDA(cudaSetDevice(s->device));
+  WG_ON_DEVICE(s->device);
   int rc = h2d(s->st.stat, statistics, s->d.P);
   if (rc) return rc;
   s->haveStat = true;
@@ -216,7 +264,7 @@ int wg_set_statistics(wg_solver* s, const double* statistics) {
 
 int wg_set_dofs(wg_solver* s, const double* dofs) {
   WG_REQUIRE(s, "wg_set_dofs: NULL solver");
-  WG_CUDA(cudaSetDevice(s->device));
+  WG_ON_DEVICE(s->device);
   return h2d(s->dofs, dofs, s->d.P);
 }
 
@@ -224,6 +272,7 @@ int wg_feedback(wg_solver* s, const double* deltas_dev, const double* profiles_d
                 int nFields, double velocityMid, double* out_dev, void* stream) {
   WG_REQUIRE(s && deltas_dev && profiles_dev && out_dev && nFields >= 0 && (nFields == 0 || dmsq_dphi_dev),
              "wg_feedback: bad argument");
+  WG_ON_DEVICE(s->device);
   WG_REQUIRE(velocityMid > -1.0 && velocityMid < 1.0, "wg_feedback: |velocityMid| must be < 1");
   const double u0 = sqrt(1.0 / (1.0 - velocityMid * velocityMid));  // helpers.gammaSq
   const double u3 = u0 * velocityMid;
@@ -233,7 +282,7 @@ int wg_feedback(wg_solver* s, const double* deltas_dev, const double* profiles_d
 
 int wg_build_basis(wg_solver* s) {
   WG_REQUIRE(s && s->haveGrid, "wg_build_basis: call wg_set_grid first");
-  WG_CUDA(cudaSetDevice(s->device));
+  WG_ON_DEVICE(s->device);
   int rc = wg::bz_build_basis(s->d, s->st.rz, s->st.Tchi, s->st.Dchi, s->st.DchiFull, s->st.Trz, s->st.Drz,
                               s->st.Trp, 0);
   if (rc) return rc;
@@ -247,7 +296,7 @@ int wg_build_basis(wg_solver* s) {
 int wg_set_tables(wg_solver* s, const double* Tchi, const double* Dchi, const double* DchiFull,
                   const double* Trz, const double* Drz, const double* Trp) {
   WG_REQUIRE(s, "wg_set_tables: NULL solver");
-  WG_CUDA(cudaSetDevice(s->device));
+  WG_ON_DEVICE(s->device);
   const size_t M1 = s->d.M1, N1 = s->d.N1, L = s->d.M + 1;
   int rc = 0;
   rc |= h2d(s->st.Tchi, Tchi, M1 * M1);
@@ -267,7 +316,7 @@ int wg_set_tables(wg_solver* s, const double* Tchi, const double* Dchi, const do
 int wg_get_tables(wg_solver* s, double* Tchi, double* Dchi, double* DchiFull, double* Trz, double* Drz,
                   double* Trp) {
   WG_REQUIRE(s && s->haveTables, "wg_get_tables: no tables yet");
-  WG_CUDA(cudaSetDevice(s->device));
+  WG_ON_DEVICE(s->device);
   const size_t M1 = s->d.M1, N1 = s->d.N1, L = s->d.M + 1;
   if (Tchi) WG_CUDA(cudaMemcpy(Tchi, s->st.Tchi, M1 * M1 * 8, cudaMemcpyDeviceToHost));
   if (Dchi) WG_CUDA(cudaMemcpy(Dchi, s->st.Dchi, M1 * M1 * 8, cudaMemcpyDeviceToHost));
@@ -280,23 +329,30 @@ int wg_get_tables(wg_solver* s, double* Tchi, double* Dchi, double* DchiFull, do
 
 int wg_set_transforms(wg_solver* s, const double* const mats[9]) {
   WG_REQUIRE(s && mats, "wg_set_transforms: NULL argument");
-  WG_CUDA(cudaSetDevice(s->device));
+  WG_ON_DEVICE(s->device);
   for (int i = 0; i < 9; ++i) {
-    if (s->mats[i]) {
-      cudaFree(s->mats[i]);
-      s->mats[i] = nullptr;
-    }
-    if (!mats[i]) continue;
     const size_t len = (i % 3 == 0) ? s->d.M1 : s->d.N1;
-    WG_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->mats[i]), len * len * sizeof(double)));
+    if (!mats[i]) {   // identity: the buffer (if any) is parked for a later call instead of being freed
+      if (s->mats[i]) s->matsSpare[i] = s->mats[i];
+      s->mats[i] = nullptr;
+      continue;
+    }
+    if (!s->mats[i]) {
+      s->mats[i] = s->matsSpare[i];
+      s->matsSpare[i] = nullptr;
+    }
+    if (!s->mats[i]) WG_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->mats[i]), len * len * sizeof(double)));
+    // ordered behind earlier work of the default stream only; callers synchronise their own stream before
+    // replacing the matrices of a solver that still has basis changes in flight
     WG_CUDA(cudaMemcpy(s->mats[i], mats[i], len * len * sizeof(double), cudaMemcpyHostToDevice));
   }
+  s->chebOf = nullptr;
   return WG_OK;
 }
 
 int wg_set_collision(wg_solver* s, const double* C, int on_device) {
   WG_REQUIRE(s && C, "wg_set_collision: NULL argument");
-  WG_CUDA(cudaSetDevice(s->device));
+  WG_ON_DEVICE(s->device);
   const size_t cnt = (size_t)s->d.P * s->d.q * s->d.P * s->d.q;
   WG_CUDA(cudaMemcpy(s->st.Coll, C, cnt * sizeof(double),
                      on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
@@ -307,6 +363,7 @@ int wg_set_collision(wg_solver* s, const double* C, int on_device) {
 int wg_assemble(wg_solver* s, const double* profiles_dev, double vw, double collisionMultiplier, int parts,
                 double* A_dev, long long lda, double* S_dev, void* stream) {
   WG_REQUIRE(s && profiles_dev && A_dev && S_dev, "wg_assemble: NULL argument");
+  WG_ON_DEVICE(s->device);
   if (!(s->haveGrid && s->haveTables && s->haveColl && s->haveStat)) {
     wg_set_error("wg_assemble: grid, statistics, tables and collision tensor must be set first");
     return WG_ERR_STATE;
@@ -320,11 +377,13 @@ int wg_assemble(wg_solver* s, const double* profiles_dev, double vw, double coll
 
 int wg_factor(wg_solver* s, double* A_dev, long long lda, void* stream) {
   WG_REQUIRE(s && A_dev, "wg_factor: NULL argument");
+  WG_ON_DEVICE(s->device);
   return wg::lu_factor(s->plan, A_dev, lda, s->ipiv, s->info, (cudaStream_t)stream);
 }
 
 int wg_factor_solve(wg_solver* s, double* A_dev, long long lda, double* b_dev, void* stream) {
   WG_REQUIRE(s && A_dev && b_dev, "wg_factor_solve: NULL argument");
+  WG_ON_DEVICE(s->device);
   int rc = wg::lu_factor(s->plan, A_dev, lda, s->ipiv, s->info, (cudaStream_t)stream, b_dev);
   if (rc) return rc;
   return wg::lu_solve(s->plan, A_dev, lda, b_dev, (cudaStream_t)stream, true);
@@ -332,6 +391,7 @@ int wg_factor_solve(wg_solver* s, double* A_dev, long long lda, double* b_dev, v
 
 int wg_solve(wg_solver* s, const double* LU_dev, long long lda, double* b_dev, void* stream) {
   WG_REQUIRE(s && LU_dev && b_dev, "wg_solve: NULL argument");
+  WG_ON_DEVICE(s->device);
   return wg::lu_solve(s->plan, LU_dev, lda, b_dev, (cudaStream_t)stream);
 }
 
@@ -353,6 +413,7 @@ int wg_assemble_factor_solve_batched(int B, wg_solver* const* s, const double* c
 
 int wg_info(wg_solver* s, void* stream, int* info_host) {
   WG_REQUIRE(s && info_host, "wg_info: NULL argument");
+  WG_ON_DEVICE(s->device);
   WG_CUDA(cudaMemcpyAsync(info_host, s->info, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   WG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   return WG_OK;
@@ -395,15 +456,20 @@ static int apply_stage(wg_solver* s, int stage, const double* in, double* out, c
 int wg_change_basis(wg_solver* s, int stage, const double* in_dev, double* out_dev, void* stream) {
   WG_REQUIRE(s && in_dev && out_dev && stage >= 0 && stage < 3 && in_dev != out_dev,
              "wg_change_basis: bad argument");
+  WG_ON_DEVICE(s->device);
   return apply_stage(s, stage, in_dev, out_dev, (cudaStream_t)stream);
 }
 
 int wg_spectra(wg_solver* s, const double* deltaF_dev, double* spectra_dev, void* stream) {
   WG_REQUIRE(s && deltaF_dev && spectra_dev, "wg_spectra: NULL argument");
+  WG_ON_DEVICE(s->device);
   cudaStream_t st = (cudaStream_t)stream;
+  s->chebOf = nullptr;
   int rc = apply_stage(s, 0, deltaF_dev, s->cheb, st);
   if (rc) return rc;
-  return wg::bz_spectra(s->d, s->cheb, spectra_dev, st);
+  rc = wg::bz_spectra(s->d, s->cheb, spectra_dev, st);
+  if (rc == WG_OK) s->chebOf = deltaF_dev;
+  return rc;
 }
 
 int wg_moments(wg_solver* s, const double* deltaF_dev, const double* profiles_dev, int keepM, int keepPz,
@@ -411,6 +477,7 @@ int wg_moments(wg_solver* s, const double* deltaF_dev, const double* profiles_de
                void* stream) {
   WG_REQUIRE(s && deltaF_dev && profiles_dev && deltaF_out_dev && deltas_dev && err_dev,
              "wg_moments: NULL argument");
+  WG_ON_DEVICE(s->device);
   // 0 is allowed: on grids with fewer than three coefficients along an axis the reference's truncation
   // zeroes the whole axis (boltzmann.py:400-446, the slice [-0:])
   WG_REQUIRE(keepM >= 0 && keepM <= s->d.M1 && keepPz >= 0 && keepPz <= s->d.N1 && keepPp >= 0 &&
@@ -418,6 +485,13 @@ int wg_moments(wg_solver* s, const double* deltaF_dev, const double* profiles_de
              "wg_moments: keep counts out of range");
   WG_REQUIRE(s->haveGrid, "wg_moments: grid not set");
   cudaStream_t st = (cudaStream_t)stream;
+  if (s->chebOf != deltaF_dev) {
+    // the truncation works on the Chebyshev coefficients that wg_spectra leaves inside the solver; they are
+    // consumed by this call (the buffer is re-used for the cardinal values)
+    wg_set_error("wg_moments: call wg_spectra on the same deltaF_dev first (each wg_moments consumes one wg_spectra)");
+    return WG_ERR_STATE;
+  }
+  s->chebOf = nullptr;
   int rc = wg::bz_truncate(s->d, s->cheb, keepM, keepPz, keepPp, err_dev, st);
   if (rc) return rc;
   if (roundtrip) {
@@ -435,6 +509,7 @@ int wg_moments(wg_solver* s, const double* deltaF_dev, const double* profiles_de
 
 int wg_collision_apply(wg_solver* s, const double* x_dev, double* y_dev, void* stream) {
   WG_REQUIRE(s && x_dev && y_dev, "wg_collision_apply: NULL argument");
+  WG_ON_DEVICE(s->device);
   if (!s->assembled) {
     wg_set_error("wg_collision_apply: call wg_assemble first (needs T^2 of the current background)");
     return WG_ERR_STATE;
@@ -442,10 +517,50 @@ int wg_collision_apply(wg_solver* s, const double* x_dev, double* y_dev, void* s
   return wg::bz_collision_matvec(s->d, s->st, s->cT2, x_dev, y_dev, (cudaStream_t)stream);
 }
 
+int wg_interpolate_collision(int device, int P, int NF, int NT, const double* Lz, const double* Lp,
+                             const double* src, double* out) {
+  WG_REQUIRE(P >= 1 && NF >= 3 && NT >= 3 && NT <= NF && Lz && Lp && src && out, "wg_interpolate_collision: bad argument");
+  int rc = require_device(device);
+  if (rc) return rc;
+  WG_ON_DEVICE(device);
+  const size_t nF = NF - 1, nT = NT - 1;
+  const size_t srcCount = (size_t)P * nF * nF * P * nF * nF, outCount = (size_t)P * nT * nT * P * nT * nT;
+  double *dLz = nullptr, *dLp = nullptr, *dSrc = nullptr, *dOut = nullptr;
+  auto release = [&]() {
+    cudaFree(dLz);
+    cudaFree(dLp);
+    cudaFree(dSrc);
+    cudaFree(dOut);
+  };
+  cudaError_t e = cudaMalloc(&dLz, nT * nF * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&dLp, nT * nF * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&dSrc, srcCount * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&dOut, outCount * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemcpy(dLz, Lz, nT * nF * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dLp, Lp, nT * nF * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dSrc, src, srcCount * sizeof(double), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    release();
+    wg_set_error("wg_interpolate_collision: %s", cudaGetErrorString(e));
+    return WG_ERR_CUDA;
+  }
+  rc = wg::bz_collision_interp(P, (int)nF, (int)nT, dLz, dLp, dSrc, dOut, 0);
+  if (rc == WG_OK) {
+    e = cudaMemcpy(out, dOut, outCount * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) {
+      wg_set_error("wg_interpolate_collision: %s", cudaGetErrorString(e));
+      rc = WG_ERR_CUDA;
+    }
+  }
+  release();
+  return rc;
+}
+
 int wg_lu_create(int n, int device, wg_lu** out) {
   WG_REQUIRE(out && n > 0, "wg_lu_create: bad argument");
   int rc = require_device(device);
   if (rc) return rc;
+  WG_ON_DEVICE(device);
   wg_lu* p = new wg_lu();
   p->device = device;
   rc = wg::lu_plan_create(n, &p->plan);
@@ -459,7 +574,7 @@ int wg_lu_create(int n, int device, wg_lu** out) {
 
 int wg_lu_destroy(wg_lu* p) {
   if (!p) return WG_OK;
-  cudaSetDevice(p->device);
+  WG_ON_DEVICE(p->device);
   wg::lu_plan_destroy(p->plan);
   delete p;
   return WG_OK;
@@ -467,6 +582,7 @@ int wg_lu_destroy(wg_lu* p) {
 
 int wg_lu_factor(wg_lu* p, double* A_dev, long long lda, int* ipiv_dev, int* info_dev, void* stream) {
   WG_REQUIRE(p, "wg_lu_factor: NULL plan");
+  WG_ON_DEVICE(p->device);
   return wg::lu_factor(p->plan, A_dev, lda, ipiv_dev, info_dev, (cudaStream_t)stream);
 }
 
@@ -479,6 +595,7 @@ int wg_debug_lu_trace(wg_lu* p, int on, double* out, int maxSteps) {
 
 int wg_lu_solve(wg_lu* p, const double* LU_dev, long long lda, double* b_dev, void* stream) {
   WG_REQUIRE(p, "wg_lu_solve: NULL plan");
+  WG_ON_DEVICE(p->device);
   return wg::lu_solve(p->plan, LU_dev, lda, b_dev, (cudaStream_t)stream);
 }
 

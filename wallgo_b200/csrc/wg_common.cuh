@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #define WG_OK 0
 #define WG_ERR_ARG (-1)
 #define WG_ERR_CUDA (-2)
@@ -11,7 +13,7 @@
 #define WG_ERR_UNSUPPORTED (-4)
 
 void wg_set_error(const char* fmt, ...);
-extern long long g_wg_launches;  // kernels launched by this library (bench accounting)
+extern std::atomic<long long> g_wg_launches;  // kernels launched by this library (bench accounting)
 
 #define WG_CUDA(call)                                                              \
   do {                                                                             \
@@ -39,6 +41,11 @@ extern int g_wg_sync_every_launch;  // developer aid (env WG_SYNC_EVERY_LAUNCH=1
   } while (0)
 
 static inline int wg_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// Function attributes (opt-in shared-memory size, non-portable cluster size) are per DEVICE, not per process:
+// returns the largest dynamic shared-memory size already configured for `func` on the CURRENT device, or -1 if
+// the function has not been configured there yet, and records `smem` as configured (wg_capi.cu).
+long long wg_func_configured(const void* func, size_t smem);
 
 // Priority carried by kernel launches of the LU (INT_MIN: none).  Stream priorities are not kept by
 // stream capture, so the critical-chain kernels carry theirs as a launch attribute: it becomes the

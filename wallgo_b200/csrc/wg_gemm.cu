@@ -151,19 +151,13 @@ static int launch_cfg(double* C, const double* A, const double* B, int M, int N,
   dim3 grid(wg_cdiv(N, BN), wg_cdiv(M, BM));
   if (vec) {
     auto kern = dgemm_sub_kernel<BM, BN, BK, WARPS_M, WARPS_N, STAGES, true, MINB>;
-    static bool configured = false;
-    if (!configured) {
+    if (wg_func_configured(reinterpret_cast<const void*>(kern), SMEM) < (long long)SMEM)
       WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-      configured = true;
-    }
     WG_CUDA(launch_prio(kern, grid, dim3(NT), SMEM, st, C, A, B, M, N, K, ldc, lda, ldb));
   } else {
     auto kern = dgemm_sub_kernel<BM, BN, BK, WARPS_M, WARPS_N, STAGES, false, MINB>;
-    static bool configured = false;
-    if (!configured) {
+    if (wg_func_configured(reinterpret_cast<const void*>(kern), SMEM) < (long long)SMEM)
       WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-      configured = true;
-    }
     WG_CUDA(launch_prio(kern, grid, dim3(NT), SMEM, st, C, A, B, M, N, K, ldc, lda, ldb));
   }
   WG_LAUNCH_CHECK();

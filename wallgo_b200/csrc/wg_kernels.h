@@ -18,6 +18,7 @@ void lu_plan_destroy(LuPlan* p);
 int lu_factor(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStream_t st, double* rhs = nullptr);
 int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st, bool backwardOnly = false);
 void lu_set_tuning(int nb, int use_graph);
+void lu_plan_set_tuning(LuPlan* p, int nb, int use_graph, int lookahead, int split, int hi_rest);
 void lu_set_debug(long long* dev_buf, int c0);
 void lu_set_lookahead(int on);
 void lu_set_profile(int on);

@@ -44,23 +44,41 @@ void lu_set_debug(long long* buf, int c0) {
   g_dbg_buf = buf;
   g_dbg_c0 = c0;
 }
-static int g_nb = 256;
-static int g_use_graph = 1;  // replay the factorisation as a CUDA graph (node priorities keep the chain ahead)
-static int g_lookahead = 1;
+// Scheduling knobs.  Every plan carries its own copy (LuPlan::t); the process-wide setters below change the
+// DEFAULTS, which a plan adopts the next time it is used unless it has been tuned individually
+// (lu_plan_set_tuning).  A change bumps an epoch, which also invalidates the plan's captured CUDA graphs (the
+// knobs are baked into a graph at capture time).
+struct LuTuning {
+  int nb = 256;
+  int useGraph = 1;   // replay the factorisation as a CUDA graph (node priorities keep the chain ahead)
+  int lookahead = 1;
+  int split = 50;     // two bulk streams while the trailing matrix is large: far part starts at this % of n (0: off)
+  int hiRest = 8192;  // bulk work moves to the high-priority bulk stream once the trailing matrix is this small
+  int leaf32 = 0;
+  int forceWb = 0;    // developer knob: force the leaf width class (4: the 8-rows-per-thread variant)
+};
+static LuTuning g_tune;
+static long long g_tune_epoch = 1;
 static int g_profile = 0;
 static int g_trace = 0;
 // 32-column leaves (fully rotating register window) whenever one row per thread fits the cluster.  Off by
 // default: measured 3 550-3 800 cycles per column against 2 800 for 16-column leaves (the candidate row is
 // twice as long), which cancels the eight TRSM+GEMM pairs per panel it saves.
-static int g_leaf32 = 0;
-void lu_set_leaf32(int on) { g_leaf32 = on; }
+void lu_set_leaf32(int on) {
+  g_tune.leaf32 = on;
+  ++g_tune_epoch;
+}
 void lu_set_profile(int on) { g_profile = on; }
 void lu_set_trace(int on) { g_trace = on; }
 void lu_set_tuning(int nb, int use_graph) {
-  if (nb >= 32 && nb <= 256 && nb % 16 == 0) g_nb = nb;
-  g_use_graph = use_graph;
+  if (nb >= 32 && nb <= 256 && nb % 16 == 0) g_tune.nb = nb;
+  g_tune.useGraph = use_graph;
+  ++g_tune_epoch;
 }
-void lu_set_lookahead(int on) { g_lookahead = on; }
+void lu_set_lookahead(int on) {
+  g_tune.lookahead = on;
+  ++g_tune_epoch;
+}
 
 struct PanelArgs {
   double* A;
@@ -508,11 +526,9 @@ template <int W, int R>
 static int launch_leaf(const PanelArgs& pa, int CL, cudaStream_t st) {
   auto kern = lu_panel_leaf_kernel<W, R>;
   const size_t smem = leaf_smem<W, R>();
-  static bool configured = false;
-  if (!configured) {
+  if (wg_func_configured(reinterpret_cast<const void*>(kern), smem) < (long long)smem) {
     WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    configured = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CL, 1, 1);
@@ -773,12 +789,9 @@ static int trsm_rec(const double* L, long long ldl, double* B, long long ldb, in
   }
   if (w <= 256) {
     const size_t smem = (size_t)((w + 31) & ~31) * TLDB * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
-      WG_CUDA(cudaFuncSetAttribute(lu_trsm_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(256 * TLDB * sizeof(double))));
-      configured = true;
-    }
+    const size_t smemMax = 256 * TLDB * sizeof(double);
+    if (wg_func_configured(reinterpret_cast<const void*>(lu_trsm_strip_kernel), smemMax) < (long long)smemMax)
+      WG_CUDA(cudaFuncSetAttribute(lu_trsm_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMax));
     WG_CUDA(launch_prio(lu_trsm_strip_kernel, dim3(wg_cdiv(ncols, TSC)), dim3(256), smem, st, L, ldl, B, ldb, w, ncols));
     WG_LAUNCH_CHECK();
     return WG_OK;
@@ -951,7 +964,9 @@ __global__ void __launch_bounds__(256) lu_trisolve_step_kernel(const double* __r
 // ------------------------------------------------------------------ host-side plan / scheduler
 struct LuPlan {
   int n = 0;
-  int nb = 256;
+  LuTuning t;              // this plan's scheduling knobs
+  long long tuneEpoch = 0; // epoch of the process-wide defaults this plan last adopted
+  bool tunePinned = false; // tuned individually: ignores later changes of the defaults
   int maxCL = 16;
   int *grpSrcTop = nullptr, *grpBDst = nullptr;
   int *permSrcTop = nullptr, *permBDst = nullptr, *permBSrc = nullptr, *permNBot = nullptr;
@@ -1022,11 +1037,24 @@ static int probe_max_cluster() {
   return 1;
 }
 
+static int lu_plan_fill(LuPlan* p, int n);
+
 int lu_plan_create(int n, LuPlan** out) {
   WG_REQUIRE(n > 0 && out != nullptr, "lu_plan_create: bad arguments");
   LuPlan* p = new LuPlan();
+  const int rc = lu_plan_fill(p, n);
+  if (rc) {
+    lu_plan_destroy(p);   // frees whatever was allocated before the failure
+    return rc;
+  }
+  *out = p;
+  return WG_OK;
+}
+
+static int lu_plan_fill(LuPlan* p, int n) {
   p->n = n;
-  p->nb = g_nb;
+  p->t = g_tune;
+  p->tuneEpoch = g_tune_epoch;
   p->maxCL = probe_max_cluster<16, 2>();
   const int npanels = wg_cdiv(n, 32) + 1;
   WG_CUDA(cudaMalloc(&p->grpSrcTop, sizeof(int) * n));
@@ -1062,14 +1090,19 @@ int lu_plan_create(int n, LuPlan** out) {
   }
   WG_CUDA(cudaEventCreateWithFlags(&p->evFork, cudaEventDisableTiming));
   WG_CUDA(cudaEventCreateWithFlags(&p->evJoin, cudaEventDisableTiming));
-  *out = p;
   return WG_OK;
+}
+
+static void lu_drop_graphs(LuPlan* p) {
+  if (p->exec) cudaGraphExecDestroy(p->exec);
+  if (p->solveExec) cudaGraphExecDestroy(p->solveExec);
+  p->exec = nullptr;
+  p->solveExec = nullptr;
 }
 
 void lu_plan_destroy(LuPlan* p) {
   if (!p) return;
-  if (p->exec) cudaGraphExecDestroy(p->exec);
-  if (p->solveExec) cudaGraphExecDestroy(p->solveExec);
+  lu_drop_graphs(p);
   if (p->panelStream) cudaStreamDestroy(p->panelStream);
   if (p->bulkHiStream) cudaStreamDestroy(p->bulkHiStream);
   if (p->farStream) cudaStreamDestroy(p->farStream);
@@ -1164,7 +1197,7 @@ static int panel_rec(FactorCtx& c, int c0, int w, int pc0, int pc1) {
 
 // brackets one trailing-update GEMM with CUDA events when profiling is on (never during graph capture)
 static void prof_mark(LuPlan* p, cudaStream_t st, double flops, bool begin) {
-  if (!g_profile || g_use_graph) return;
+  if (!g_profile || p->t.useGraph) return;
   const size_t idx = 2 * (size_t)p->profCount + (begin ? 0 : 1);
   while (p->profEv.size() <= idx) {
     cudaEvent_t e;
@@ -1181,7 +1214,7 @@ static void prof_mark(LuPlan* p, cudaStream_t st, double flops, bool begin) {
 }
 
 static void trace_mark(LuPlan* p, cudaStream_t st, int step, int slot) {
-  if (!g_trace || g_use_graph) return;
+  if (!g_trace || p->t.useGraph) return;
   const size_t idx = 5 * (size_t)step + slot;
   while (p->traceEv.size() <= idx) {
     cudaEvent_t e;
@@ -1222,14 +1255,16 @@ int lu_profile_read(LuPlan* p, double* ms, double* flops, int* count) {
   return WG_OK;
 }
 
-static int g_force_wb = 0;  // developer knob: force the leaf width class (4: the 8-rows-per-thread variant)
-void lu_set_force_wb(int wb) { g_force_wb = wb; }
+void lu_set_force_wb(int wb) {
+  g_tune.forceWb = wb;
+  ++g_tune_epoch;
+}
 
 static int panel_width_class(LuPlan* p, int m) {
-  if (g_force_wb == 2 && m <= p->maxCL * PT * 16) return 2;
-  if (g_force_wb == 4 && m <= p->maxCL * PT * 8) return 4;
-  if (g_force_wb == 8 && m <= p->maxCL * PT * 4) return 8;
-  if (g_leaf32 && m <= p->maxCL * PT) return 32;
+  if (p->t.forceWb == 2 && m <= p->maxCL * PT * 16) return 2;
+  if (p->t.forceWb == 4 && m <= p->maxCL * PT * 8) return 4;
+  if (p->t.forceWb == 8 && m <= p->maxCL * PT * 4) return 8;
+  if (p->t.leaf32 && m <= p->maxCL * PT) return 32;
   if (m <= p->maxCL * PT * 2) return 16;
   if (m <= p->maxCL * PT * 4) return 8;
   if (m <= p->maxCL * PT * 8) return 4;
@@ -1237,10 +1272,35 @@ static int panel_width_class(LuPlan* p, int m) {
   return 0;
 }
 
-static int g_hi_rest = 8192;  // bulk work moves to the high-priority bulk stream once the trailing matrix is this small
-static int g_split = 50;      // two bulk streams while the trailing matrix is large: far part starts at this % of n (0: off)
-void lu_set_split(int on) { g_split = on == 1 ? 50 : on; }
-void lu_set_bulk_hi(int rest) { g_hi_rest = rest; }
+void lu_set_split(int on) {
+  g_tune.split = on == 1 ? 50 : on;
+  ++g_tune_epoch;
+}
+void lu_set_bulk_hi(int rest) {
+  g_tune.hiRest = rest;
+  ++g_tune_epoch;
+}
+
+static void lu_drop_graphs(LuPlan* p);
+
+// adopt changed process-wide defaults (unless this plan was tuned individually); captured graphs are dropped
+static void lu_sync_tuning(LuPlan* p) {
+  if (p->tunePinned || p->tuneEpoch == g_tune_epoch) return;
+  p->t = g_tune;
+  p->tuneEpoch = g_tune_epoch;
+  lu_drop_graphs(p);
+}
+
+// per-plan tuning; a negative value keeps the current setting
+void lu_plan_set_tuning(LuPlan* p, int nb, int use_graph, int lookahead, int split, int hi_rest) {
+  if (nb >= 32 && nb <= 256 && nb % 16 == 0) p->t.nb = nb;
+  if (use_graph >= 0) p->t.useGraph = use_graph;
+  if (lookahead >= 0) p->t.lookahead = lookahead;
+  if (split >= 0) p->t.split = split == 1 ? 50 : split;
+  if (hi_rest >= 0) p->t.hiRest = hi_rest;
+  p->tunePinned = true;
+  lu_drop_graphs(p);
+}
 
 static int apply_perm(LuPlan* p, double* A, long long lda, ColMap cm, int k, int nb, int pnl, double* S, double* S2,
                       int vecA, cudaStream_t st) {
@@ -1257,12 +1317,10 @@ static int apply_perm(LuPlan* p, double* A, long long lda, ColMap cm, int k, int
 }
 
 static int trisolve_configure() {
-  static bool configured = false;
-  if (!configured) {
-    const size_t smem = (size_t)(TS_BS * TS_LD + 2 * TS_BS) * sizeof(double);
+  const size_t smem = (size_t)(TS_BS * TS_LD + 2 * TS_BS) * sizeof(double);
+  if (wg_func_configured(reinterpret_cast<const void*>(lu_trisolve_step_kernel<false>), smem) < (long long)smem) {
     WG_CUDA(cudaFuncSetAttribute(lu_trisolve_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WG_CUDA(cudaFuncSetAttribute(lu_trisolve_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   return WG_OK;
 }
@@ -1316,10 +1374,10 @@ static int rhs_panel(LuPlan* p, const double* LU, long long lda, int k, int nb, 
 // the bulk is throughput bound, so one hides behind the other; once the trailing matrix is small the bulk
 // also moves to a high-priority stream so that a second system sharing the GPU cannot starve this one's tail.
 static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStream_t st) {
-  const int n = p->n, NB = p->nb;
+  const int n = p->n, NB = p->t.nb;
   FactorCtx c{p, A, lda, ipiv, info, st, 16, 0};
   c.vecA = (lda % 2 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0);
-  const bool look = g_lookahead != 0;
+  const bool look = p->t.lookahead != 0;
   WG_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
   if (panel_width_class(p, n) == 0) {
     wg_set_error("lu_factor: n=%d exceeds the leaf-panel capacity (%d rows) of this build", n,
@@ -1342,7 +1400,7 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
   // [.., X) stays on the bulk stream (the chain depends on it), the far part [X, n) runs one step behind on
   // its own low-priority stream, so the latency-bound interchange + TRSM of one part overlaps the other's GEMM.
   const int npan = wg_cdiv(n, NB);
-  const int X = (look && g_split > 0 && g_split < 100 && p->Sf && n >= 8192) ? NB * ((npan * g_split + 99) / 100) : n;
+  const int X = (look && p->t.split > 0 && p->t.split < 100 && p->Sf && n >= 8192) ? NB * ((npan * p->t.split + 99) / 100) : n;
   cudaStream_t fs = p->farStream;
   bool farOn = false;
   bool panelDone = false;  // panel [k, k+nb) already factored by the chain of the previous step
@@ -1382,7 +1440,7 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
       prof_mark(p, bs, 0.0, false);
       continue;
     }
-    if (bs == st && rest <= g_hi_rest) {
+    if (bs == st && rest <= p->t.hiRest) {
       WG_CUDA(cudaEventRecord(p->evPhase, st));
       WG_CUDA(cudaStreamWaitEvent(p->bulkHiStream, p->evPhase, 0));
       bs = p->bulkHiStream;
@@ -1482,7 +1540,8 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
 int lu_factor(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStream_t st, double* rhs) {
   WG_REQUIRE(p && A && ipiv && info && lda >= p->n, "lu_factor: bad arguments");
   p->rhs = rhs;   // non-null: the forward solve L y = P rhs rides along (finish with lu_solve(..., backwardOnly))
-  if (!g_use_graph) return factor_enqueue(p, A, lda, ipiv, info, st);
+  lu_sync_tuning(p);
+  if (!p->t.useGraph) return factor_enqueue(p, A, lda, ipiv, info, st);
   if (!p->exec || p->gA != A || p->glda != lda || p->gipiv != ipiv || p->ginfo != info || p->grhs != rhs) {
     if (p->exec) {
       cudaGraphExecDestroy(p->exec);
@@ -1520,7 +1579,8 @@ static int solve_enqueue(LuPlan* p, const double* LU, long long lda, double* b, 
 
 int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st, bool backwardOnly) {
   WG_REQUIRE(p && LU && b && lda >= p->n, "lu_solve: bad arguments");
-  if (!g_use_graph) return solve_enqueue(p, LU, lda, b, st, backwardOnly);
+  lu_sync_tuning(p);
+  if (!p->t.useGraph) return solve_enqueue(p, LU, lda, b, st, backwardOnly);
   if (!p->solveExec || p->sLU != LU || p->slda != lda || p->sb != b || p->sBackOnly != (int)backwardOnly) {
     if (p->solveExec) {
       cudaGraphExecDestroy(p->solveExec);
@@ -1554,7 +1614,7 @@ int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t
 }
 
 static int solve_enqueue(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st, bool backwardOnly) {
-  const int n = p->n, NB = p->nb;
+  const int n = p->n, NB = p->t.nb;
   int rcc = trisolve_configure();
   if (rcc) return rcc;
   const size_t smem = (size_t)(TS_BS * TS_LD + 2 * TS_BS) * sizeof(double);

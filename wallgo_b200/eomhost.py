@@ -304,7 +304,16 @@ def findPlasmaProfile(eom, c1, c2, velocityMid, fields, dPhidz, offEquilDeltas, 
 def install(eomClass):
     """Rebind `findPlasmaProfile` of the given EOM class (WallGo.EOM) to the vector form."""
     def _vectorised(self, c1, c2, velocityMid, fields, dPhidz, offEquilDeltas, Tplus, Tminus):
-        return findPlasmaProfile(self, c1, c2, velocityMid, fields, dPhidz, offEquilDeltas, Tplus, Tminus)
+        # The lock-step form needs an effective potential that accepts one temperature PER field point.  Some
+        # user potentials do not (the InertDoublet example's daisy-resummed masses broadcast a scalar
+        # temperature only, inertDoubletModel.py:583-585): for those the reference's own per-point routine runs.
+        if not getattr(self, "_profileVectorUnsupported", False):
+            try:
+                return findPlasmaProfile(self, c1, c2, velocityMid, fields, dPhidz, offEquilDeltas, Tplus, Tminus)
+            except (ValueError, TypeError, IndexError):
+                self._profileVectorUnsupported = True
+        return eomClass._findPlasmaProfileReference(self, c1, c2, velocityMid, fields, dPhidz, offEquilDeltas,
+                                                    Tplus, Tminus)
     _vectorised.__doc__ = findPlasmaProfile.__doc__
     eomClass._findPlasmaProfileReference = eomClass.findPlasmaProfile
     eomClass.findPlasmaProfile = _vectorised

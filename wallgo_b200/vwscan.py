@@ -145,10 +145,12 @@ def defaultWorkers(worldSize: int = 1) -> int:
     return max(1, min(8, cores // max(gpus, worldSize) - 1))
 
 
-def scanLocal(manager, settings, vws, indices, workers=None, concurrency=None, stats=None):
+def scanLocal(manager, settings, vws, indices, workers=None, concurrency=None, stats=None, budgetSeconds=None):
     """The points `indices` of `vws` on this process' GPU.  Returns [len(indices), width] rows in the order
     of `indices`.  `manager` is a WallGoManager after setupThermodynamicsHydrodynamics with
-    wallgo_b200.dropin installed (dropin.install()); `settings` its WallSolverSettings."""
+    wallgo_b200.dropin installed (dropin.install()); `settings` its WallSolverSettings.
+    budgetSeconds: stop handing out points after this long (points are handed out in the order of `indices`;
+    rows of points that were not started stay NaN and stats["done"] counts the finished ones)."""
     import multiprocessing as mp
     from multiprocessing.connection import wait as mpWait
 
@@ -159,16 +161,23 @@ def scanLocal(manager, settings, vws, indices, workers=None, concurrency=None, s
     ws = manager.setupWallSolver(settings)          # the server's solver: holds the collision tensor
     solver = ws.boltzmannSolver
     nF, P, M = ws.eom.nbrFields, len(solver.offEqParticles), solver.grid.M
-    rows = np.zeros((len(indices), rowWidth(nF, P, M)))
+    rows = np.full((len(indices), rowWidth(nF, P, M)), np.nan)
+    tStart = time.perf_counter()
+
+    def overBudget():
+        return budgetSeconds is not None and time.perf_counter() - tStart > budgetSeconds
+
     if workers is None:
         workers = defaultWorkers()
     workers = min(int(workers), len(indices))
-    stats.update(workers=workers, host_s=0.0, solves=0)
+    stats.update(workers=workers, host_s=0.0, solves=0, done=0)
     if not indices:
         return rows
     if workers <= 0:
         wp0 = _initialWallParams(WallGo, ws)
         for k, i in enumerate(indices):
+            if overBudget():
+                break
             t0 = time.perf_counter()
             calls = [0]
             orig = solver.getDeltas
@@ -185,6 +194,7 @@ def scanLocal(manager, settings, vws, indices, workers=None, concurrency=None, s
             rows[k] = _row(out, calls[0])
             stats["host_s"] += time.perf_counter() - t0
             stats["solves"] += calls[0]
+            stats["done"] += 1
         return rows
 
     # ---- solve server + forked host workers
@@ -202,10 +212,11 @@ def scanLocal(manager, settings, vws, indices, workers=None, concurrency=None, s
     todo = list(enumerate(indices))[::-1]
     waiting = []                      # solve requests that found no free slot: (conn, raw)
     done = 0
+    started = 0
     tServerBusy = 0.0
     try:
         live = set(conns)
-        while done < len(indices):
+        while live:
             ready = mpWait(list(live), timeout=0.0004 if (pool.busy() or waiting) else 0.05)
             for c in ready:
                 msg = c.recv()
@@ -220,9 +231,10 @@ def scanLocal(manager, settings, vws, indices, workers=None, concurrency=None, s
                         stats["host_s"] += secs
                         stats["solves"] += int(row[1 + 2 * nF])
                         done += 1
-                    if todo:
+                    if todo and not overBudget():
                         k, i = todo.pop()
                         c.send(("point", k, float(vws[i])))
+                        started += 1
                     else:
                         c.send(("stop",))
                         live.discard(c)
@@ -248,12 +260,15 @@ def scanLocal(manager, settings, vws, indices, workers=None, concurrency=None, s
             if pr.is_alive():
                 pr.terminate()
     stats["server_s"] = tServerBusy
+    stats["done"] = done
+    assert done == started
     return rows
 
 
-def scanWallPressure(manager, settings, vws, workers=None, concurrency=None, stats=None):
+def scanWallPressure(manager, settings, vws, workers=None, concurrency=None, stats=None, budgetSeconds=None):
     """All points of `vws`, sharded round-robin over the ranks of the default process group (one per GPU),
-    gathered with ONE all_gather.  Every rank returns the full [len(vws), width] table."""
+    gathered with ONE all_gather.  Every rank returns the full [len(vws), width] table (NaN rows: points a
+    rank did not start within budgetSeconds)."""
     import torch.distributed as dist  # pylint: disable=import-outside-toplevel
 
     from . import scan  # pylint: disable=import-outside-toplevel
@@ -263,5 +278,6 @@ def scanWallPressure(manager, settings, vws, workers=None, concurrency=None, sta
     mine = scan.shardPoints(len(vws), rank, world)
     if workers is None:
         workers = defaultWorkers(world)
-    rows = scanLocal(manager, settings, vws, mine, workers=workers, concurrency=concurrency, stats=stats)
+    rows = scanLocal(manager, settings, vws, mine, workers=workers, concurrency=concurrency, stats=stats,
+                     budgetSeconds=budgetSeconds)
     return scan.gatherPoints(rows, len(vws), rows.shape[1])
