@@ -279,7 +279,32 @@ def reference_scan(a):
                         f"{len(idx)} of the {a.scan_points} scan points, host cores {os.cpu_count()}"}
 
 
-def run_scan(a, world, rank, local):
+def prepare_scan(a, world):
+    """Host side of the scan, done BEFORE this process initialises CUDA: the reference's WallGoManager for the
+    scan model (phase tracing, hydrodynamics: tens of seconds of host work) and the forked host workers, which
+    then idle on their pipes until the scan starts."""
+    import contextlib
+
+    from oracle import ref_drivers as rd
+    if rd.reference_root() is None:
+        return None
+    with contextlib.redirect_stdout(sys.stderr):
+        rd.load_reference()
+        from wallgo_b200 import dropin, vwscan
+
+        P, M, N = SCAN_MODELS[a.scan_model]
+        cls = dropin.install(vectoriseEOM=True)
+        rd.patch_load_collisions(cls)      # shipped .hdf5 are Git-LFS pointers: relaxation-time tensor, both arms
+        t0 = time.perf_counter()
+        manager, settings, _ = rd.build_manager(a.scan_model, M, N)
+        setup = time.perf_counter() - t0
+        vws = scan_velocities(manager, a.scan_points)
+        nworkers = vwscan.defaultWorkers(world) if a.scan_workers < 0 else a.scan_workers
+        hostWorkers = vwscan.HostWorkers(manager, settings, nworkers) if nworkers > 0 else None
+    return {"manager": manager, "settings": settings, "vws": vws, "setup_s": setup, "hostWorkers": hostWorkers}
+
+
+def run_scan(a, world, rank, local, prep=None):
     """Second half of the BASELINE metric: wall-velocity scan points/s, a point being what SURVEY.md section
     8(d)(2) defines: one `EOM.wallPressure(vw_i, wallParams0, boltzmannResultsInput=None)` of the UNMODIFIED
     reference wall solver (equationOfMotion.py:786-1131; ~4 Boltzmann solves + host loop) on the InertDoublet
@@ -295,20 +320,17 @@ def run_scan(a, world, rank, local):
     from oracle import ref_drivers as rd
     if rd.reference_root() is None:
         return run_scan_boltzmann_only(a, world, rank, local)
+    if prep is None and a.scan_points > 0:
+        raise RuntimeError("scan preparation failed (see stderr)")
+    prep = prep if prep is not None else prepare_scan(a, world)
+    P, M, N = SCAN_MODELS[a.scan_model]
     with contextlib.redirect_stdout(sys.stderr):
-        WallGo = rd.load_reference()
-        from wallgo_b200 import _lib, dropin, vwscan
+        from wallgo_b200 import _lib, vwscan
 
-        P, M, N = SCAN_MODELS[a.scan_model]
-        cls = dropin.install(vectoriseEOM=True)
-        rd.patch_load_collisions(cls)      # shipped .hdf5 are Git-LFS pointers: relaxation-time tensor, both arms
-        t0 = time.perf_counter()
-        manager, settings, _ = rd.build_manager(a.scan_model, M, N)
-        setup = time.perf_counter() - t0
-        vws = scan_velocities(manager, a.scan_points)
-        workers = vwscan.defaultWorkers(world) if a.scan_workers < 0 else a.scan_workers
-        # warm-up: engines, buffers and CUDA graphs of every slot; forks nothing
-        vwscan.scanLocal(manager, settings, vws, [rank % len(vws)], workers=0)
+        manager, settings, vws, setup = prep["manager"], prep["settings"], prep["vws"], prep["setup_s"]
+        workers = len(prep["hostWorkers"]) if prep["hostWorkers"] is not None else 0
+        # warm-up: engines, buffers and CUDA graphs of every slot (in-process, one point + one batch)
+        vwscan.warmUp(manager, settings, float(vws[rank % len(vws)]))
         lib = _lib.load()
         if world > 1:
             dist.barrier()
@@ -317,7 +339,7 @@ def run_scan(a, world, rank, local):
         stats = {}
         t0 = time.perf_counter()
         table = vwscan.scanWallPressure(manager, settings, vws, workers=workers, stats=stats,
-                                        budgetSeconds=a.scan_budget_s)
+                                        budgetSeconds=a.scan_budget_s, hostWorkers=prep["hostWorkers"])
         torch.cuda.synchronize()
         el = time.perf_counter() - t0
         launches = lib.wg_launch_count() - l0
@@ -412,6 +434,13 @@ def run_b200(a):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    scan_prep = None
+    if a.scan_points > 0:
+        try:
+            scan_prep = prepare_scan(a, world)      # forks the scan's host workers before CUDA is initialised
+        except Exception:
+            import traceback
+            traceback.print_exc()
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -608,7 +637,7 @@ def run_b200(a):
     scan_line = None
     if a.scan_points > 0:
         try:
-            scan_line = run_scan(a, world, rank, local)
+            scan_line = run_scan(a, world, rank, local, scan_prep)
         except Exception as exc:   # the secondary metric must not take the headline line down with it
             import traceback
             traceback.print_exc()

@@ -82,9 +82,13 @@ __global__ void wg_kron_kernel(int N1, const double* __restrict__ X, const doubl
 
 // ============================================================================ per-solve prologue
 // profiles = [ T(M+1) | v(M+1) | msq(P x (M+1)) | dxidchi(M-1) ]; derivs = [ dT | dv | dmsq ] on M+1 nodes
+// Batches: blockIdx.y (blockIdx.x for the one-CTA kernels, blockIdx.z for the assembly) is the system of a
+// strided batch of independent systems processed in lock step; per-system arrays are contiguous ([B][...]).
 __global__ void wg_profile_deriv_kernel(int M, int P, const double* __restrict__ DchiFull,
-                                        const double* __restrict__ prof, double* __restrict__ derivs) {
+                                        const double* __restrict__ prof, double* __restrict__ derivs, int nprof) {
   const int L = M + 1;
+  prof += (long long)blockIdx.x * nprof;
+  derivs += (long long)blockIdx.x * (2 + P) * L;
   for (int e = threadIdx.x; e < (2 + P) * L; e += blockDim.x) {
     const int f = e / L, j = e % L;
     const double* fv = prof + f * L;
@@ -99,10 +103,21 @@ __global__ void wg_rows_kernel(BzDims d, const double* __restrict__ prof, const 
                                const double* __restrict__ pz, const double* __restrict__ pp,
                                const double* __restrict__ dpzdrz, const double* __restrict__ stat, double vw,
                                double collMult, double liouScale, double* __restrict__ w1, double* __restrict__ w2,
-                               double* __restrict__ cT2, double* __restrict__ S) {
+                               double* __restrict__ cT2, double* __restrict__ S, const double* __restrict__ vwArr,
+                               int nprof, long long sV) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= d.n) return;
   const int L = d.M + 1;
+  {
+    const long long bz = blockIdx.y;
+    prof += bz * nprof;
+    derivs += bz * (2 + d.P) * L;
+    w1 += bz * d.n;
+    w2 += bz * d.n;
+    cT2 += bz * d.M1;
+    S += bz * sV;
+    if (vwArr) vw = vwArr[bz];
+  }
   const int gmm = r % d.N1, bt = (r / d.N1) % d.N1, al = (r / d.q) % d.M1, a = r / (d.q * d.M1);
   const double T = prof[al + 1], v = prof[L + al + 1], msq = prof[(2 + a) * L + al + 1];
   const double dxidchi = prof[(2 + d.P) * L + al];
@@ -154,9 +169,13 @@ __global__ void __launch_bounds__(512, WG_ASM_MINB) wg_assemble_kernel(BzDims d,
                                                           const double* __restrict__ w1,
                                                           const double* __restrict__ w2,
                                                           const double* __restrict__ cT2,
-                                                          double* __restrict__ A, long long lda) {
+                                                          double* __restrict__ A, long long lda, long long sA) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int q = d.q, M1 = d.M1, P = d.P;
+  w1 += (long long)blockIdx.z * d.n;
+  w2 += (long long)blockIdx.z * d.n;
+  cT2 += (long long)blockIdx.z * M1;
+  A += (long long)blockIdx.z * sA;
   double* K1s = reinterpret_cast<double*>(smraw);  // [R][q]
   double* K2s = K1s + R * q;                       // [R][q]
   double* Cs = K2s + R * q;                        // [R][P*q]
@@ -274,6 +293,8 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 __global__ void wg_spectra_kernel(BzDims d, const double* __restrict__ c, double* __restrict__ spectra) {
   __shared__ double red[32];
   const int bin = blockIdx.x;
+  c += (long long)blockIdx.y * d.n;
+  spectra += (long long)blockIdx.y * (d.M1 + 2 * d.N1);
   const int M1 = d.M1, N1 = d.N1, q = d.q;
   double s = 0.0;
   if (bin < M1) {
@@ -294,9 +315,16 @@ __global__ void wg_spectra_kernel(BzDims d, const double* __restrict__ c, double
 // zero the truncated tails in place and reduce the truncation-error sums:
 //   err[a*4+0] = sum |c| over the kept box, err[a*4+1..3] = sum |c| on the last kept chi / pz / pp slice
 __global__ void wg_truncate_kernel(BzDims d, double* __restrict__ c, int keepM, int keepN1, int keepN2,
-                                   double* __restrict__ err) {
+                                   double* __restrict__ err, const int* __restrict__ keepArr) {
   __shared__ double red[32];
   const int a = blockIdx.x;
+  c += (long long)blockIdx.y * d.n;
+  err += (long long)blockIdx.y * 4 * d.P;
+  if (keepArr) {   // per-system keep counts of a batch
+    keepM = keepArr[3 * blockIdx.y];
+    keepN1 = keepArr[3 * blockIdx.y + 1];
+    keepN2 = keepArr[3 * blockIdx.y + 2];
+  }
   const int M1 = d.M1, N1 = d.N1, q = d.q;
   double tot = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
   for (int e = threadIdx.x; e < M1 * q; e += blockDim.x) {
@@ -330,9 +358,12 @@ __global__ void wg_moments_kernel(BzDims d, const double* __restrict__ card, con
                                   const double* __restrict__ rz, const double* __restrict__ rp,
                                   const double* __restrict__ pz, const double* __restrict__ pp,
                                   const double* __restrict__ dpzdrz, const double* __restrict__ dppdrp,
-                                  double* __restrict__ deltas) {
+                                  double* __restrict__ deltas, int nprof) {
   __shared__ double red[32];
   const int a = blockIdx.x / d.M1, al = blockIdx.x % d.M1;
+  card += (long long)blockIdx.y * d.n;
+  prof += (long long)blockIdx.y * nprof;
+  deltas += (long long)blockIdx.y * 4 * d.P * d.M1;
   const int N1 = d.N1, q = d.q, L = d.M + 1;
   const double msq = prof[(2 + a) * L + al + 1];
   const double* f = card + ((long long)a * d.M1 + al) * q;
@@ -496,14 +527,16 @@ void bz_set_asm_wide(int on) { g_asm_wide = on; }
 
 int bz_assemble(const BzDims& d, const BzStatic& s, const double* prof, double vw, double collMult, int parts,
                 double* derivs, double* w1, double* w2, double* cT2, double* A, long long lda, double* S,
-                cudaStream_t st) {
+                cudaStream_t st, const BzBatch& bb) {
   WG_REQUIRE(d.q % 4 == 0, "assemble: (N-1)^2 must be a multiple of 4 (N odd)");
-  WG_REQUIRE(lda % 2 == 0 && reinterpret_cast<uintptr_t>(A) % 16 == 0, "assemble: A must be 16B aligned, lda even");
-  wg_profile_deriv_kernel<<<1, 256, 0, st>>>(d.M, d.P, s.DchiFull, prof, derivs);
+  WG_REQUIRE(lda % 2 == 0 && bb.sA % 2 == 0 && reinterpret_cast<uintptr_t>(A) % 16 == 0,
+             "assemble: A must be 16B aligned, lda and the batch stride even");
+  const int nprof = (2 + d.P) * (d.M + 1) + d.M1;
+  wg_profile_deriv_kernel<<<bb.count, 256, 0, st>>>(d.M, d.P, s.DchiFull, prof, derivs, nprof);
   WG_LAUNCH_CHECK();
-  wg_rows_kernel<<<wg_cdiv(d.n, 256), 256, 0, st>>>(d, prof, derivs, s.pz, s.pp, s.dpzdrz, s.stat, vw,
-                                                   (parts & 2) ? collMult : 0.0, (parts & 1) ? 1.0 : 0.0, w1, w2,
-                                                   cT2, S);
+  wg_rows_kernel<<<dim3(wg_cdiv(d.n, 256), bb.count), 256, 0, st>>>(d, prof, derivs, s.pz, s.pp, s.dpzdrz, s.stat, vw,
+                                                                   (parts & 2) ? collMult : 0.0, (parts & 1) ? 1.0 : 0.0,
+                                                                   w1, w2, cT2, S, bb.vwArr, nprof, bb.sV);
   WG_LAUNCH_CHECK();
   constexpr int R = 4;
   const size_t smem = ((size_t)R * d.q * (2 + d.P) + 2 * d.M1) * sizeof(double);
@@ -516,16 +549,16 @@ int bz_assemble(const BzDims& d, const BzStatic& s, const double* prof, double v
     WG_CUDA(cudaFuncSetAttribute(wg_assemble_kernel<R, 4>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared));
   }
-  dim3 grid(d.q / R, d.P * d.M1);
-  const bool wide = g_asm_wide && d.q % 4 == 0 && lda % 4 == 0 && reinterpret_cast<uintptr_t>(A) % 32 == 0;
+  dim3 grid(d.q / R, d.P * d.M1, bb.count);
+  const bool wide = g_asm_wide && d.q % 4 == 0 && lda % 4 == 0 && bb.sA % 4 == 0 && reinterpret_cast<uintptr_t>(A) % 32 == 0;
   const int per = wide ? 4 : 2;
   int threads = ((d.q / per + 31) / 32) * 32;
   if (threads > 512) threads = 512;
   if (threads < 64) threads = 64;
   if (wide)
-    wg_assemble_kernel<R, 4><<<grid, threads, smem, st>>>(d, s.K1, s.K2, s.Coll, s.Tchi, s.Dchi, w1, w2, cT2, A, lda);
+    wg_assemble_kernel<R, 4><<<grid, threads, smem, st>>>(d, s.K1, s.K2, s.Coll, s.Tchi, s.Dchi, w1, w2, cT2, A, lda, bb.sA);
   else
-    wg_assemble_kernel<R, 2><<<grid, threads, smem, st>>>(d, s.K1, s.K2, s.Coll, s.Tchi, s.Dchi, w1, w2, cT2, A, lda);
+    wg_assemble_kernel<R, 2><<<grid, threads, smem, st>>>(d, s.K1, s.K2, s.Coll, s.Tchi, s.Dchi, w1, w2, cT2, A, lda, bb.sA);
   WG_LAUNCH_CHECK();
   return WG_OK;
 }
@@ -540,21 +573,24 @@ int bz_apply_axis(const double* in, double* out, const double* Mat, int outer, i
   return WG_OK;
 }
 
-int bz_spectra(const BzDims& d, const double* c, double* spectra, cudaStream_t st) {
-  wg_spectra_kernel<<<d.M1 + 2 * d.N1, 256, 0, st>>>(d, c, spectra);
+int bz_spectra(const BzDims& d, const double* c, double* spectra, cudaStream_t st, int batch) {
+  wg_spectra_kernel<<<dim3(d.M1 + 2 * d.N1, batch), 256, 0, st>>>(d, c, spectra);
   WG_LAUNCH_CHECK();
   return WG_OK;
 }
 
-int bz_truncate(const BzDims& d, double* c, int keepM, int keepN1, int keepN2, double* err, cudaStream_t st) {
-  wg_truncate_kernel<<<d.P, 256, 0, st>>>(d, c, keepM, keepN1, keepN2, err);
+int bz_truncate(const BzDims& d, double* c, int keepM, int keepN1, int keepN2, double* err, cudaStream_t st, int batch,
+                const int* keepArr) {
+  wg_truncate_kernel<<<dim3(d.P, batch), 256, 0, st>>>(d, c, keepM, keepN1, keepN2, err, keepArr);
   WG_LAUNCH_CHECK();
   return WG_OK;
 }
 
 int bz_moments(const BzDims& d, const BzStatic& s, const double* card, const double* prof, double* deltas,
-               cudaStream_t st) {
-  wg_moments_kernel<<<d.P * d.M1, 128, 0, st>>>(d, card, prof, s.rz, s.rp, s.pz, s.pp, s.dpzdrz, s.dppdrp, deltas);
+               cudaStream_t st, int batch) {
+  const int nprof = (2 + d.P) * (d.M + 1) + d.M1;
+  wg_moments_kernel<<<dim3(d.P * d.M1, batch), 128, 0, st>>>(d, card, prof, s.rz, s.rp, s.pz, s.pp, s.dpzdrz, s.dppdrp,
+                                                            deltas, nprof);
   WG_LAUNCH_CHECK();
   return WG_OK;
 }

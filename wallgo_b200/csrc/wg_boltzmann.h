@@ -22,6 +22,14 @@ struct BzStatic {
   double* Coll;                                       // [(P q)^2]  C[a,bg,b,jk], solver basis
 };
 
+// strided batch of independent systems in lock step (count 1: one system)
+struct BzBatch {
+  int count = 1;
+  long long sA = 0;               // doubles between consecutive operators
+  long long sV = 0;               // doubles between consecutive source vectors
+  const double* vwArr = nullptr;  // device array of wall velocities, one per system (nullptr: the scalar argument)
+};
+
 int bz_build_basis(const BzDims& d, const double* rz, double* Tchi, double* Dchi, double* DchiFull,
                    double* Trz, double* Drz, double* Trp, cudaStream_t st);
 int bz_build_kron(const BzDims& d, const double* Trz, const double* Drz, const double* Trp, double* K1,
@@ -29,13 +37,14 @@ int bz_build_kron(const BzDims& d, const double* Trz, const double* Drz, const d
 void bz_set_asm_wide(int on);
 int bz_assemble(const BzDims& d, const BzStatic& s, const double* prof, double vw, double collMult, int parts,
                 double* derivs, double* w1, double* w2, double* cT2, double* A, long long lda, double* S,
-                cudaStream_t st);
+                cudaStream_t st, const BzBatch& bb = BzBatch());
 int bz_apply_axis(const double* in, double* out, const double* Mat, int outer, int len, int inner,
                   cudaStream_t st);
-int bz_spectra(const BzDims& d, const double* c, double* spectra, cudaStream_t st);
-int bz_truncate(const BzDims& d, double* c, int keepM, int keepN1, int keepN2, double* err, cudaStream_t st);
+int bz_spectra(const BzDims& d, const double* c, double* spectra, cudaStream_t st, int batch = 1);
+int bz_truncate(const BzDims& d, double* c, int keepM, int keepN1, int keepN2, double* err, cudaStream_t st, int batch = 1,
+                const int* keepArr = nullptr);
 int bz_moments(const BzDims& d, const BzStatic& s, const double* card, const double* prof, double* deltas,
-               cudaStream_t st);
+               cudaStream_t st, int batch = 1);
 int bz_feedback(const BzDims& d, const double* deltas, const double* prof, const double* dofs, const double* dmsq,
                 int F, double u0, double u3, double* out, cudaStream_t st);
 int bz_collision_interp(int P, int nF, int nT, const double* Lz, const double* Lp, const double* src, double* out,

@@ -15,7 +15,12 @@ namespace wg {
 template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES, bool VEC, int MINB = 1>
 __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
 dgemm_sub_kernel(double* __restrict__ C, const double* __restrict__ A, const double* __restrict__ B,
-                 int M, int N, int K, long long ldc, long long lda, long long ldb) {
+                 int M, int N, int K, long long ldc, long long lda, long long ldb, long long sC, long long sA,
+                 long long sB) {
+  // blockIdx.z = system of a strided batch (independent systems in lock step; strides 0 for one system)
+  C += (long long)blockIdx.z * sC;
+  A += (long long)blockIdx.z * sA;
+  B += (long long)blockIdx.z * sB;
   constexpr int NT = WARPS_M * WARPS_N * 32;
   constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
   constexpr int MI = WM / 8, NJ = WN / 8;
@@ -145,20 +150,20 @@ dgemm_sub_kernel(double* __restrict__ C, const double* __restrict__ A, const dou
 
 template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES, int MINB = 1>
 static int launch_cfg(double* C, const double* A, const double* B, int M, int N, int K, long long ldc,
-                      long long lda, long long ldb, bool vec, cudaStream_t st) {
+                      long long lda, long long ldb, bool vec, cudaStream_t st, const GemmBatch& gb) {
   constexpr int NT = WARPS_M * WARPS_N * 32;
   constexpr size_t SMEM = (size_t)STAGES * (BM * (BK + 4) + BK * (BN + 4)) * sizeof(double);
-  dim3 grid(wg_cdiv(N, BN), wg_cdiv(M, BM));
+  dim3 grid(wg_cdiv(N, BN), wg_cdiv(M, BM), gb.count);
   if (vec) {
     auto kern = dgemm_sub_kernel<BM, BN, BK, WARPS_M, WARPS_N, STAGES, true, MINB>;
     if (wg_func_configured(reinterpret_cast<const void*>(kern), SMEM) < (long long)SMEM)
       WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    WG_CUDA(launch_prio(kern, grid, dim3(NT), SMEM, st, C, A, B, M, N, K, ldc, lda, ldb));
+    WG_CUDA(launch_prio(kern, grid, dim3(NT), SMEM, st, C, A, B, M, N, K, ldc, lda, ldb, gb.sC, gb.sA, gb.sB));
   } else {
     auto kern = dgemm_sub_kernel<BM, BN, BK, WARPS_M, WARPS_N, STAGES, false, MINB>;
     if (wg_func_configured(reinterpret_cast<const void*>(kern), SMEM) < (long long)SMEM)
       WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    WG_CUDA(launch_prio(kern, grid, dim3(NT), SMEM, st, C, A, B, M, N, K, ldc, lda, ldb));
+    WG_CUDA(launch_prio(kern, grid, dim3(NT), SMEM, st, C, A, B, M, N, K, ldc, lda, ldb, gb.sC, gb.sA, gb.sB));
   }
   WG_LAUNCH_CHECK();
   return WG_OK;
@@ -168,16 +173,17 @@ static int g_gemm_variant = 1;  // 1: 128x64 tiles, two CTAs per SM (default); 0
 void gemm_set_variant(int v) { g_gemm_variant = v; }
 
 int dgemm_sub(double* C, const double* A, const double* B, int M, int N, int K, long long ldc,
-              long long lda, long long ldb, cudaStream_t st) {
-  if (M <= 0 || N <= 0 || K <= 0) return WG_OK;
-  const bool vec = ((ldc | lda | ldb) % 2 == 0) && (N % 2 == 0) && (K % 2 == 0) &&
+              long long lda, long long ldb, cudaStream_t st, GemmBatch gb) {
+  if (M <= 0 || N <= 0 || K <= 0 || gb.count <= 0) return WG_OK;
+  const bool vec = ((ldc | lda | ldb | gb.sC | gb.sA | gb.sB) % 2 == 0) && (N % 2 == 0) && (K % 2 == 0) &&
                    ((reinterpret_cast<uintptr_t>(C) | reinterpret_cast<uintptr_t>(A) |
                      reinterpret_cast<uintptr_t>(B)) % 16 == 0);
-  if (N > 64 && g_gemm_variant == 1) return launch_cfg<128, 64, 16, 2, 2, 3, 2>(C, A, B, M, N, K, ldc, lda, ldb, vec, st);
-  if (N > 64 && g_gemm_variant == 2) return launch_cfg<128, 128, 32, 2, 4, 3>(C, A, B, M, N, K, ldc, lda, ldb, vec, st);
-  if (N > 64) return launch_cfg<128, 128, 16, 2, 4, 4>(C, A, B, M, N, K, ldc, lda, ldb, vec, st);
-  if (N > 32) return launch_cfg<128, 64, 16, 4, 2, 4>(C, A, B, M, N, K, ldc, lda, ldb, vec, st);
-  return launch_cfg<128, 32, 16, 8, 1, 4>(C, A, B, M, N, K, ldc, lda, ldb, vec, st);
+  // every variant accumulates k in the same order, so the choice of tile never changes a result bit
+  if (N > 64 && g_gemm_variant == 1) return launch_cfg<128, 64, 16, 2, 2, 3, 2>(C, A, B, M, N, K, ldc, lda, ldb, vec, st, gb);
+  if (N > 64 && g_gemm_variant == 2) return launch_cfg<128, 128, 32, 2, 4, 3>(C, A, B, M, N, K, ldc, lda, ldb, vec, st, gb);
+  if (N > 64) return launch_cfg<128, 128, 16, 2, 4, 4>(C, A, B, M, N, K, ldc, lda, ldb, vec, st, gb);
+  if (N > 32) return launch_cfg<128, 64, 16, 4, 2, 4>(C, A, B, M, N, K, ldc, lda, ldb, vec, st, gb);
+  return launch_cfg<128, 32, 16, 8, 1, 4>(C, A, B, M, N, K, ldc, lda, ldb, vec, st, gb);
 }
 
 }  // namespace wg

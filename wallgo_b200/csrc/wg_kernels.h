@@ -4,19 +4,28 @@
 
 namespace wg {
 
+// strided batch of independent products (blockIdx.z); one system: count 1, strides 0
+struct GemmBatch {
+  int count = 1;
+  long long sC = 0, sA = 0, sB = 0;
+};
 // C[MxN] -= A[MxK] * B[KxN], row-major, FP64 tensor cores (wg_gemm.cu)
 int dgemm_sub(double* C, const double* A, const double* B, int M, int N, int K, long long ldc,
-              long long lda, long long ldb, cudaStream_t st);
+              long long lda, long long ldb, cudaStream_t st, GemmBatch gb = GemmBatch());
 
 void gemm_set_variant(int v);
 
 // Blocked LU with partial pivoting (wg_lu.cu)
 struct LuPlan;
-int lu_plan_create(int n, LuPlan** out);
+// batch > 1: every launch serves `batch` independent systems in lock step (strided batch)
+int lu_plan_create(int n, LuPlan** out, int batch = 1);
 void lu_plan_destroy(LuPlan* p);
 // rhs != nullptr: the forward solve of that right-hand side is fused into the factorisation
-int lu_factor(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStream_t st, double* rhs = nullptr);
-int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st, bool backwardOnly = false);
+// strideA / strideRhs: doubles between consecutive systems of the batch (ipiv: n ints, info: 1 int per system)
+int lu_factor(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStream_t st, double* rhs = nullptr,
+              long long strideA = 0, long long strideRhs = 0);
+int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st, bool backwardOnly = false,
+             long long strideA = 0, long long strideB = 0);
 void lu_set_tuning(int nb, int use_graph);
 void lu_plan_set_tuning(LuPlan* p, int nb, int use_graph, int lookahead, int split, int hi_rest);
 void lu_set_debug(long long* dev_buf, int c0);

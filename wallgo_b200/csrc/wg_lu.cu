@@ -80,8 +80,20 @@ void lu_set_lookahead(int on) {
   ++g_tune_epoch;
 }
 
+// Strided batch of independent systems factored in lock step (one kernel launch serves all of them): the
+// system index is a grid dimension of every kernel; one system = count 1.
+struct Bt {
+  int count = 1;
+  long long sA = 0;  // doubles between consecutive operators
+  long long sV = 0;  // doubles between consecutive right-hand sides
+  int sI = 0;        // ints between consecutive systems' row-index tables (ipiv, permutations): n
+  int sP = 0;        // ints between consecutive systems' per-panel counters
+};
+
 struct PanelArgs {
   double* A;
+  long long sA;  // batch strides (system = blockIdx.y)
+  int sI;
   long long lda;
   int n;
   int c0, w;      // leaf columns [c0, c0+w)
@@ -181,10 +193,15 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
   const int c0 = p.c0, w = p.w;
   const int m = p.n - c0;
   const long long lda = p.lda;
-  double* __restrict__ A = p.A;
+  const int bz = blockIdx.y;   // system of the batch: one cluster per system
+  double* __restrict__ A = p.A + (long long)bz * p.sA;
+  int* __restrict__ ipiv = p.ipiv + (long long)bz * p.sI;
+  int* __restrict__ info = p.info + bz;
+  int* __restrict__ grpSrcTop = p.grpSrcTop + (long long)bz * p.sI;
+  int* __restrict__ grpBDst = p.grpBDst + (long long)bz * p.sI;
   const int nLeft = c0 - p.pc0;
   const int ext = nLeft + (p.pc1 - (c0 + w));
-  const bool dbg = p.dbg != nullptr && rank == 0 && tid == 0;
+  const bool dbg = p.dbg != nullptr && rank == 0 && tid == 0 && bz == 0;
   if (dbg) p.dbg[0] = clock64();
 
   if (tid == 0) {
@@ -410,8 +427,8 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
     }
     if (dbg) p.dbg[2 + (j & 15)] = clock64();
     if (rank == 0 && tid == 0) {
-      p.ipiv[dj] = mpos;
-      if (sing && *p.info == 0) *p.info = dj + 1;
+      ipiv[dj] = mpos;
+      if (sing && *info == 0) *info = dj + 1;
     }
   }
   if (dbg) p.dbg[1] = clock64();
@@ -482,9 +499,9 @@ __global__ void __launch_bounds__(PT, 1) lu_panel_leaf_kernel(const PanelArgs p)
   for (int k = 0; k < R; ++k) {
     const bool moved = pos[k] >= 0 && pos[k] != spos[k];
     if (pos[k] >= 0) {
-      if (pos[k] < c0 + w) p.grpSrcTop[pos[k]] = spos[k];
+      if (pos[k] < c0 + w) grpSrcTop[pos[k]] = spos[k];
       if (spos[k] < c0 + w) {
-        p.grpBDst[spos[k]] = (pos[k] >= c0 + w) ? pos[k] : -1;
+        grpBDst[spos[k]] = (pos[k] >= c0 + w) ? pos[k] : -1;
         sm.moveDst[spos[k] - c0] = moved ? pos[k] : -1;  // only threads of CTA 0 own top rows
       }
     }
@@ -523,7 +540,7 @@ static size_t leaf_smem() {
 }
 
 template <int W, int R>
-static int launch_leaf(const PanelArgs& pa, int CL, cudaStream_t st) {
+static int launch_leaf(const PanelArgs& pa, int CL, int batch, cudaStream_t st) {
   auto kern = lu_panel_leaf_kernel<W, R>;
   const size_t smem = leaf_smem<W, R>();
   if (wg_func_configured(reinterpret_cast<const void*>(kern), smem) < (long long)smem) {
@@ -531,7 +548,7 @@ static int launch_leaf(const PanelArgs& pa, int CL, cudaStream_t st) {
     WG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(CL, 1, 1);
+  cfg.gridDim = dim3(CL, batch, 1);
   cfg.blockDim = dim3(PT, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
@@ -559,7 +576,17 @@ static int launch_leaf(const PanelArgs& pa, int CL, cudaStream_t st) {
 __global__ void lu_perm_compose_kernel(int n, int k, int nb, int wb, const int* __restrict__ grpSrcTop,
                                        const int* __restrict__ grpBDst, int* __restrict__ posContent,
                                        int* __restrict__ srcTop, int* __restrict__ bDst,
-                                       int* __restrict__ bSrc, int* __restrict__ nbotOut) {
+                                       int* __restrict__ bSrc, int* __restrict__ nbotOut, int sI, int sP) {
+  {
+    const long long o = (long long)blockIdx.x * sI;   // system of the batch
+    grpSrcTop += o;
+    grpBDst += o;
+    posContent += o;
+    srcTop += o;
+    bDst += o;
+    bSrc += o;
+    nbotOut += (long long)blockIdx.x * sP;
+  }
   __shared__ int topC[256];
   __shared__ int touched[256];
   __shared__ int ntouched;
@@ -614,10 +641,21 @@ struct ColMap {
   int ncol, split, off0, off1;
 };
 
+struct PermBatch {   // strides of the batch (system = blockIdx.z)
+  long long sA, sS;
+  int sI, sP;
+};
+
 __global__ void lu_perm_gather_kernel(const double* __restrict__ A, long long lda, ColMap cm, int k,
                                       const int* __restrict__ srcTop, const int* __restrict__ bSrc,
                                       const int* __restrict__ nbotPtr, double* __restrict__ S,
-                                      double* __restrict__ S2, int vec) {
+                                      double* __restrict__ S2, int vec, PermBatch pb) {
+  A += (long long)blockIdx.z * pb.sA;
+  S += (long long)blockIdx.z * pb.sS;
+  S2 += (long long)blockIdx.z * pb.sS;
+  srcTop += (long long)blockIdx.z * pb.sI;
+  bSrc += (long long)blockIdx.z * pb.sI;
+  nbotPtr += (long long)blockIdx.z * pb.sP;
   const int i = blockIdx.y;
   const int ncol = cm.ncol;
   const int nbot = *nbotPtr;
@@ -648,7 +686,13 @@ __global__ void lu_perm_gather_kernel(const double* __restrict__ A, long long ld
 __global__ void lu_perm_write_kernel(double* __restrict__ A, long long lda, ColMap cm, int k,
                                      const int* __restrict__ srcTop, const int* __restrict__ bDst,
                                      const int* __restrict__ nbotPtr, const double* __restrict__ S,
-                                     const double* __restrict__ S2, int vec) {
+                                     const double* __restrict__ S2, int vec, PermBatch pb) {
+  A += (long long)blockIdx.z * pb.sA;
+  S += (long long)blockIdx.z * pb.sS;
+  S2 += (long long)blockIdx.z * pb.sS;
+  srcTop += (long long)blockIdx.z * pb.sI;
+  bDst += (long long)blockIdx.z * pb.sI;
+  nbotPtr += (long long)blockIdx.z * pb.sP;
   const int i = blockIdx.y;
   const int ncol = cm.ncol;
   const int nbot = *nbotPtr;
@@ -679,7 +723,9 @@ __global__ void lu_perm_write_kernel(double* __restrict__ A, long long lda, ColM
 template <int W>
 __global__ void __launch_bounds__(64) lu_trsm_base_kernel(const double* __restrict__ L, long long ldl,
                                                          double* __restrict__ B, long long ldb, int w,
-                                                         int ncols) {
+                                                         int ncols, long long sA) {
+  L += (long long)blockIdx.y * sA;   // system of the batch
+  B += (long long)blockIdx.y * sA;
   __shared__ double Ls[W][W + 1];
   for (int e = threadIdx.x; e < W * W; e += blockDim.x) {
     const int r = e / W, c = e % W;
@@ -711,7 +757,9 @@ constexpr int TLDB = TSC + 4;  // strip leading dimension (== 4 mod 16: conflict
 
 __global__ void __launch_bounds__(256, 2) lu_trsm_strip_kernel(const double* __restrict__ L, long long ldl,
                                                            double* __restrict__ B, long long ldb, int w,
-                                                           int ncols) {
+                                                           int ncols, long long sA) {
+  L += (long long)blockIdx.y * sA;   // system of the batch
+  B += (long long)blockIdx.y * sA;
   extern __shared__ __align__(16) unsigned char smraw[];
   double* Bs = reinterpret_cast<double*>(smraw);  // [wpad][TLDB]
   __shared__ double Ld[32][33];
@@ -773,17 +821,24 @@ __global__ void __launch_bounds__(256, 2) lu_trsm_strip_kernel(const double* __r
     if (cok) B[(long long)r * ldb + col0 + lane] = Bs[r * TLDB + lane];
 }
 
+static inline GemmBatch gemm_batch(const Bt& bt) {
+  GemmBatch gb;
+  gb.count = bt.count;
+  gb.sC = gb.sA = gb.sB = bt.sA;   // all three operands live inside the system's own matrix
+  return gb;
+}
+
 static int trsm_rec(const double* L, long long ldl, double* B, long long ldb, int w, int ncols,
-                    cudaStream_t st) {
+                    cudaStream_t st, const Bt& bt) {
   if (w <= 0 || ncols <= 0) return WG_OK;
   if (w <= 32) {
-    const int grid = wg_cdiv(ncols, 64);
+    const dim3 grid(wg_cdiv(ncols, 64), bt.count);
     if (w <= 8)
-      WG_CUDA(launch_prio(lu_trsm_base_kernel<8>, dim3(grid), dim3(64), 0, st, L, ldl, B, ldb, w, ncols));
+      WG_CUDA(launch_prio(lu_trsm_base_kernel<8>, grid, dim3(64), 0, st, L, ldl, B, ldb, w, ncols, bt.sA));
     else if (w <= 16)
-      WG_CUDA(launch_prio(lu_trsm_base_kernel<16>, dim3(grid), dim3(64), 0, st, L, ldl, B, ldb, w, ncols));
+      WG_CUDA(launch_prio(lu_trsm_base_kernel<16>, grid, dim3(64), 0, st, L, ldl, B, ldb, w, ncols, bt.sA));
     else
-      WG_CUDA(launch_prio(lu_trsm_base_kernel<32>, dim3(grid), dim3(64), 0, st, L, ldl, B, ldb, w, ncols));
+      WG_CUDA(launch_prio(lu_trsm_base_kernel<32>, grid, dim3(64), 0, st, L, ldl, B, ldb, w, ncols, bt.sA));
     WG_LAUNCH_CHECK();
     return WG_OK;
   }
@@ -792,22 +847,28 @@ static int trsm_rec(const double* L, long long ldl, double* B, long long ldb, in
     const size_t smemMax = 256 * TLDB * sizeof(double);
     if (wg_func_configured(reinterpret_cast<const void*>(lu_trsm_strip_kernel), smemMax) < (long long)smemMax)
       WG_CUDA(cudaFuncSetAttribute(lu_trsm_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemMax));
-    WG_CUDA(launch_prio(lu_trsm_strip_kernel, dim3(wg_cdiv(ncols, TSC)), dim3(256), smem, st, L, ldl, B, ldb, w, ncols));
+    WG_CUDA(launch_prio(lu_trsm_strip_kernel, dim3(wg_cdiv(ncols, TSC), bt.count), dim3(256), smem, st, L, ldl, B, ldb, w,
+                        ncols, bt.sA));
     WG_LAUNCH_CHECK();
     return WG_OK;
   }
   const int w1 = 32 * (((w + 31) / 32 + 1) / 2);
-  int rc = trsm_rec(L, ldl, B, ldb, w1, ncols, st);
+  int rc = trsm_rec(L, ldl, B, ldb, w1, ncols, st, bt);
   if (rc) return rc;
-  rc = dgemm_sub(B + (long long)w1 * ldb, L + (long long)w1 * ldl, B, w - w1, ncols, w1, ldb, ldl, ldb, st);
+  rc = dgemm_sub(B + (long long)w1 * ldb, L + (long long)w1 * ldl, B, w - w1, ncols, w1, ldb, ldl, ldb, st, gemm_batch(bt));
   if (rc) return rc;
-  return trsm_rec(L + (long long)w1 * ldl + w1, ldl, B + (long long)w1 * ldb, ldb, w - w1, ncols, st);
+  return trsm_rec(L + (long long)w1 * ldl + w1, ldl, B + (long long)w1 * ldb, ldb, w - w1, ncols, st, bt);
 }
 
 // ------------------------------------------------------------------ solve kernels
 __global__ void lu_rhs_perm_kernel(double* __restrict__ b, const int* __restrict__ srcTop,
                                    const int* __restrict__ bDst, const int* __restrict__ bSrc,
-                                   const int* __restrict__ nbot, int n, int NB) {
+                                   const int* __restrict__ nbot, int n, int NB, long long sV, int sI, int sP) {
+  b += (long long)blockIdx.x * sV;   // system of the batch
+  srcTop += (long long)blockIdx.x * sI;
+  bDst += (long long)blockIdx.x * sI;
+  bSrc += (long long)blockIdx.x * sI;
+  nbot += (long long)blockIdx.x * sP;
   const int tid = threadIdx.x;
   for (int k = 0, pnl = 0; k < n; k += NB, ++pnl) {
     const int nb = min(NB, n - k);
@@ -830,7 +891,13 @@ __global__ void lu_rhs_perm_kernel(double* __restrict__ b, const int* __restrict
 // the interchanges of ONE panel applied to the right-hand side (forward solve fused into the factorisation)
 __global__ void lu_rhs_perm_panel_kernel(double* __restrict__ b, const int* __restrict__ srcTop,
                                          const int* __restrict__ bDst, const int* __restrict__ bSrc,
-                                         const int* __restrict__ nbotPtr, int k, int nb) {
+                                         const int* __restrict__ nbotPtr, int k, int nb, long long sV, int sI,
+                                         int sP) {
+  b += (long long)blockIdx.x * sV;   // system of the batch
+  srcTop += (long long)blockIdx.x * sI;
+  bDst += (long long)blockIdx.x * sI;
+  bSrc += (long long)blockIdx.x * sI;
+  nbotPtr += (long long)blockIdx.x * sP;
   const int tid = threadIdx.x;
   const int nbt = *nbotPtr;
   double v = 0.0;
@@ -858,7 +925,10 @@ constexpr int TS_LD = TS_BS + 1;
 template <bool UPPER>
 __global__ void __launch_bounds__(256) lu_trisolve_step_kernel(const double* __restrict__ LU, long long lda,
                                                                double* __restrict__ b, int n, int kprev,
-                                                               int bsprev, int kb, int bs) {
+                                                               int bsprev, int kb, int bs, long long sA,
+                                                               long long sV) {
+  LU += (long long)blockIdx.y * sA;   // system of the batch
+  b += (long long)blockIdx.y * sV;
   extern __shared__ __align__(16) unsigned char smraw[];
   double* T = reinterpret_cast<double*>(smraw);  // [TS_BS][TS_LD]
   double* xs = T + TS_BS * TS_LD;                // [TS_BS] previous block's solution
@@ -964,6 +1034,10 @@ __global__ void __launch_bounds__(256) lu_trisolve_step_kernel(const double* __r
 // ------------------------------------------------------------------ host-side plan / scheduler
 struct LuPlan {
   int n = 0;
+  int batch = 1;          // independent systems factored in lock step by every launch (strided batch)
+  int npanelSlots = 0;    // per-system stride of the per-panel counters
+  long long sStage = 0;   // per-system stride of the bulk staging buffers
+  Bt bt;                  // strides of the current call (operator / right-hand side strides come from the caller)
   LuTuning t;              // this plan's scheduling knobs
   long long tuneEpoch = 0; // epoch of the process-wide defaults this plan last adopted
   bool tunePinned = false; // tuned individually: ignores later changes of the defaults
@@ -1037,12 +1111,12 @@ static int probe_max_cluster() {
   return 1;
 }
 
-static int lu_plan_fill(LuPlan* p, int n);
+static int lu_plan_fill(LuPlan* p, int n, int batch);
 
-int lu_plan_create(int n, LuPlan** out) {
-  WG_REQUIRE(n > 0 && out != nullptr, "lu_plan_create: bad arguments");
+int lu_plan_create(int n, LuPlan** out, int batch) {
+  WG_REQUIRE(n > 0 && out != nullptr && batch >= 1 && batch <= 65535, "lu_plan_create: bad arguments");
   LuPlan* p = new LuPlan();
-  const int rc = lu_plan_fill(p, n);
+  const int rc = lu_plan_fill(p, n, batch);
   if (rc) {
     lu_plan_destroy(p);   // frees whatever was allocated before the failure
     return rc;
@@ -1051,26 +1125,33 @@ int lu_plan_create(int n, LuPlan** out) {
   return WG_OK;
 }
 
-static int lu_plan_fill(LuPlan* p, int n) {
+static int lu_plan_fill(LuPlan* p, int n, int batch) {
   p->n = n;
+  p->batch = batch;
+  const size_t B = (size_t)batch;
   p->t = g_tune;
   p->tuneEpoch = g_tune_epoch;
   p->maxCL = probe_max_cluster<16, 2>();
   const int npanels = wg_cdiv(n, 32) + 1;
-  WG_CUDA(cudaMalloc(&p->grpSrcTop, sizeof(int) * n));
-  WG_CUDA(cudaMalloc(&p->grpBDst, sizeof(int) * n));
-  WG_CUDA(cudaMalloc(&p->permSrcTop, sizeof(int) * n));
-  WG_CUDA(cudaMalloc(&p->permBDst, sizeof(int) * n));
-  WG_CUDA(cudaMalloc(&p->permBSrc, sizeof(int) * n));
-  WG_CUDA(cudaMalloc(&p->permNBot, sizeof(int) * npanels));
-  WG_CUDA(cudaMalloc(&p->posContent, sizeof(int) * n));
-  WG_CUDA(cudaMemset(p->posContent, 0xff, sizeof(int) * n));
-  WG_CUDA(cudaMemset(p->permNBot, 0, sizeof(int) * npanels));
-  const size_t sbytes = sizeof(double) * (size_t)256 * (size_t)n;
+  p->npanelSlots = npanels;
+  p->sStage = (long long)256 * n;
+  p->bt.count = batch;
+  p->bt.sI = n;
+  p->bt.sP = npanels;
+  WG_CUDA(cudaMalloc(&p->grpSrcTop, sizeof(int) * n * B));
+  WG_CUDA(cudaMalloc(&p->grpBDst, sizeof(int) * n * B));
+  WG_CUDA(cudaMalloc(&p->permSrcTop, sizeof(int) * n * B));
+  WG_CUDA(cudaMalloc(&p->permBDst, sizeof(int) * n * B));
+  WG_CUDA(cudaMalloc(&p->permBSrc, sizeof(int) * n * B));
+  WG_CUDA(cudaMalloc(&p->permNBot, sizeof(int) * npanels * B));
+  WG_CUDA(cudaMalloc(&p->posContent, sizeof(int) * n * B));
+  WG_CUDA(cudaMemset(p->posContent, 0xff, sizeof(int) * n * B));
+  WG_CUDA(cudaMemset(p->permNBot, 0, sizeof(int) * npanels * B));
+  const size_t sbytes = sizeof(double) * (size_t)256 * (size_t)n * B;
   WG_CUDA(cudaMalloc(&p->S, sbytes));
   WG_CUDA(cudaMalloc(&p->S2, sbytes));
-  WG_CUDA(cudaMalloc(&p->Sc, sizeof(double) * 256 * 256));
-  WG_CUDA(cudaMalloc(&p->Sc2, sizeof(double) * 256 * 256));
+  WG_CUDA(cudaMalloc(&p->Sc, sizeof(double) * 256 * 256 * B));
+  WG_CUDA(cudaMalloc(&p->Sc2, sizeof(double) * 256 * 256 * B));
   int prLow = 0, prHigh = 0;
   WG_CUDA(cudaDeviceGetStreamPriorityRange(&prLow, &prHigh));
   WG_CUDA(cudaStreamCreateWithPriority(&p->panelStream, cudaStreamNonBlocking, prHigh));
@@ -1084,7 +1165,7 @@ static int lu_plan_fill(LuPlan* p, int n) {
   WG_CUDA(cudaStreamCreateWithPriority(&p->rhsStream, cudaStreamNonBlocking, prLow));
   WG_CUDA(cudaEventCreateWithFlags(&p->evRhsIn, cudaEventDisableTiming));
   WG_CUDA(cudaEventCreateWithFlags(&p->evRhsOut, cudaEventDisableTiming));
-  if (n >= 8192) {
+  if (n >= 8192) {   // far-column staging of the split bulk (large systems only)
     WG_CUDA(cudaMalloc(&p->Sf, sbytes));
     WG_CUDA(cudaMalloc(&p->Sf2, sbytes));
   }
@@ -1147,6 +1228,8 @@ static int leaf(FactorCtx& c, int c0, int w, int pc0, int pc1) {
   const int m = c.p->n - c0;
   PanelArgs pa;
   pa.A = c.A;
+  pa.sA = c.p->bt.sA;
+  pa.sI = c.p->bt.sI;
   pa.lda = c.lda;
   pa.n = c.p->n;
   pa.c0 = c0;
@@ -1166,16 +1249,17 @@ static int leaf(FactorCtx& c, int c0, int w, int pc0, int pc1) {
   };
   // one row per thread whenever the cluster can hold the block: the column loop is issue bound
   // (4 warps per scheduler), so fewer rows per thread is ~20% faster per column
-  if (c.wb == 32) return launch_leaf<32, 1>(pa, pick_cl(PT), c.st);
+  const int nb_ = c.p->bt.count;
+  if (c.wb == 32) return launch_leaf<32, 1>(pa, pick_cl(PT), nb_, c.st);
   if (c.wb == 16) {
-    if (m <= c.p->maxCL * PT) return launch_leaf<16, 1>(pa, pick_cl(PT), c.st);
-    return launch_leaf<16, 2>(pa, pick_cl(PT * 2), c.st);
+    if (m <= c.p->maxCL * PT) return launch_leaf<16, 1>(pa, pick_cl(PT), nb_, c.st);
+    return launch_leaf<16, 2>(pa, pick_cl(PT * 2), nb_, c.st);
   }
-  if (c.wb == 2) return launch_leaf<2, 16>(pa, pick_cl(PT * 16), c.st);  // up to 131072 rows: 16 rows x 2 columns per thread
-  if (c.wb == 4) return launch_leaf<4, 8>(pa, pick_cl(PT * 8), c.st);   // up to 65536 rows: 8 rows x 4 columns per thread
-  if (m <= c.p->maxCL * PT) return launch_leaf<8, 1>(pa, pick_cl(PT), c.st);
-  if (m <= c.p->maxCL * PT * 2) return launch_leaf<8, 2>(pa, pick_cl(PT * 2), c.st);
-  return launch_leaf<8, 4>(pa, pick_cl(PT * 4), c.st);
+  if (c.wb == 2) return launch_leaf<2, 16>(pa, pick_cl(PT * 16), nb_, c.st);  // up to 131072 rows: 16 rows x 2 columns per thread
+  if (c.wb == 4) return launch_leaf<4, 8>(pa, pick_cl(PT * 8), nb_, c.st);   // up to 65536 rows: 8 rows x 4 columns per thread
+  if (m <= c.p->maxCL * PT) return launch_leaf<8, 1>(pa, pick_cl(PT), nb_, c.st);
+  if (m <= c.p->maxCL * PT * 2) return launch_leaf<8, 2>(pa, pick_cl(PT * 2), nb_, c.st);
+  return launch_leaf<8, 4>(pa, pick_cl(PT * 4), nb_, c.st);
 }
 
 static int panel_rec(FactorCtx& c, int c0, int w, int pc0, int pc1) {
@@ -1187,10 +1271,10 @@ static int panel_rec(FactorCtx& c, int c0, int w, int pc0, int pc1) {
   if (rc) return rc;
   double* A = c.A;
   const long long lda = c.lda;
-  rc = trsm_rec(A + (long long)c0 * lda + c0, lda, A + (long long)c0 * lda + c0 + w1, lda, w1, w - w1, c.st);
+  rc = trsm_rec(A + (long long)c0 * lda + c0, lda, A + (long long)c0 * lda + c0 + w1, lda, w1, w - w1, c.st, c.p->bt);
   if (rc) return rc;
   rc = dgemm_sub(A + (long long)(c0 + w1) * lda + c0 + w1, A + (long long)(c0 + w1) * lda + c0,
-                 A + (long long)c0 * lda + c0 + w1, n - c0 - w1, w - w1, w1, lda, lda, lda, c.st);
+                 A + (long long)c0 * lda + c0 + w1, n - c0 - w1, w - w1, w1, lda, lda, lda, c.st, gemm_batch(c.p->bt));
   if (rc) return rc;
   return panel_rec(c, c0 + w1, w - w1, pc0, pc1);
 }
@@ -1303,15 +1387,16 @@ void lu_plan_set_tuning(LuPlan* p, int nb, int use_graph, int lookahead, int spl
 }
 
 static int apply_perm(LuPlan* p, double* A, long long lda, ColMap cm, int k, int nb, int pnl, double* S, double* S2,
-                      int vecA, cudaStream_t st) {
+                      int vecA, cudaStream_t st, long long sStage) {
   if (cm.ncol <= 0) return WG_OK;
   const int vec = vecA && ((cm.ncol | cm.split | cm.off0 | cm.off1) % 2 == 0);
-  dim3 grid(wg_cdiv(cm.ncol, 2048), nb);
+  dim3 grid(wg_cdiv(cm.ncol, 2048), nb, p->bt.count);
+  const PermBatch pb{p->bt.sA, sStage, p->bt.sI, p->bt.sP};
   WG_CUDA(launch_prio(lu_perm_gather_kernel, grid, dim3(256), 0, st, A, lda, cm, k, p->permSrcTop, p->permBSrc,
-                      p->permNBot + pnl, S, S2, vec));
+                      p->permNBot + pnl, S, S2, vec, pb));
   WG_LAUNCH_CHECK();
   WG_CUDA(launch_prio(lu_perm_write_kernel, grid, dim3(256), 0, st, A, lda, cm, k, p->permSrcTop, p->permBDst,
-                      p->permNBot + pnl, S, S2, vec));
+                      p->permNBot + pnl, S, S2, vec, pb));
   WG_LAUNCH_CHECK();
   return WG_OK;
 }
@@ -1347,16 +1432,16 @@ static int rhs_panel(LuPlan* p, const double* LU, long long lda, int k, int nb, 
   cudaStream_t st = p->rhsStream;
   WG_CUDA(cudaEventRecord(p->evRhsIn, after));
   WG_CUDA(cudaStreamWaitEvent(st, p->evRhsIn, 0));
-  WG_CUDA(launch_prio(lu_rhs_perm_panel_kernel, dim3(1), dim3(1024), 0, st, p->rhs, p->permSrcTop, p->permBDst,
-                      p->permBSrc, p->permNBot + pnl, k, nb));
+  WG_CUDA(launch_prio(lu_rhs_perm_panel_kernel, dim3(p->bt.count), dim3(1024), 0, st, p->rhs, p->permSrcTop, p->permBDst,
+                      p->permBSrc, p->permNBot + pnl, k, nb, p->bt.sV, p->bt.sI, p->bt.sP));
   WG_LAUNCH_CHECK();
   const size_t smem = (size_t)(TS_BS * TS_LD + 2 * TS_BS) * sizeof(double);
   for (int kb = k; kb < k + nb; kb += TS_BS) {
     const int bs = TS_BS < k + nb - kb ? TS_BS : k + nb - kb;
     const int rest = n - kb - bs;
     const int grid = 1 + ((p->rhsPrev >= 0 && rest > 0) ? wg_cdiv(rest, 8) : 0);
-    WG_CUDA(launch_prio(lu_trisolve_step_kernel<false>, dim3(grid), dim3(256), smem, st, LU, lda, p->rhs, n, p->rhsPrev,
-                        p->rhsPrevBs, kb, bs));
+    WG_CUDA(launch_prio(lu_trisolve_step_kernel<false>, dim3(grid, p->bt.count), dim3(256), smem, st, LU, lda, p->rhs, n,
+                        p->rhsPrev, p->rhsPrevBs, kb, bs, p->bt.sA, p->bt.sV));
     WG_LAUNCH_CHECK();
     p->rhsPrev = kb;
     p->rhsPrevBs = bs;
@@ -1376,9 +1461,12 @@ static int rhs_panel(LuPlan* p, const double* LU, long long lda, int k, int nb, 
 static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStream_t st) {
   const int n = p->n, NB = p->t.nb;
   FactorCtx c{p, A, lda, ipiv, info, st, 16, 0};
-  c.vecA = (lda % 2 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0);
+  c.vecA = (lda % 2 == 0) && (p->bt.sA % 2 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0);
   const bool look = p->t.lookahead != 0;
-  WG_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
+  WG_CUDA(cudaMemsetAsync(info, 0, sizeof(int) * p->bt.count, st));
+  const Bt& bt = p->bt;
+  const GemmBatch gb = gemm_batch(bt);
+  const long long sS = p->sStage, sSc = 256 * 256;
   if (panel_width_class(p, n) == 0) {
     wg_set_error("lu_factor: n=%d exceeds the leaf-panel capacity (%d rows) of this build", n,
                  p->maxCL * PT * 16);
@@ -1413,8 +1501,8 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
       c.wb = panel_width_class(p, n - k);
       rc = panel_rec(c, k, nb, k, k + nb);
       if (rc) return rc;
-      WG_CUDA(launch_prio(lu_perm_compose_kernel, dim3(1), dim3(256), 0, bs, n, k, nb, c.wb, p->grpSrcTop, p->grpBDst,
-                          p->posContent, p->permSrcTop, p->permBDst, p->permBSrc, p->permNBot + pnl));
+      WG_CUDA(launch_prio(lu_perm_compose_kernel, dim3(bt.count), dim3(256), 0, bs, n, k, nb, c.wb, p->grpSrcTop, p->grpBDst,
+                          p->posContent, p->permSrcTop, p->permBDst, p->permBSrc, p->permNBot + pnl, bt.sI, bt.sP));
       WG_LAUNCH_CHECK();
     }
     panelDone = false;
@@ -1427,15 +1515,15 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
     if (!(look && rest > nb2)) {
       rc = rhs_wait(p, bs);
       if (rc) return rc;
-      rc = apply_perm(p, A, lda, ColMap{n - nb, k, 0, nb}, k, nb, pnl, p->S, p->S2, c.vecA, bs);
+      rc = apply_perm(p, A, lda, ColMap{n - nb, k, 0, nb}, k, nb, pnl, p->S, p->S2, c.vecA, bs, sS);
       if (rc) return rc;
       rc = rhs_panel(p, A, lda, k, nb, pnl, bs);
       if (rc) return rc;
       if (rest <= 0) break;
-      rc = trsm_rec(L11, lda, U12, lda, nb, rest, bs);
+      rc = trsm_rec(L11, lda, U12, lda, nb, rest, bs, bt);
       if (rc) return rc;
-      prof_mark(p, bs, 2.0 * rest * (double)rest * nb, true);
-      rc = dgemm_sub(C22, L21, U12, rest, rest, nb, lda, lda, lda, bs);
+      prof_mark(p, bs, 2.0 * rest * (double)rest * nb * bt.count, true);
+      rc = dgemm_sub(C22, L21, U12, rest, rest, nb, lda, lda, lda, bs, gb);
       if (rc) return rc;
       prof_mark(p, bs, 0.0, false);
       continue;
@@ -1463,18 +1551,19 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
     WG_CUDA(cudaEventRecord(p->evFork, bs));
     WG_CUDA(cudaStreamWaitEvent(cs, p->evFork, 0));
     g_wg_launch_prio = p->prioChain;
-    rc = apply_perm(p, A, lda, ColMap{nb2, nb2, k + nb, 0}, k, nb, pnl, p->Sc, p->Sc2, c.vecA, cs);
+    rc = apply_perm(p, A, lda, ColMap{nb2, nb2, k + nb, 0}, k, nb, pnl, p->Sc, p->Sc2, c.vecA, cs, sSc);
     if (rc) return rc;
-    rc = trsm_rec(L11, lda, U12, lda, nb, nb2, cs);
+    rc = trsm_rec(L11, lda, U12, lda, nb, nb2, cs, bt);
     if (rc) return rc;
-    rc = dgemm_sub(C22, L21, U12, rest, nb2, nb, lda, lda, lda, cs);
+    rc = dgemm_sub(C22, L21, U12, rest, nb2, nb, lda, lda, lda, cs, gb);
     if (rc) return rc;
     c.st = cs;
     c.wb = panel_width_class(p, rest);
     rc = panel_rec(c, k + nb, nb2, k + nb, k + nb + nb2);
     if (rc) return rc;
-    WG_CUDA(launch_prio(lu_perm_compose_kernel, dim3(1), dim3(256), 0, cs, n, k + nb, nb2, c.wb, p->grpSrcTop,
-                        p->grpBDst, p->posContent, p->permSrcTop, p->permBDst, p->permBSrc, p->permNBot + pnl + 1));
+    WG_CUDA(launch_prio(lu_perm_compose_kernel, dim3(bt.count), dim3(256), 0, cs, n, k + nb, nb2, c.wb, p->grpSrcTop,
+                        p->grpBDst, p->posContent, p->permSrcTop, p->permBDst, p->permBSrc, p->permNBot + pnl + 1, bt.sI,
+                        bt.sP));
     WG_LAUNCH_CHECK();
     WG_CUDA(cudaEventRecord(p->evJoin, cs));
     trace_mark(p, cs, pnl, 4);
@@ -1486,18 +1575,18 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
       if (rc) return rc;
     }
     rc = apply_perm(p, A, lda, farOn ? ColMap{Xe - R0, Xe - R0, R0, 0} : ColMap{k + (Xe - R0), k, 0, nb + nb2}, k, nb,
-                    pnl, p->S, p->S2, c.vecA, bs);
+                    pnl, p->S, p->S2, c.vecA, bs, sS);
     if (rc) return rc;
     if (!farOn) {
       rc = rhs_panel(p, A, lda, k, nb, pnl, bs);
       if (rc) return rc;
     }
     trace_mark(p, bs, pnl, 1);
-    rc = trsm_rec(L11, lda, U12 + nb2, lda, nb, Xe - R0, bs);
+    rc = trsm_rec(L11, lda, U12 + nb2, lda, nb, Xe - R0, bs, bt);
     if (rc) return rc;
     trace_mark(p, bs, pnl, 2);
-    prof_mark(p, bs, 2.0 * rest * (double)(Xe - R0) * nb, true);
-    rc = dgemm_sub(C22 + nb2, L21, U12 + nb2, rest, Xe - R0, nb, lda, lda, lda, bs);
+    prof_mark(p, bs, 2.0 * rest * (double)(Xe - R0) * nb * bt.count, true);
+    rc = dgemm_sub(C22 + nb2, L21, U12 + nb2, rest, Xe - R0, nb, lda, lda, lda, bs, gb);
     if (rc) return rc;
     prof_mark(p, bs, 0.0, false);
     trace_mark(p, bs, pnl, 3);
@@ -1507,13 +1596,13 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
       const int off = X - (k + nb);
       rc = rhs_wait(p, fs);
       if (rc) return rc;
-      rc = apply_perm(p, A, lda, ColMap{k + (n - X), k, 0, X - k}, k, nb, pnl, p->Sf, p->Sf2, c.vecA, fs);
+      rc = apply_perm(p, A, lda, ColMap{k + (n - X), k, 0, X - k}, k, nb, pnl, p->Sf, p->Sf2, c.vecA, fs, sS);
       if (rc) return rc;
       rc = rhs_panel(p, A, lda, k, nb, pnl, fs);
       if (rc) return rc;
-      rc = trsm_rec(L11, lda, U12 + off, lda, nb, n - X, fs);
+      rc = trsm_rec(L11, lda, U12 + off, lda, nb, n - X, fs, bt);
       if (rc) return rc;
-      rc = dgemm_sub(C22 + off, L21, U12 + off, rest, n - X, nb, lda, lda, lda, fs);
+      rc = dgemm_sub(C22 + off, L21, U12 + off, rest, n - X, nb, lda, lda, lda, fs, gb);
       if (rc) return rc;
       WG_CUDA(cudaStreamWaitEvent(fs, p->evJoin, 0));   // its next step needs the next panel ...
       WG_CUDA(cudaStreamWaitEvent(fs, p->evNear, 0));   // ... and interchanges rows of L21 that this near GEMM reads
@@ -1537,10 +1626,15 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
   return WG_OK;
 }
 
-int lu_factor(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStream_t st, double* rhs) {
+int lu_factor(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStream_t st, double* rhs,
+              long long strideA, long long strideRhs) {
   WG_REQUIRE(p && A && ipiv && info && lda >= p->n, "lu_factor: bad arguments");
+  WG_REQUIRE(p->batch == 1 || strideA >= (long long)p->n * lda, "lu_factor: batch stride smaller than one operator");
   p->rhs = rhs;   // non-null: the forward solve L y = P rhs rides along (finish with lu_solve(..., backwardOnly))
   lu_sync_tuning(p);
+  if (p->bt.sA != strideA || p->bt.sV != strideRhs) lu_drop_graphs(p);   // strides are baked into a captured graph
+  p->bt.sA = p->batch > 1 ? strideA : 0;
+  p->bt.sV = p->batch > 1 ? strideRhs : 0;
   if (!p->t.useGraph) return factor_enqueue(p, A, lda, ipiv, info, st);
   if (!p->exec || p->gA != A || p->glda != lda || p->gipiv != ipiv || p->ginfo != info || p->grhs != rhs) {
     if (p->exec) {
@@ -1577,9 +1671,16 @@ int lu_factor(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStr
 
 static int solve_enqueue(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st, bool backwardOnly);
 
-int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st, bool backwardOnly) {
+int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st, bool backwardOnly,
+             long long strideA, long long strideB) {
   WG_REQUIRE(p && LU && b && lda >= p->n, "lu_solve: bad arguments");
   lu_sync_tuning(p);
+  {
+    const long long sA = p->batch > 1 ? strideA : 0, sV = p->batch > 1 ? strideB : 0;
+    if (p->bt.sA != sA || p->bt.sV != sV) lu_drop_graphs(p);
+    p->bt.sA = sA;
+    p->bt.sV = sV;
+  }
   if (!p->t.useGraph) return solve_enqueue(p, LU, lda, b, st, backwardOnly);
   if (!p->solveExec || p->sLU != LU || p->slda != lda || p->sb != b || p->sBackOnly != (int)backwardOnly) {
     if (p->solveExec) {
@@ -1621,7 +1722,8 @@ static int solve_enqueue(LuPlan* p, const double* LU, long long lda, double* b, 
   const int nblk = wg_cdiv(n, TS_BS);
   int kprev = -1, bsprev = 0;
   if (!backwardOnly) {
-    lu_rhs_perm_kernel<<<1, 1024, 0, st>>>(b, p->permSrcTop, p->permBDst, p->permBSrc, p->permNBot, n, NB);
+    lu_rhs_perm_kernel<<<p->bt.count, 1024, 0, st>>>(b, p->permSrcTop, p->permBDst, p->permBSrc, p->permNBot, n, NB, p->bt.sV,
+                                                     p->bt.sI, p->bt.sP);
     WG_LAUNCH_CHECK();
   }
   for (int q = 0; q < nblk && !backwardOnly; ++q) {
@@ -1629,7 +1731,8 @@ static int solve_enqueue(LuPlan* p, const double* LU, long long lda, double* b, 
     const int bs = TS_BS < n - kb ? TS_BS : n - kb;
     const int rest = n - kb - bs;
     const int grid = 1 + ((kprev >= 0 && rest > 0) ? wg_cdiv(rest, 8) : 0);
-    lu_trisolve_step_kernel<false><<<grid, 256, smem, st>>>(LU, lda, b, n, kprev, bsprev, kb, bs);
+    lu_trisolve_step_kernel<false><<<dim3(grid, p->bt.count), 256, smem, st>>>(LU, lda, b, n, kprev, bsprev, kb, bs, p->bt.sA,
+                                                                              p->bt.sV);
     WG_LAUNCH_CHECK();
     kprev = kb;
     bsprev = bs;
@@ -1640,7 +1743,8 @@ static int solve_enqueue(LuPlan* p, const double* LU, long long lda, double* b, 
     const int kb = q * TS_BS;
     const int bs = TS_BS < n - kb ? TS_BS : n - kb;
     const int grid = 1 + ((kprev >= 0 && kb > 0) ? wg_cdiv(kb, 8) : 0);
-    lu_trisolve_step_kernel<true><<<grid, 256, smem, st>>>(LU, lda, b, n, kprev, bsprev, kb, bs);
+    lu_trisolve_step_kernel<true><<<dim3(grid, p->bt.count), 256, smem, st>>>(LU, lda, b, n, kprev, bsprev, kb, bs, p->bt.sA,
+                                                                             p->bt.sV);
     WG_LAUNCH_CHECK();
     kprev = kb;
     bsprev = bs;

@@ -99,6 +99,12 @@ def makeRemoteClass(conn):
 
 def _workerMain(conn, manager, settings):
     """Host worker: unmodified EOM.wallPressure, Boltzmann solves forwarded to the server."""
+    import gc  # pylint: disable=import-outside-toplevel
+
+    # The worker never touches CUDA.  If the rank process had initialised CUDA before the fork, garbage inherited
+    # from it (cyclic references holding device tensors) must not be collected HERE, where the driver is unusable:
+    # everything that exists at this point is moved out of the collector's reach.
+    gc.freeze()
     import WallGo  # pylint: disable=import-outside-toplevel
     import WallGo.manager as _manager  # pylint: disable=import-outside-toplevel
 
@@ -133,6 +139,45 @@ def _workerMain(conn, manager, settings):
         conn.close()
 
 
+class HostWorkers:
+    """The forked host processes of one rank.  Start them as early as possible -- ideally before the process
+    has initialised CUDA -- and hand them to scanLocal / scanWallPressure; they idle on their pipe until then."""
+
+    def __init__(self, manager, settings, count: int):
+        import gc  # pylint: disable=import-outside-toplevel
+        import multiprocessing as mp  # pylint: disable=import-outside-toplevel
+
+        gc.collect()        # no pending garbage (possibly holding device tensors) goes into the children
+        ctx = mp.get_context("fork")
+        self.conns, self.procs = [], []
+        for _ in range(max(0, int(count))):
+            parent, child = ctx.Pipe(duplex=True)
+            pr = ctx.Process(target=_workerMain, args=(child, manager, settings), daemon=True)
+            pr.start()
+            child.close()
+            self.conns.append(parent)
+            self.procs.append(pr)
+
+    def __len__(self):
+        return len(self.conns)
+
+    def close(self):
+        for c in self.conns:
+            try:
+                c.send(("stop",))
+            except Exception:  # pylint: disable=broad-except
+                pass
+            try:
+                c.close()
+            except Exception:  # pylint: disable=broad-except
+                pass
+        for pr in self.procs:
+            pr.join(timeout=5)
+            if pr.is_alive():
+                pr.terminate()
+        self.conns, self.procs = [], []
+
+
 def defaultWorkers(worldSize: int = 1) -> int:
     """Host processes per rank: the node's cores are divided evenly among its GPUs (so the per-GPU host budget
     does not depend on how many ranks a run uses), one core stays with the rank process, at most 8."""
@@ -145,20 +190,46 @@ def defaultWorkers(worldSize: int = 1) -> int:
     return max(1, min(8, cores // max(gpus, worldSize) - 1))
 
 
-def scanLocal(manager, settings, vws, indices, workers=None, concurrency=None, stats=None, budgetSeconds=None):
+def _serverWallSolver(manager, settings):
+    """The rank's own WallSolver (EOM + grid + drop-in Boltzmann solver with its engines, slots and captured
+    graphs), built once per (manager, settings) and kept on the manager."""
+    cached = getattr(manager, "_b200ScanSolver", None)
+    if cached is None or cached[0] is not settings:
+        cached = (settings, manager.setupWallSolver(settings))
+        manager._b200ScanSolver = cached  # pylint: disable=protected-access
+    return cached[1]
+
+
+def warmUp(manager, settings, vw, concurrency=None):
+    """One point in-process, then one batch through every slot: engines, operator buffers and CUDA graphs of the
+    whole slot pool exist before a timed scan starts."""
+    rows = scanLocal(manager, settings, [vw], [0], workers=0)
+    solver = _serverWallSolver(manager, settings).boltzmannSolver
+    pool = solver.slotPool(concurrency)
+    count = len(pool.sibs)
+    pool.close()
+    import copy  # pylint: disable=import-outside-toplevel
+    bg = copy.deepcopy(solver.background)
+    bg.velocityMid = 0.0       # already in the plasma frame: the batch's own boost becomes the identity
+    solver.getDeltasBatch([bg] * count, concurrency=count)
+    return rows
+
+
+def scanLocal(manager, settings, vws, indices, workers=None, concurrency=None, stats=None, budgetSeconds=None,
+              hostWorkers=None):
     """The points `indices` of `vws` on this process' GPU.  Returns [len(indices), width] rows in the order
     of `indices`.  `manager` is a WallGoManager after setupThermodynamicsHydrodynamics with
     wallgo_b200.dropin installed (dropin.install()); `settings` its WallSolverSettings.
     budgetSeconds: stop handing out points after this long (points are handed out in the order of `indices`;
-    rows of points that were not started stay NaN and stats["done"] counts the finished ones)."""
-    import multiprocessing as mp
+    rows of points that were not started stay NaN and stats["done"] counts the finished ones).
+    hostWorkers: a HostWorkers started earlier (closed by this call); None: forked here."""
     from multiprocessing.connection import wait as mpWait
 
     import WallGo  # pylint: disable=import-outside-toplevel
 
     indices = list(indices)
     stats = {} if stats is None else stats
-    ws = manager.setupWallSolver(settings)          # the server's solver: holds the collision tensor
+    ws = _serverWallSolver(manager, settings)       # the server's solver: holds the collision tensor
     solver = ws.boltzmannSolver
     nF, P, M = ws.eom.nbrFields, len(solver.offEqParticles), solver.grid.M
     rows = np.full((len(indices), rowWidth(nF, P, M)), np.nan)
@@ -167,11 +238,15 @@ def scanLocal(manager, settings, vws, indices, workers=None, concurrency=None, s
     def overBudget():
         return budgetSeconds is not None and time.perf_counter() - tStart > budgetSeconds
 
-    if workers is None:
+    if hostWorkers is not None:
+        workers = len(hostWorkers)
+    elif workers is None:
         workers = defaultWorkers()
-    workers = min(int(workers), len(indices))
+    workers = int(workers) if hostWorkers is not None else min(int(workers), len(indices))
     stats.update(workers=workers, host_s=0.0, solves=0, done=0)
     if not indices:
+        if hostWorkers is not None:
+            hostWorkers.close()
         return rows
     if workers <= 0:
         wp0 = _initialWallParams(WallGo, ws)
@@ -198,15 +273,9 @@ def scanLocal(manager, settings, vws, indices, workers=None, concurrency=None, s
         return rows
 
     # ---- solve server + forked host workers
-    ctx = mp.get_context("fork")
-    conns, procs = [], []
-    for _ in range(workers):
-        parent, child = ctx.Pipe(duplex=True)
-        pr = ctx.Process(target=_workerMain, args=(child, manager, settings), daemon=True)
-        pr.start()
-        child.close()
-        conns.append(parent)
-        procs.append(pr)
+    if hostWorkers is None:
+        hostWorkers = HostWorkers(manager, settings, workers)
+    conns = hostWorkers.conns
     pool = solver.slotPool(concurrency)
     pool.rawResults = True
     todo = list(enumerate(indices))[::-1]
@@ -250,22 +319,15 @@ def scanLocal(manager, settings, vws, indices, workers=None, concurrency=None, s
             tServerBusy += time.perf_counter() - t0
     finally:
         pool.close()
-        for c in conns:
-            try:
-                c.close()
-            except Exception:  # pylint: disable=broad-except
-                pass
-        for pr in procs:
-            pr.join(timeout=5)
-            if pr.is_alive():
-                pr.terminate()
+        hostWorkers.close()
     stats["server_s"] = tServerBusy
     stats["done"] = done
     assert done == started
     return rows
 
 
-def scanWallPressure(manager, settings, vws, workers=None, concurrency=None, stats=None, budgetSeconds=None):
+def scanWallPressure(manager, settings, vws, workers=None, concurrency=None, stats=None, budgetSeconds=None,
+                     hostWorkers=None):
     """All points of `vws`, sharded round-robin over the ranks of the default process group (one per GPU),
     gathered with ONE all_gather.  Every rank returns the full [len(vws), width] table (NaN rows: points a
     rank did not start within budgetSeconds)."""
@@ -279,5 +341,5 @@ def scanWallPressure(manager, settings, vws, workers=None, concurrency=None, sta
     if workers is None:
         workers = defaultWorkers(world)
     rows = scanLocal(manager, settings, vws, mine, workers=workers, concurrency=concurrency, stats=stats,
-                     budgetSeconds=budgetSeconds)
+                     budgetSeconds=budgetSeconds, hostWorkers=hostWorkers)
     return scan.gatherPoints(rows, len(vws), rows.shape[1])
