@@ -519,6 +519,7 @@ def run_b200(a):
             e.factor()
             rec[2].record()
             e.solve()
+            rec[5].record()
         elif fused_now[0]:             # alternative entry: forward solve fused into the factorisation
             e.factor_solve()
             if rec:
@@ -528,6 +529,8 @@ def run_b200(a):
             e.solve()
             if rec:
                 rec[2].record()
+        if solver.refinementSteps:     # part of the product path (BoltzmannSolver._solveOnDevice)
+            e.refine(vws[i], 1.0)
         if rec:
             rec[3].record()
         e.spectra_async(e.S)
@@ -565,6 +568,8 @@ def run_b200(a):
     step(engines[0], W, evu)
     torch.cuda.synchronize()
     unfused = [evu[j].elapsed_time(evu[j + 1]) for j in range(4)]
+    unfused[2] = evu[2].elapsed_time(evu[5])           # both triangular solves
+    refine_ms = evu[5].elapsed_time(evu[3])            # residual (double-double, operator regenerated) + solve + update
 
     fused_now[0] = bool(a.fused)
     pm = 4 * P * (M - 1)
@@ -661,7 +666,8 @@ def run_b200(a):
                        "parallelism": f"{world} x independent systems, no collective inside a solve"},
             "stages_ms_solo": {"assemble": stage[0], "lu_factor_and_solves": stage[1],
                                "spectra_moments": stage[3], "lu_factor": unfused[1],
-                               "tri_solve": unfused[2], "lu_tflops_solo": lu_tf_solo,
+                               "tri_solve": unfused[2], "refinement_step": refine_ms,
+                               "lu_tflops_solo": lu_tf_solo,
                                "note": "one system alone on the GPU, CUDA events around each stage"},
             "latency_ms_sequential_getDeltas": seq_ms,
             "roofline": {"kernel": "dgemm_sub_kernel<128,64,16,2,2,3> (trailing update of the LU, DMMA.8x8x4)",

@@ -36,6 +36,7 @@ extern "C" {
 
 typedef struct wg_solver wg_solver;
 typedef struct wg_lu wg_lu;
+typedef struct wg_batch wg_batch;
 
 int wg_version(void);
 const char* wg_last_error(void);
@@ -120,6 +121,15 @@ int wg_factor_solve(wg_solver* s, double* A_dev, long long lda, double* b_dev, v
 /* ... and the triangular solves; b_dev (n) is overwritten by the solution.  May be called again with
  * another right-hand side (checkLinearization re-uses the factors, boltzmann.py:541-550). */
 int wg_solve(wg_solver* s, const double* LU_dev, long long lda, double* b_dev, void* stream);
+/* One step of mixed-precision iterative refinement of x_dev = deltaF: the residual
+ * r = S - A x of the system of (profiles_dev, vw, collisionMultiplier) is formed with the operator entries
+ * regenerated exactly as wg_assemble forms them (A is not needed in memory: LU_dev holds its factors) and
+ * accumulated in double-double arithmetic; LU_dev solves for the correction, which is added to x_dev.  Removes the
+ * cond(A)*eps forward error of the FP64 solve (np.linalg.solve, boltzmann.py:283, carries the same error).
+ * stats_dev[2] = { max|correction|, max|x| }: their ratio is the forward error the first solve had; divided by
+ * 2^-53 it estimates the condition number the solve experienced. */
+int wg_refine(wg_solver* s, const double* profiles_dev, double vw, double collisionMultiplier, const double* LU_dev,
+              long long lda, double* x_dev, double* stats_dev, void* stream);
 /* Batched form for scans / many small systems: B independent systems (one solver handle, operator buffer,
  * source vector and stream each) are assembled, factored and solved; call b is enqueued on streams[b], so
  * the systems overlap on the GPU (a single LU cannot fill a B200 during its panel chain).  Equivalent to B
@@ -163,8 +173,42 @@ int wg_change_basis(wg_solver* s, int stage, const double* in_dev, double* out_d
  * and resets the sums of the launches bracketed so far (synchronise the stream first). */
 int wg_profile_gemm(wg_solver* s, int enable, double* ms, double* flops, int* count);
 
+/* ---- strided batches: many small systems per launch (north star (2): "a batched FP64 blocked LU";
+ * BASELINE configs[0], n = 1900).  A wg_batch belongs to one solver (shares its grid, tables, statistics and
+ * collision tensor, which must outlive it) and owns the scratch of `count` independent systems of that shape.
+ * Every kernel of the path carries the system index as a grid dimension, so ONE launch sequence (and one
+ * captured CUDA graph) assembles, factors, solves and reduces all `count` systems in lock step -- no per-system
+ * stream or graph -- and each system's result is bit-identical to the single-system entry points above.
+ * Layout: operators A_dev + b*strideA (strideA >= n*lda doubles, a multiple of 4), everything else contiguous
+ * per system: profiles_dev[count][(2+P)(M+1)+(M-1)], vw_dev[count], S_dev / deltaF[count][n],
+ * spectra_dev[count][(M-1)+2(N-1)], keep_dev[count][3] (int: keepM, keepPz, keepPp), deltas_dev[count][4 P (M-1)],
+ * err_dev[count][4 P], info_host[count]. */
+int wg_batch_create(wg_solver* s, int count, wg_batch** out);
+int wg_batch_destroy(wg_batch* b);
+/* wg_assemble for every system of the batch; the wall velocities come from device memory */
+int wg_batch_assemble(wg_batch* b, const double* profiles_dev, const double* vw_dev, double collisionMultiplier,
+                      int parts, double* A_dev, long long lda, long long strideA, double* S_dev, void* stream);
+int wg_batch_factor(wg_batch* b, double* A_dev, long long lda, long long strideA, void* stream);
+int wg_batch_solve(wg_batch* b, const double* LU_dev, long long lda, long long strideA, double* rhs_dev,
+                   void* stream);
+/* wg_refine for every system of the batch; stats_dev[count][2] */
+int wg_batch_refine(wg_batch* b, const double* profiles_dev, const double* vw_dev, double collisionMultiplier,
+                    const double* LU_dev, long long lda, long long strideA, double* x_dev, double* stats_dev,
+                    void* stream);
+int wg_batch_info(wg_batch* b, void* stream, int* info_host);
+int wg_batch_spectra(wg_batch* b, const double* deltaF_dev, double* spectra_dev, void* stream);
+int wg_batch_moments(wg_batch* b, const double* deltaF_dev, const double* profiles_dev, const int* keep_dev,
+                     int roundtrip, double* deltaF_out_dev, double* deltas_dev, double* err_dev, void* stream);
+
 /* ---- generic dense pieces (used by the solver; exported for tests and other callers) */
 int wg_lu_create(int n, int device, wg_lu** out);
+/* `batch` systems of order n factored / solved in lock step by every launch: operators at A_dev + b*strideA,
+ * pivots ipiv_dev[batch][n], info_dev[batch], right-hand sides at b_dev + b*strideB */
+int wg_lu_create_batched(int n, int batch, int device, wg_lu** out);
+int wg_lu_factor_batched(wg_lu* p, double* A_dev, long long lda, long long strideA, int* ipiv_dev, int* info_dev,
+                         void* stream);
+int wg_lu_solve_batched(wg_lu* p, const double* LU_dev, long long lda, long long strideA, double* b_dev,
+                        long long strideB, void* stream);
 int wg_lu_destroy(wg_lu* p);
 int wg_lu_factor(wg_lu* p, double* A_dev, long long lda, int* ipiv_dev, int* info_dev, void* stream);
 int wg_lu_solve(wg_lu* p, const double* LU_dev, long long lda, double* b_dev, void* stream);

@@ -579,3 +579,21 @@ def synthetic_problem(P, M, N, *, vw_mid=-0.5, r=0.5, noise=1e-3, seed=0, T0=100
                    T=T, v=boost_velocity(vwall, vw_mid), msq=msq,
                    vw=float(boost_velocity(0.0, vw_mid)), statistics=stats, collision=coll,
                    collisionMultiplier=collisionMultiplier, dofs=np.full(P, 12.0))
+
+
+def solve_extended(A: np.ndarray, b: np.ndarray, iterations: int = 4):
+    """Solution of the FP64 system A x = b to (nearly) extended precision: LAPACK solve, then iterative
+    refinement with the residual formed in np.longdouble (x87 80-bit here: 64-bit mantissa) and the
+    correction carried as a separate low part.  Test infrastructure: the yardstick for wg_refine, which no FP64
+    solver -- LAPACK included -- matches better than cond(A) * 2^-53.  Returns (x_hi + x_lo rounded, x_lapack)."""
+    from scipy.linalg import lu_factor, lu_solve
+
+    lu = lu_factor(A)
+    x0 = lu_solve(lu, b)
+    Al = A.astype(np.longdouble)
+    bl = b.astype(np.longdouble)
+    x = x0.astype(np.longdouble)
+    for _ in range(iterations):
+        r = bl - Al @ x
+        x = x + lu_solve(lu, np.asarray(r, dtype=np.float64)).astype(np.longdouble)
+    return np.asarray(x, dtype=np.float64), x0

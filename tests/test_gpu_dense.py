@@ -560,3 +560,127 @@ def test_lu_tall_panel_leaf_variants_at_small_size(env, wb):
     assert np.max(np.abs(LU0 - LU1)) / np.max(np.abs(LU0)) < 1e-11
     assert np.max(np.abs(x0 - x1)) / np.max(np.abs(x0)) < 1e-9
     _check_factors(A, LU1, ipiv1)
+
+
+# ---------------------------------------------------------------- strided batches (lock-step LU of many systems)
+def _lu_batched(env, As, bs, pad=0, graph=None):
+    """Factor + solve a list of equally sized systems with ONE batched plan; returns (LU[B], ipiv[B], info[B], x[B])."""
+    torch, lib, _lib = env
+    B, n = len(As), As[0].shape[0]
+    lda = n + pad
+    strideA = n * lda + 4 * (pad > 0)
+    buf = np.zeros(B * strideA)
+    for i, A in enumerate(As):
+        buf[i * strideA:i * strideA + n * lda].reshape(n, lda)[:, :n] = A
+    Ad = torch.from_numpy(buf).cuda()
+    bd = torch.from_numpy(np.stack(bs).copy()).cuda()
+    ipiv = torch.zeros(B * n, dtype=torch.int32, device="cuda")
+    info = torch.zeros(B, dtype=torch.int32, device="cuda")
+    plan = C.c_void_p()
+    _lib.check(lib.wg_lu_create_batched(n, B, 0, C.byref(plan)), "wg_lu_create_batched")
+    try:
+        for _ in range(2 if graph else 1):      # second pass replays the captured graph on restored data
+            Ad.copy_(torch.from_numpy(buf))
+            bd.copy_(torch.from_numpy(np.stack(bs)))
+            _lib.check(lib.wg_lu_factor_batched(plan, Ad.data_ptr(), lda, strideA, ipiv.data_ptr(), info.data_ptr(),
+                                                _stream(torch)), "wg_lu_factor_batched")
+            _lib.check(lib.wg_lu_solve_batched(plan, Ad.data_ptr(), lda, strideA, bd.data_ptr(), n, _stream(torch)),
+                       "wg_lu_solve_batched")
+            torch.cuda.synchronize()
+    finally:
+        lib.wg_lu_destroy(plan)
+    out = Ad.cpu().numpy()
+    LUs = [out[i * strideA:i * strideA + n * lda].reshape(n, lda)[:, :n].copy() for i in range(B)]
+    return LUs, ipiv.cpu().numpy().reshape(B, n), info.cpu().numpy(), bd.cpu().numpy()
+
+
+@pytest.mark.parametrize("n,B,pad", [(37, 5, 0), (300, 7, 0), (513, 3, 2), (1900, 6, 0), (700, 40, 0)])
+def test_lu_batched_is_bit_identical_to_single(env, n, B, pad):
+    """Every system of a lock-step batch gets exactly the factors, pivots and solution of the single-system
+    path (same kernels, the batch is only a grid dimension) and agrees with LAPACK."""
+    rng = np.random.default_rng(n * 31 + B)
+    As = [rng.standard_normal((n, n)) + (i % 3) * np.eye(n) for i in range(B)]
+    bs = [rng.standard_normal(n) for _ in range(B)]
+    LUs, ipivs, infos, xs = _lu_batched(env, As, bs, pad=pad, graph=True)
+    assert not infos.any()
+    for i in (0, B // 2, B - 1):
+        LU1, ipiv1, info1, x1 = _lu(env, As[i], bs[i], lda=n + pad)
+        assert info1 == 0
+        assert np.array_equal(ipivs[i], ipiv1)
+        assert np.array_equal(LUs[i], LU1)
+        assert np.array_equal(xs[i], x1)
+    for i in range(B):
+        ref = np.linalg.solve(As[i], bs[i])
+        assert np.max(np.abs(xs[i] - ref)) <= 1e-9 * np.max(np.abs(ref))
+
+
+def test_lu_batched_singular_member(env):
+    """One singular system in a batch: its info is set LAPACK-style, the others are unaffected."""
+    n, B = 200, 4
+    rng = np.random.default_rng(5)
+    As = [rng.standard_normal((n, n)) for _ in range(B)]
+    As[2][:, 17] = 0.0
+    bs = [rng.standard_normal(n) for _ in range(B)]
+    LUs, ipivs, infos, xs = _lu_batched(env, As, bs)
+    assert list(infos) == [0, 0, 18, 0]
+    for i in (0, 1, 3):
+        ref = np.linalg.solve(As[i], bs[i])
+        assert np.max(np.abs(xs[i] - ref)) <= 1e-9 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("n", [1, 31, 128, 129, 300, 1900, 5000])
+def test_trisolve_wavefront_equals_block_steps(env, n):
+    """The persistent wavefront form of the triangular solves (two launches, ticket + published counter) gives
+    the bits of the one-launch-per-block form, on streams and as a graph, run after run; and solves the system."""
+    torch, lib, _ = env
+    rng = np.random.default_rng(11 * n + 1)
+    A = rng.standard_normal((n, n))
+    b = rng.standard_normal(n)
+    outs = []
+    try:
+        for wave, graph in ((1, 1), (0, 1), (1, 0), (1, 1)):
+            lib.wg_debug_wave_solve(wave)
+            lib.wg_set_tuning(256, graph)
+            LU, ipiv, info, x = _lu(env, A, b)
+            assert info == 0
+            outs.append(x)
+    finally:
+        lib.wg_debug_wave_solve(1)
+        lib.wg_set_tuning(256, 1)
+    for x in outs[1:]:
+        assert np.array_equal(outs[0], x)
+    xr = np.linalg.solve(A, b)
+    assert np.max(np.abs(outs[0] - xr)) / np.max(np.abs(xr)) < 1e-9
+
+
+def test_trisolve_wavefront_many_right_hand_sides(env):
+    """Repeated solves with one set of factors (checkLinearization re-uses them): the counters are reset by every
+    call, results repeat exactly."""
+    torch, lib, _lib = env
+    n = 2000
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((n, n))
+    Ad = torch.from_numpy(A.copy()).cuda()
+    ipiv = torch.zeros(n, dtype=torch.int32, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    plan = C.c_void_p()
+    _lib.check(lib.wg_lu_create(n, 0, C.byref(plan)), "wg_lu_create")
+    try:
+        _lib.check(lib.wg_lu_factor(plan, Ad.data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), _stream(torch)), "factor")
+        first = None
+        for rep in range(5):
+            bs = [rng.standard_normal(n) for _ in range(3)] if rep == 0 else bs
+            xs = []
+            for b in bs:
+                bd = torch.from_numpy(b.copy()).cuda()
+                _lib.check(lib.wg_lu_solve(plan, Ad.data_ptr(), n, bd.data_ptr(), _stream(torch)), "solve")
+                xs.append(bd.cpu().numpy())
+            if first is None:
+                first = xs
+                for b, x in zip(bs, xs):
+                    assert np.max(np.abs(A @ x - b)) < 1e-8 * np.max(np.abs(x)) * n ** 0.5
+            else:
+                for x0, x in zip(first, xs):
+                    assert np.array_equal(x0, x)
+    finally:
+        lib.wg_lu_destroy(plan)

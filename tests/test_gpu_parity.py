@@ -253,6 +253,43 @@ def test_getDeltasBatch_equals_sequential(cuda_device):
     assert solver.getDeltasBatch([], concurrency=2) == []
 
 
+@pytest.mark.parametrize("P,M,N,option", [(2, 12, 7, "AUTO"), (1, 20, 11, "AUTO"), (3, 8, 9, "THIRD"), (1, 10, 7, "NONE")])
+def test_getDeltasStrided_equals_sequential(cuda_device, P, M, N, option):
+    """The lock-step strided-batch path (wg_batch_*: one launch sequence for a whole batch of small systems)
+    returns, for every system, exactly what getDeltas() returns -- deltaF, all four moments, truncation
+    decisions, peaks and error estimate -- for full, short (padded) and single batches."""
+    import wallgo_b200 as wb
+    from wallgo_b200 import synthetic
+    from wallgo_b200.containers import ETruncationOption
+
+    grid = synthetic.makeGrid(M, N)
+    parts = synthetic.makeParticles(P)
+    solver = wb.BoltzmannSolver(grid, truncationOption=ETruncationOption[option])
+    solver.updateParticleList(parts)
+    solver.setCollisionArray(synthetic.makeCollision(grid, parts))
+    bgs = [synthetic.makeBackground(grid, velocityMid=-0.25 - 0.045 * i) for i in range(11)]
+    seq = []
+    for bg in bgs:
+        solver.setBackground(bg)
+        seq.append(solver.getDeltas())
+
+    def same(a, b):
+        assert np.array_equal(a.deltaF, b.deltaF)
+        for name in ("Delta00", "Delta02", "Delta20", "Delta11"):
+            assert np.array_equal(getattr(a.Deltas, name).coefficients, getattr(b.Deltas, name).coefficients)
+        assert a.truncatedTail == b.truncatedTail and a.spectralPeaks == b.spectralPeaks
+        assert a.truncationError == b.truncationError
+
+    for batch in (4, 11, 1, None):
+        out = solver.getDeltasStrided(bgs, batch=batch) if batch else solver.getDeltasBatch(bgs)
+        assert len(out) == len(bgs)
+        for a, b in zip(seq, out):
+            same(a, b)
+    # the single-system path still works on the same solver afterwards
+    solver.setBackground(bgs[3])
+    same(seq[3], solver.getDeltas())
+
+
 def test_batched_c_abi_equals_single_calls(cuda_device):
     """wg_assemble_factor_solve_batched (B systems, B streams, one C call) gives exactly the deltaF of the
     single-system calls."""
@@ -438,3 +475,85 @@ def test_per_solver_tuning_does_not_leak(cuda_device):
     _lib.check(ea.lib.wg_solver_set_tuning(ea.h, 64, 0, 0, 0, 0), "wg_solver_set_tuning")
     ra, rb = a.getDeltas(), b.getDeltas()
     assert relmax(ra.deltaF, rb.deltaF) < 1e-12 and relmax(ra.deltaF, g["ref_deltaF_trunc"]) < TOL
+
+
+def _fuzz_solver(P, M, N, **kw):
+    """Solver + oracle problem of one tools/parity_fuzz.py case."""
+    import wallgo_b200 as wb
+    from conftest import FixtureBackground, FixtureGrid
+    from oracle import boltzmann_oracle as bo
+
+    option = kw.pop("option", "AUTO")
+    pb = bo.synthetic_problem(P, M, N, **kw)
+    g = dict(P=P, M=M, N=N, chi=pb.tab.chi, rz=pb.tab.rz, rp=pb.tab.rp, pz=pb.pz, pp=pb.pp,
+             dxidchi=pb.xi_dxidchi, dpzdrz=pb.dpzdrz, dppdrp=pb.dppdrp, vw=pb.vw, v=pb.v, T=pb.T, msq=pb.msq)
+    grid = FixtureGrid(g)
+    parts = [wb.Particle(f"p{a}", a, (lambda f, a=a: f.msq[a]), None, "Fermion" if pb.statistics[a] < 0 else "Boson", 12)
+             for a in range(P)]
+    solver = wb.BoltzmannSolver(grid, kw.get("basisM", "Cardinal"), kw.get("basisN", "Chebyshev"),
+                                kw.get("derivatives", "Spectral"), pb.collisionMultiplier,
+                                getattr(wb.ETruncationOption, option))
+    solver.updateParticleList(parts)
+    solver.setBackground(FixtureBackground(g))
+    solver.setCollisionArray(wb.CollisionArray(grid, kw.get("basisN", "Chebyshev"), parts, pb.collision))
+    return solver, pb
+
+
+@pytest.mark.parametrize("case", [
+    # the round-1 fuzz outlier (cond ~ 1.2e7: LAPACK itself is 3.6e-11 off the true solution)
+    dict(P=3, M=10, N=13, seed=220, r=0.05, collisionMultiplier=0.01, vw_mid=-0.7303480839249901, basisM="Cardinal",
+         basisN="Cardinal", derivatives="Finite Difference", grid3=False, option="THIRD"),
+    dict(P=2, M=12, N=9, seed=7, r=0.05, collisionMultiplier=0.01, vw_mid=-0.6, grid3=True),
+    dict(P=1, M=14, N=11, seed=3, r=0.5, collisionMultiplier=1.0, vw_mid=-0.3, grid3=True),
+])
+def test_refinement_reaches_the_extended_precision_solution(cuda_device, case):
+    """wg_refine (residual with regenerated operator entries in double-double + one solve with the existing
+    factors): deltaF agrees with the extended-precision solution of the assembled FP64 system to 1e-12 -- far
+    inside the 1e-10 gate also where cond(A) * eps is not -- and the reported correction is the forward error
+    the unrefined solve had."""
+    from oracle import boltzmann_oracle as bo
+
+    case = dict(case)
+    P, M, N = case.pop("P"), case.pop("M"), case.pop("N")
+    solver, pb = _fuzz_solver(P, M, N, **case)
+    A, b = bo.assemble(pb)
+    xTrue, xLapack = bo.solve_extended(A, b)
+    solver.refinementSteps = 0
+    x0 = solver.solveBoltzmannEquations().reshape(-1)
+    solver.refinementSteps = 1
+    x1 = solver.solveBoltzmannEquations().reshape(-1)
+    e0, e1, eL = relmax(x0, xTrue), relmax(x1, xTrue), relmax(xLapack, xTrue)
+    print(f"n={A.shape[0]} cond~{np.linalg.cond(A):.1e}: unrefined {e0:.2e}, LAPACK {eL:.2e}, refined {e1:.2e}")
+    assert e1 < 1e-12
+    assert e1 <= max(e0, 1e-15)
+    assert relmax(x1, xLapack) < 1e-10 or eL > 5e-11      # the reference path's own answer, where it is accurate
+    solver.getDeltas()
+    dmax, xmax = solver.lastRefinement
+    assert abs(dmax / xmax - e0) <= 0.5 * e0 + 1e-15      # the correction IS the forward error of the first solve
+
+
+def test_refinement_in_every_path_is_the_same(cuda_device):
+    """getDeltas, the slot pool and the strided batch all apply the same refinement step: bit-identical results,
+    and switching it off changes them (so the step really runs)."""
+    import wallgo_b200 as wb
+    from wallgo_b200 import synthetic
+
+    P, M, N = 2, 10, 7
+    grid = synthetic.makeGrid(M, N)
+    parts = synthetic.makeParticles(P)
+    solver = wb.BoltzmannSolver(grid)
+    solver.updateParticleList(parts)
+    solver.setCollisionArray(synthetic.makeCollision(grid, parts))
+    bgs = [synthetic.makeBackground(grid, velocityMid=-0.3 - 0.05 * i) for i in range(5)]
+    seq = []
+    for bg in bgs:
+        solver.setBackground(bg)
+        seq.append(solver.getDeltas().deltaF)
+    for out in (solver.getDeltasBatch(bgs, concurrency=2), solver.getDeltasStrided(bgs, batch=3)):
+        for a, r in zip(seq, out):
+            assert np.array_equal(a, r.deltaF)
+    solver.refinementSteps = 0
+    solver.setBackground(bgs[0])
+    plain = solver.getDeltas().deltaF
+    assert not np.array_equal(plain, seq[0])
+    assert relmax(plain, seq[0]) < 1e-10

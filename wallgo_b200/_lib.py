@@ -38,6 +38,7 @@ SYMBOLS = {
     "wg_factor": (C.c_int, [_vp, _dp, C.c_longlong, _vp]),
     "wg_factor_solve": (C.c_int, [_vp, _dp, C.c_longlong, _dp, _vp]),
     "wg_solve": (C.c_int, [_vp, _dp, C.c_longlong, _dp, _vp]),
+    "wg_refine": (C.c_int, [_vp, _dp, C.c_double, C.c_double, _dp, C.c_longlong, _dp, _dp, _vp]),
     "wg_assemble_factor_solve_batched": (C.c_int, [C.c_int, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_double),
                                                    C.POINTER(C.c_double), C.POINTER(_vp), C.POINTER(C.c_longlong),
                                                    C.POINTER(_vp), C.POINTER(_vp)]),
@@ -49,7 +50,19 @@ SYMBOLS = {
     "wg_feedback": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int, C.c_double, _dp, _vp]),
     "wg_collision_apply": (C.c_int, [_vp, _dp, _dp, _vp]),
     "wg_change_basis": (C.c_int, [_vp, C.c_int, _dp, _dp, _vp]),
+    "wg_batch_create": (C.c_int, [_vp, C.c_int, C.POINTER(_vp)]),
+    "wg_batch_destroy": (C.c_int, [_vp]),
+    "wg_batch_assemble": (C.c_int, [_vp, _dp, _dp, C.c_double, C.c_int, _dp, C.c_longlong, C.c_longlong, _dp, _vp]),
+    "wg_batch_factor": (C.c_int, [_vp, _dp, C.c_longlong, C.c_longlong, _vp]),
+    "wg_batch_solve": (C.c_int, [_vp, _dp, C.c_longlong, C.c_longlong, _dp, _vp]),
+    "wg_batch_refine": (C.c_int, [_vp, _dp, _dp, C.c_double, _dp, C.c_longlong, C.c_longlong, _dp, _dp, _vp]),
+    "wg_batch_info": (C.c_int, [_vp, _vp, C.POINTER(C.c_int)]),
+    "wg_batch_spectra": (C.c_int, [_vp, _dp, _dp, _vp]),
+    "wg_batch_moments": (C.c_int, [_vp, _dp, _dp, _ip, C.c_int, _dp, _dp, _dp, _vp]),
     "wg_lu_create": (C.c_int, [C.c_int, C.c_int, C.POINTER(_vp)]),
+    "wg_lu_create_batched": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "wg_lu_factor_batched": (C.c_int, [_vp, _dp, C.c_longlong, C.c_longlong, _ip, _ip, _vp]),
+    "wg_lu_solve_batched": (C.c_int, [_vp, _dp, C.c_longlong, C.c_longlong, _dp, C.c_longlong, _vp]),
     "wg_lu_destroy": (C.c_int, [_vp]),
     "wg_lu_factor": (C.c_int, [_vp, _dp, C.c_longlong, _ip, _ip, _vp]),
     "wg_lu_solve": (C.c_int, [_vp, _dp, C.c_longlong, _dp, _vp]),

@@ -106,7 +106,8 @@ class _SlotPool:
         pm = 4 * eng.P * eng.M1
         dF = h[:eng.n].reshape(eng.P, eng.M1, eng.N1, eng.N1).copy()
         deltas = h[eng.n:eng.n + pm].reshape(4, eng.P, eng.M1).copy()
-        err = h[eng.n + pm:].reshape(eng.P, 4).copy()
+        err = h[eng.n + pm:eng.n + pm + 4 * eng.P].reshape(eng.P, 4).copy()
+        s_.lastRefinement = (float(h[-2]), float(h[-1])) if getattr(s_, "refinementSteps", 1) else None
         self.state[slot] = None
         finished.append((token, (dF, deltas, err, keep, peaks) if self.rawResults else
                          s_._wrapResults(dF, deltas, err, keep, peaks)))
@@ -151,6 +152,11 @@ class BoltzmannSolverB200Mixin:
         self.device = device
         self._engine = None
         self._staticKey = None
+        # Steps of mixed-precision iterative refinement after the LU solve (0 or 1; wg_refine): removes the
+        # cond(A)*eps forward error of the FP64 solve for ~1 % of its cost.  lastRefinement = (max|correction|,
+        # max|deltaF|) of the most recent getDeltas(); the ratio / 2^-53 estimates the condition number.
+        self.refinementSteps = 1
+        self.lastRefinement = None
 
     def setBackground(self, background) -> None:
         """Deep-copies and boosts to the plasma frame (boltzmann.py:116-123)."""
@@ -183,6 +189,7 @@ class BoltzmannSolverB200Mixin:
         st["_staticKey"] = None
         st["_sibs"] = None
         st["_stream"] = None
+        st["_batchEng"] = None
         return st
 
     def __deepcopy__(self, memo):
@@ -190,7 +197,7 @@ class BoltzmannSolverB200Mixin:
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_engine", "_staticKey", "_sibs", "_stream"):
+            if k in ("_engine", "_staticKey", "_sibs", "_stream", "_batchEng"):
                 setattr(new, k, None)
             elif k == "grid":
                 setattr(new, k, deepcopy(v, memo))
@@ -264,6 +271,8 @@ class BoltzmannSolverB200Mixin:
         eng.assemble(float(vw), float(self.collisionMultiplier))
         eng.factor()
         eng.solve()
+        if getattr(self, "refinementSteps", 1):
+            eng.refine(float(vw), float(self.collisionMultiplier))
         return eng
 
     def _solveOnDevice(self, fused: bool = False):
@@ -279,6 +288,8 @@ class BoltzmannSolverB200Mixin:
         else:
             eng.factor()
             eng.solve()
+        if getattr(self, "refinementSteps", 1):
+            eng.refine(float(self.background.velocityWall), float(self.collisionMultiplier))
         return eng
 
     def _shape(self):
@@ -391,6 +402,7 @@ class BoltzmannSolverB200Mixin:
             info = eng.info()
             if info != 0:
                 raise np.linalg.LinAlgError("Singular matrix")
+            self.lastRefinement = eng.last_refinement if getattr(self, "refinementSteps", 1) else None
         return self._wrapResults(dF, deltas, err, keep, peaks)
 
     def getFeedback(self):
@@ -429,12 +441,13 @@ class BoltzmannSolverB200Mixin:
             sibs = [self] if sibs is None else sibs
             while len(sibs) < count:
                 c = copy.copy(self)
-                c._engine, c._staticKey, c._sibs, c._stream = None, None, None, None
+                c._engine, c._staticKey, c._sibs, c._stream, c._batchEng = None, None, None, None, None
                 sibs.append(c)
             self._sibs = sibs
         for s_ in sibs[:count]:
             s_.basisM, s_.basisN, s_.derivatives = self.basisM, self.basisN, self.derivatives
             s_.collisionMultiplier, s_.truncationOption = self.collisionMultiplier, self.truncationOption
+            s_.refinementSteps = getattr(self, "refinementSteps", 1)
             s_.collisionArray, s_.offEqParticles, s_.grid = self.collisionArray, self.offEqParticles, self.grid
         return sibs[:count]
 
@@ -480,6 +493,8 @@ class BoltzmannSolverB200Mixin:
         nItems = len(backgrounds)
         if nItems == 0:
             return []
+        if concurrency is None and nItems >= 2 and self._getEngine().n <= self.STRIDED_MAX_N:
+            return self.getDeltasStrided(backgrounds)
         if concurrency is None or int(concurrency) <= 0:
             concurrency = self._autoSlotCount()
         C = max(1, min(int(concurrency), nItems))
@@ -508,6 +523,92 @@ class BoltzmannSolverB200Mixin:
                         nextItem += 1
         finally:
             pool.close()
+        return results
+
+    # ------------------------------------------------------------------ strided batches (many small systems)
+    STRIDED_MAX_N = 4096     # systems up to this order go through the lock-step strided-batch kernels
+    STRIDED_BATCH = 64       # systems per launch sequence
+
+    def _batchEngines(self, count):
+        from .engine import BatchEngine
+
+        eng = self._getEngine()
+        cur = getattr(self, "_batchEng", None)
+        if cur is None or cur[0] is not eng or cur[1] != count:
+            if cur is not None:
+                for b in cur[2]:
+                    b.close()
+            cur = (eng, count, [BatchEngine(eng, count), BatchEngine(eng, count)])
+            self._batchEng = cur
+        return cur[2]
+
+    def getDeltasStrided(self, backgrounds, batch: int | None = None):
+        """getDeltas() for many independent backgrounds of a SMALL system (north star (2): batched LU): the
+        systems are processed `batch` at a time by launch sequences whose kernels carry the system index as a
+        grid dimension (wg_batch_*), two batches in flight so the host half of the truncation decision and the
+        result wrapping of one overlap the device work of the other.  Each result is bit-identical to
+        getDeltas() on the same background.  A short last batch is padded with copies of its last system."""
+        nItems = len(backgrounds)
+        if nItems == 0:
+            return []
+        eng = self._getEngine()
+        free = eng.torch.cuda.mem_get_info(eng.dev)[0]
+        cap = max(1, int(0.4 * free) // (2 * (8 * eng.n * eng.n + 2 * 8 * 256 * eng.n + 200 * eng.n)))
+        B = max(1, min(int(batch) if batch else self.STRIDED_BATCH, nItems, cap))
+        bes = self._batchEngines(B)
+        dxidchi, _, _ = self.grid.getCompactificationDerivatives()
+        roundtrip = self.truncationOption.name != "NONE"
+        mult = float(self.collisionMultiplier)
+        chunks = [list(range(i, min(i + B, nItems))) for i in range(0, nItems, B)]
+        results = [None] * nItems
+        state = {}       # chunk -> (event, keeps)
+
+        def start(c):
+            be = bes[c % 2]
+            for slot in range(B):
+                item = chunks[c][min(slot, len(chunks[c]) - 1)]
+                if slot >= len(chunks[c]) and slot > 0:
+                    be.inp_host[slot].copy_(be.inp_host[slot - 1])
+                    continue
+                self.setBackground(backgrounds[item])
+                bg = self.background
+                be.set_system(slot, np.asarray(bg.temperatureProfile, dtype=np.float64),
+                              np.asarray(bg.velocityProfile, dtype=np.float64), self._msq(bg.fieldProfiles), dxidchi,
+                              float(bg.velocityWall))
+            state[c] = (be.solve_async(mult, bool(getattr(self, "refinementSteps", 1))), None)
+
+        def decide(c):
+            be = bes[c % 2]
+            state[c][0].synchronize()
+            sp = be.spectra_host.numpy()
+            keeps = [self._decideTruncation(sp[slot].copy()) for slot in range(B)]
+            state[c] = (be.moments_async([k.dev for k, _ in keeps], roundtrip), keeps)
+
+        def finish(c):
+            be = bes[c % 2]
+            ev, keeps = state.pop(c)
+            ev.synchronize()
+            if any(be.infos()[:len(chunks[c])]):
+                raise np.linalg.LinAlgError("Singular matrix")
+            P, M1, N1 = eng.P, eng.M1, eng.N1
+            dFh, dh, eh = be.dF_host.numpy(), be.deltas_host.numpy(), be.err_host.numpy()
+            rs = be.refstats_host.numpy()
+            self.lastRefinement = (float(rs[len(chunks[c]) - 1, 0]), float(rs[len(chunks[c]) - 1, 1])) \
+                if getattr(self, "refinementSteps", 1) else None
+            for slot, item in enumerate(chunks[c]):
+                keep, peaks = keeps[slot]
+                results[item] = self._wrapResults(dFh[slot].reshape(P, M1, N1, N1).copy(),
+                                                  dh[slot].reshape(4, P, M1).copy(), eh[slot].reshape(P, 4).copy(),
+                                                  keep, peaks)
+
+        nC = len(chunks)
+        for c in range(nC + 2):
+            if c >= 2:
+                finish(c - 2)
+            if c < nC:
+                start(c)
+            if 1 <= c <= nC:
+                decide(c - 1)
         return results
 
     def _wrapResults(self, dF, deltas, err, keep, peaks):

@@ -258,6 +258,190 @@ __global__ void __launch_bounds__(512, WG_ASM_MINB) wg_assemble_kernel(BzDims d,
   }
 }
 
+// ============================================================================ residual for iterative refinement
+// r = S - A x with A never stored: every operator entry is formed exactly as wg_assemble_kernel forms it (same
+// expressions, same roundings: this file is compiled with -fmad=false) and multiplied into a DOUBLE-DOUBLE
+// accumulator (error-free product through fma, error-free sum), so the residual of the FP64 system is known
+// to ~1e-32 relative to |A||x| before it is rounded.  One solve with the existing LU factors on this residual
+// then removes the cond(A)*eps forward error of the first solve (mixed-precision refinement, SURVEY.md
+// section 7: "one step of FP64 iterative refinement").  Same CTA shape as the assembly: R rows per CTA.
+__device__ __forceinline__ void dd_add_prod(double& hi, double& lo, double a, double b) {
+  const double p = a * b;
+  const double e = fma(a, b, -p);          // a*b = p + e exactly
+  const double s = hi + p;
+  const double bb = s - hi;
+  const double err = (hi - (s - bb)) + (p - bb);   // hi + p = s + err exactly
+  hi = s;
+  lo += err + e;
+}
+__device__ __forceinline__ void dd_add_dd(double& hi, double& lo, double h2, double l2) {
+  const double s = hi + h2;
+  const double bb = s - hi;
+  const double err = (hi - (s - bb)) + (h2 - bb);
+  hi = s;
+  lo += l2 + err;
+}
+
+template <int R, int V>
+__global__ void __launch_bounds__(512, 1) wg_residual_kernel(BzDims d, const double* __restrict__ K1,
+                                                             const double* __restrict__ K2,
+                                                             const double* __restrict__ Coll,
+                                                             const double* __restrict__ Tchi,
+                                                             const double* __restrict__ Dchi,
+                                                             const double* __restrict__ w1,
+                                                             const double* __restrict__ w2,
+                                                             const double* __restrict__ cT2,
+                                                             const double* __restrict__ x, const double* __restrict__ S,
+                                                             double* __restrict__ rout, long long sV) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int q = d.q, M1 = d.M1, P = d.P;
+  w1 += (long long)blockIdx.z * d.n;
+  w2 += (long long)blockIdx.z * d.n;
+  cT2 += (long long)blockIdx.z * M1;
+  x += (long long)blockIdx.z * sV;
+  S += (long long)blockIdx.z * sV;
+  rout += (long long)blockIdx.z * sV;
+  double* K1s = reinterpret_cast<double*>(smraw);  // [R][q]
+  double* K2s = K1s + R * q;                       // [R][q]
+  double* Cs = K2s + R * q;                        // [R][P*q]
+  double* dch = Cs + (size_t)R * P * q;            // [M1]
+  double* tch = dch + M1;                          // [M1]
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ double redh[16][R], redl[16][R];
+
+  const int a = blockIdx.y / M1, al = blockIdx.y % M1;
+  const int bg0 = blockIdx.x * R;
+  const long long r0 = ((long long)a * M1 + al) * q + bg0;
+  const int tid = threadIdx.x;
+
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t kb = (uint32_t)(R * q * sizeof(double));
+    const uint32_t cb = (uint32_t)((size_t)R * P * q * sizeof(double));
+    mbar_expect_tx(&bar, 2 * kb + cb);
+    tma_load_1d(K1s, K1 + (size_t)bg0 * q, kb, &bar);
+    tma_load_1d(K2s, K2 + (size_t)bg0 * q, kb, &bar);
+    tma_load_1d(Cs, Coll + ((size_t)a * q + bg0) * ((size_t)P * q), cb, &bar);
+  }
+  for (int i = tid; i < M1; i += blockDim.x) {
+    dch[i] = Dchi[al * M1 + i];
+    tch[i] = Tchi[al * M1 + i];
+  }
+  double rw1[R], rw2[R];
+#pragma unroll
+  for (int rr = 0; rr < R; ++rr) {
+    rw1[rr] = w1[r0 + rr];
+    rw2[rr] = w2[r0 + rr];
+  }
+  const double ct2 = cT2[al];
+  __syncthreads();
+  mbar_wait(&bar, 0);
+
+  double hi[R], lo[R];
+#pragma unroll
+  for (int rr = 0; rr < R; ++rr) hi[rr] = lo[rr] = 0.0;
+  for (int cp = tid; cp < q / V; cp += blockDim.x) {
+    double wk[R][V];
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+      for (int v = 0; v < V; ++v) wk[rr][v] = rw1[rr] * K1s[rr * q + V * cp + v];
+    for (int b = 0; b < P; ++b) {
+      const bool same = (b == a);
+      const double* xin = x + (long long)b * M1 * q + V * cp;
+      for (int i = 0; i < M1; ++i, xin += q) {
+        const double dv = same ? dch[i] : 0.0;
+        const double tx = tch[i];
+        double xv[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) xv[v] = __ldg(xin + v);
+        if (tx == 0.0) {
+          if (dv == 0.0) continue;   // an exact zero block of the operator
+#pragma unroll
+          for (int rr = 0; rr < R; ++rr)
+#pragma unroll
+            for (int v = 0; v < V; ++v) dd_add_prod(hi[rr], lo[rr], wk[rr][v] * dv, xv[v]);
+        } else {
+          const double ctx = ct2 * tx;
+#pragma unroll
+          for (int rr = 0; rr < R; ++rr) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+              double e = wk[rr][v] * dv;
+              if (same) e -= (rw2[rr] * tx) * K2s[rr * q + V * cp + v];
+              e += ctx * Cs[((size_t)rr * P + b) * q + V * cp + v];
+              dd_add_prod(hi[rr], lo[rr], e, xv[v]);
+            }
+          }
+        }
+      }
+    }
+  }
+  // ---- CTA reduction of the R double-double sums, then r = S - (hi + lo)
+  const int lane = tid & 31, warp = tid >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int rr = 0; rr < R; ++rr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double h2 = __shfl_xor_sync(0xffffffffu, hi[rr], o);
+      const double l2 = __shfl_xor_sync(0xffffffffu, lo[rr], o);
+      dd_add_dd(hi[rr], lo[rr], h2, l2);
+    }
+    if (lane == 0) {
+      redh[warp][rr] = hi[rr];
+      redl[warp][rr] = lo[rr];
+    }
+  }
+  __syncthreads();
+  if (tid < R) {
+    double h = 0.0, l = 0.0;
+    for (int w = 0; w < nw; ++w) dd_add_dd(h, l, redh[w][tid], redl[w][tid]);
+    const double sv = S[r0 + tid];
+    double rh = sv, rl = 0.0;
+    dd_add_dd(rh, rl, -h, -l);
+    rout[r0 + tid] = rh + rl;
+  }
+}
+
+// x += dlt; stats[0] = max|dlt|, stats[1] = max|x| (after the update), per system
+__global__ void wg_refine_update_kernel(int n, double* __restrict__ x, const double* __restrict__ dlt,
+                                        double* __restrict__ stats, long long sV) {
+  __shared__ double red[2][32];
+  x += (long long)blockIdx.x * sV;
+  dlt += (long long)blockIdx.x * sV;
+  double md = 0.0, mx = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double dv = dlt[i];
+    const double xn = x[i] + dv;
+    x[i] = xn;
+    md = fmax(md, fabs(dv));   // fmax drops NaN operands: a non-finite correction shows up in max|x| only
+    mx = fmax(mx, fabs(xn));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+    red[0][warp] = md;
+    red[1][warp] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) {
+      md = fmax(md, red[0][w]);
+      mx = fmax(mx, red[1][w]);
+    }
+    stats[2 * blockIdx.x] = md;
+    stats[2 * blockIdx.x + 1] = mx;
+  }
+}
+
 // ============================================================================ basis changes / moments
 // in viewed as [outer][len][inner];  out[o][x][s] = sum_x' Mat[x][x'] * in[o][x'][s]
 __global__ void wg_apply_axis_kernel(const double* __restrict__ in, double* __restrict__ out,
@@ -559,6 +743,42 @@ int bz_assemble(const BzDims& d, const BzStatic& s, const double* prof, double v
     wg_assemble_kernel<R, 4><<<grid, threads, smem, st>>>(d, s.K1, s.K2, s.Coll, s.Tchi, s.Dchi, w1, w2, cT2, A, lda, bb.sA);
   else
     wg_assemble_kernel<R, 2><<<grid, threads, smem, st>>>(d, s.K1, s.K2, s.Coll, s.Tchi, s.Dchi, w1, w2, cT2, A, lda, bb.sA);
+  WG_LAUNCH_CHECK();
+  return WG_OK;
+}
+
+// r = S - A x for the operator of (prof, vw, collMult): the per-row weights and the source are re-evaluated
+// (O(n)), the operator entries are regenerated on the fly (never stored); Ssrc and r are n-vectors per system
+int bz_residual(const BzDims& d, const BzStatic& s, const double* prof, double vw, double collMult, double* derivs,
+                double* w1, double* w2, double* cT2, const double* x, double* Ssrc, double* r, cudaStream_t st,
+                const BzBatch& bb) {
+  WG_REQUIRE(d.q % 4 == 0, "residual: (N-1)^2 must be a multiple of 4 (N odd)");
+  const int nprof = (2 + d.P) * (d.M + 1) + d.M1;
+  const long long sV = bb.count > 1 ? bb.sV : 0;
+  wg_profile_deriv_kernel<<<bb.count, 256, 0, st>>>(d.M, d.P, s.DchiFull, prof, derivs, nprof);
+  WG_LAUNCH_CHECK();
+  wg_rows_kernel<<<dim3(wg_cdiv(d.n, 256), bb.count), 256, 0, st>>>(d, prof, derivs, s.pz, s.pp, s.dpzdrz, s.stat, vw,
+                                                                   collMult, 1.0, w1, w2, cT2, Ssrc, bb.vwArr, nprof, sV);
+  WG_LAUNCH_CHECK();
+  constexpr int R = 4;
+  const size_t smem = ((size_t)R * d.q * (2 + d.P) + 2 * d.M1) * sizeof(double);
+  WG_REQUIRE(smem <= 200 * 1024, "residual: basis tile does not fit in shared memory");
+  if (wg_func_configured(reinterpret_cast<const void*>(wg_residual_kernel<R, 4>), smem) < (long long)smem) {
+    WG_CUDA(cudaFuncSetAttribute(wg_residual_kernel<R, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WG_CUDA(cudaFuncSetAttribute(wg_residual_kernel<R, 4>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared));
+  }
+  dim3 grid(d.q / R, d.P * d.M1, bb.count);
+  int threads = ((d.q / 4 + 31) / 32) * 32;
+  if (threads > 512) threads = 512;
+  if (threads < 64) threads = 64;
+  wg_residual_kernel<R, 4><<<grid, threads, smem, st>>>(d, s.K1, s.K2, s.Coll, s.Tchi, s.Dchi, w1, w2, cT2, x, Ssrc, r, sV);
+  WG_LAUNCH_CHECK();
+  return WG_OK;
+}
+
+int bz_refine_update(int n, double* x, const double* dlt, double* stats, cudaStream_t st, int batch, long long sV) {
+  wg_refine_update_kernel<<<batch, 1024, 0, st>>>(n, x, dlt, stats, batch > 1 ? sV : 0);
   WG_LAUNCH_CHECK();
   return WG_OK;
 }

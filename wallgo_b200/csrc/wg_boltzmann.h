@@ -38,6 +38,10 @@ void bz_set_asm_wide(int on);
 int bz_assemble(const BzDims& d, const BzStatic& s, const double* prof, double vw, double collMult, int parts,
                 double* derivs, double* w1, double* w2, double* cT2, double* A, long long lda, double* S,
                 cudaStream_t st, const BzBatch& bb = BzBatch());
+int bz_residual(const BzDims& d, const BzStatic& s, const double* prof, double vw, double collMult, double* derivs,
+                double* w1, double* w2, double* cT2, const double* x, double* Ssrc, double* r, cudaStream_t st,
+                const BzBatch& bb = BzBatch());
+int bz_refine_update(int n, double* x, const double* dlt, double* stats, cudaStream_t st, int batch = 1, long long sV = 0);
 int bz_apply_axis(const double* in, double* out, const double* Mat, int outer, int len, int inner,
                   cudaStream_t st);
 int bz_spectra(const BzDims& d, const double* c, double* spectra, cudaStream_t st, int batch = 1);

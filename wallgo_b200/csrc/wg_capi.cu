@@ -83,6 +83,19 @@ struct wg_solver {
   const double* chebOf = nullptr;  // deltaF whose Chebyshev coefficients wg_spectra left in `cheb` (nullptr: none)
 };
 
+// Strided batch of `count` independent systems of one solver's shape, advanced in lock step by every kernel launch
+// (the system index is a grid dimension): shares the solver's static tables, owns the per-system scratch.
+struct wg_batch {
+  wg_solver* s = nullptr;
+  int count = 0;
+  std::vector<void*> allocs;
+  double *derivs = nullptr, *w1 = nullptr, *w2 = nullptr, *cT2 = nullptr;
+  double *cheb = nullptr, *bufA = nullptr, *bufB = nullptr;
+  int *ipiv = nullptr, *info = nullptr;
+  wg::LuPlan* plan = nullptr;
+  const double* chebOf = nullptr;
+};
+
 template <typename T>
 static int dev_alloc(wg_solver* s, T** p, size_t count) {
   WG_CUDA(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
@@ -156,6 +169,12 @@ int wg_debug_force_wb(int wb) {
 int wg_solver_set_tuning(wg_solver* s, int nb, int use_graph, int lookahead, int split_percent, int bulk_hi_rest) {
   WG_REQUIRE(s && s->plan, "wg_solver_set_tuning: NULL solver");
   wg::lu_plan_set_tuning(s->plan, nb, use_graph, lookahead, split_percent, bulk_hi_rest);
+  return WG_OK;
+}
+/* developer knob (not part of the public header): triangular solves as two persistent wavefront launches (1,
+ * default) or one launch per 128-row block (0); same bits either way */
+int wg_debug_wave_solve(int on) {
+  wg::lu_set_wave_solve(on);
   return WG_OK;
 }
 int wg_set_lookahead(int on) {
@@ -395,6 +414,23 @@ int wg_solve(wg_solver* s, const double* LU_dev, long long lda, double* b_dev, v
   return wg::lu_solve(s->plan, LU_dev, lda, b_dev, (cudaStream_t)stream);
 }
 
+int wg_refine(wg_solver* s, const double* profiles_dev, double vw, double collisionMultiplier, const double* LU_dev,
+              long long lda, double* x_dev, double* stats_dev, void* stream) {
+  WG_REQUIRE(s && profiles_dev && LU_dev && x_dev && stats_dev, "wg_refine: NULL argument");
+  WG_ON_DEVICE(s->device);
+  if (!(s->haveGrid && s->haveTables && s->haveColl && s->haveStat)) {
+    wg_set_error("wg_refine: grid, statistics, tables and collision tensor must be set first");
+    return WG_ERR_STATE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = wg::bz_residual(s->d, s->st, profiles_dev, vw, collisionMultiplier, s->derivs, s->w1, s->w2, s->cT2, x_dev,
+                           s->bufA, s->bufB, st);
+  if (rc) return rc;
+  rc = wg::lu_solve(s->plan, LU_dev, lda, s->bufB, st);
+  if (rc) return rc;
+  return wg::bz_refine_update(s->d.n, x_dev, s->bufB, stats_dev, st);
+}
+
 int wg_assemble_factor_solve_batched(int B, wg_solver* const* s, const double* const* profiles_dev,
                                      const double* vw, const double* collisionMultiplier, double* const* A_dev,
                                      const long long* lda, double* const* S_dev, void* const* streams) {
@@ -420,16 +456,18 @@ int wg_info(wg_solver* s, void* stream, int* info_host) {
 }
 
 // apply the (up to three) axis matrices of one stage; result always lands in `out`
-static int apply_stage(wg_solver* s, int stage, const double* in, double* out, cudaStream_t st) {
+// (batch > 1: `in`/`out` hold `batch` contiguous arrays, tmpA/tmpB are scratch of the same size)
+static int apply_stage(wg_solver* s, int stage, const double* in, double* out, cudaStream_t st, int batch = 1,
+                       double* tmpA = nullptr, double* tmpB = nullptr) {
   const wg::BzDims& d = s->d;
   const double* const* m = s->mats + 3 * stage;
   int cnt = (m[0] != nullptr) + (m[1] != nullptr) + (m[2] != nullptr);
   if (cnt == 0) {
-    if (in != out) WG_CUDA(cudaMemcpyAsync(out, in, sizeof(double) * d.n, cudaMemcpyDeviceToDevice, st));
+    if (in != out) WG_CUDA(cudaMemcpyAsync(out, in, sizeof(double) * d.n * batch, cudaMemcpyDeviceToDevice, st));
     return WG_OK;
   }
   const double* cur = in;
-  double* tmp[2] = {s->bufA, s->bufB};
+  double* tmp[2] = {tmpA ? tmpA : s->bufA, tmpB ? tmpB : s->bufB};
   int ti = 0;
   for (int ax = 0; ax < 3; ++ax) {
     if (!m[ax]) continue;
@@ -441,11 +479,11 @@ static int apply_stage(wg_solver* s, int stage, const double* in, double* out, c
     }
     int rc;
     if (ax == 0)
-      rc = wg::bz_apply_axis(cur, dst, m[ax], d.P, d.M1, d.q, st);
+      rc = wg::bz_apply_axis(cur, dst, m[ax], batch * d.P, d.M1, d.q, st);
     else if (ax == 1)
-      rc = wg::bz_apply_axis(cur, dst, m[ax], d.P * d.M1, d.N1, d.N1, st);
+      rc = wg::bz_apply_axis(cur, dst, m[ax], batch * d.P * d.M1, d.N1, d.N1, st);
     else
-      rc = wg::bz_apply_axis(cur, dst, m[ax], d.P * d.M1 * d.N1, d.N1, 1, st);
+      rc = wg::bz_apply_axis(cur, dst, m[ax], batch * d.P * d.M1 * d.N1, d.N1, 1, st);
     if (rc) return rc;
     cur = dst;
     ti ^= 1;
@@ -554,6 +592,182 @@ int wg_interpolate_collision(int device, int P, int NF, int NT, const double* Lz
   }
   release();
   return rc;
+}
+
+/* ---- strided batches: B systems per launch (many small systems; north-star "batched LU") */
+int wg_batch_create(wg_solver* s, int count, wg_batch** out) {
+  WG_REQUIRE(s && out && count >= 1 && count <= 4096, "wg_batch_create: bad argument");
+  WG_ON_DEVICE(s->device);
+  wg_batch* b = new wg_batch();
+  b->s = s;
+  b->count = count;
+  const wg::BzDims& d = s->d;
+  const size_t B = (size_t)count, n = d.n;
+  int rc = WG_OK;
+  auto alloc = [&](void** p, size_t bytes) {
+    if (rc) return;
+    if (cudaMalloc(p, bytes) != cudaSuccess) {
+      wg_set_error("wg_batch_create: out of device memory (%zu bytes)", bytes);
+      (void)cudaGetLastError();
+      rc = WG_ERR_CUDA;
+      return;
+    }
+    b->allocs.push_back(*p);
+  };
+  alloc((void**)&b->derivs, 8 * B * (size_t)(2 + d.P) * (d.M + 1));
+  alloc((void**)&b->w1, 8 * B * n);
+  alloc((void**)&b->w2, 8 * B * n);
+  alloc((void**)&b->cT2, 8 * B * d.M1);
+  alloc((void**)&b->cheb, 8 * B * n);
+  alloc((void**)&b->bufA, 8 * B * n);
+  alloc((void**)&b->bufB, 8 * B * n);
+  alloc((void**)&b->ipiv, 4 * B * n);
+  alloc((void**)&b->info, 4 * B);
+  if (!rc && cudaMemset(b->info, 0, 4 * B) != cudaSuccess) rc = WG_ERR_CUDA;
+  if (!rc) rc = wg::lu_plan_create(d.n, &b->plan, count);
+  if (rc) {
+    wg_batch_destroy(b);
+    return rc;
+  }
+  *out = b;
+  return WG_OK;
+}
+
+int wg_batch_destroy(wg_batch* b) {
+  if (!b) return WG_OK;
+  WG_ON_DEVICE(b->s->device);
+  for (void* p : b->allocs) cudaFree(p);
+  wg::lu_plan_destroy(b->plan);
+  delete b;
+  return WG_OK;
+}
+
+int wg_batch_assemble(wg_batch* b, const double* profiles_dev, const double* vw_dev, double collisionMultiplier,
+                      int parts, double* A_dev, long long lda, long long strideA, double* S_dev, void* stream) {
+  WG_REQUIRE(b && profiles_dev && vw_dev && A_dev && S_dev, "wg_batch_assemble: NULL argument");
+  wg_solver* s = b->s;
+  WG_ON_DEVICE(s->device);
+  if (!(s->haveGrid && s->haveTables && s->haveColl && s->haveStat)) {
+    wg_set_error("wg_batch_assemble: grid, statistics, tables and collision tensor must be set first");
+    return WG_ERR_STATE;
+  }
+  WG_REQUIRE(lda >= s->d.n && strideA >= lda * (long long)s->d.n, "wg_batch_assemble: lda < n or strideA < n*lda");
+  wg::BzBatch bb;
+  bb.count = b->count;
+  bb.sA = strideA;
+  bb.sV = s->d.n;
+  bb.vwArr = vw_dev;
+  return wg::bz_assemble(s->d, s->st, profiles_dev, 0.0, collisionMultiplier, parts, b->derivs, b->w1, b->w2, b->cT2,
+                         A_dev, lda, S_dev, (cudaStream_t)stream, bb);
+}
+
+int wg_batch_factor(wg_batch* b, double* A_dev, long long lda, long long strideA, void* stream) {
+  WG_REQUIRE(b && A_dev, "wg_batch_factor: NULL argument");
+  WG_ON_DEVICE(b->s->device);
+  return wg::lu_factor(b->plan, A_dev, lda, b->ipiv, b->info, (cudaStream_t)stream, nullptr, strideA, b->s->d.n);
+}
+
+int wg_batch_solve(wg_batch* b, const double* LU_dev, long long lda, long long strideA, double* rhs_dev, void* stream) {
+  WG_REQUIRE(b && LU_dev && rhs_dev, "wg_batch_solve: NULL argument");
+  WG_ON_DEVICE(b->s->device);
+  return wg::lu_solve(b->plan, LU_dev, lda, rhs_dev, (cudaStream_t)stream, false, strideA, b->s->d.n);
+}
+
+int wg_batch_refine(wg_batch* b, const double* profiles_dev, const double* vw_dev, double collisionMultiplier,
+                    const double* LU_dev, long long lda, long long strideA, double* x_dev, double* stats_dev, void* stream) {
+  WG_REQUIRE(b && profiles_dev && vw_dev && LU_dev && x_dev && stats_dev, "wg_batch_refine: NULL argument");
+  wg_solver* s = b->s;
+  WG_ON_DEVICE(s->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  wg::BzBatch bb;
+  bb.count = b->count;
+  bb.sA = strideA;
+  bb.sV = s->d.n;
+  bb.vwArr = vw_dev;
+  int rc = wg::bz_residual(s->d, s->st, profiles_dev, 0.0, collisionMultiplier, b->derivs, b->w1, b->w2, b->cT2, x_dev,
+                           b->bufA, b->bufB, st, bb);
+  if (rc) return rc;
+  rc = wg::lu_solve(b->plan, LU_dev, lda, b->bufB, st, false, strideA, s->d.n);
+  if (rc) return rc;
+  return wg::bz_refine_update(s->d.n, x_dev, b->bufB, stats_dev, st, b->count, s->d.n);
+}
+
+int wg_batch_info(wg_batch* b, void* stream, int* info_host) {
+  WG_REQUIRE(b && info_host, "wg_batch_info: NULL argument");
+  WG_ON_DEVICE(b->s->device);
+  WG_CUDA(cudaMemcpyAsync(info_host, b->info, sizeof(int) * b->count, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  WG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  return WG_OK;
+}
+
+int wg_batch_spectra(wg_batch* b, const double* deltaF_dev, double* spectra_dev, void* stream) {
+  WG_REQUIRE(b && deltaF_dev && spectra_dev, "wg_batch_spectra: NULL argument");
+  wg_solver* s = b->s;
+  WG_ON_DEVICE(s->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  b->chebOf = nullptr;
+  int rc = apply_stage(s, 0, deltaF_dev, b->cheb, st, b->count, b->bufA, b->bufB);
+  if (rc) return rc;
+  rc = wg::bz_spectra(s->d, b->cheb, spectra_dev, st, b->count);
+  if (rc == WG_OK) b->chebOf = deltaF_dev;
+  return rc;
+}
+
+int wg_batch_moments(wg_batch* b, const double* deltaF_dev, const double* profiles_dev, const int* keep_dev,
+                     int roundtrip, double* deltaF_out_dev, double* deltas_dev, double* err_dev, void* stream) {
+  WG_REQUIRE(b && deltaF_dev && profiles_dev && keep_dev && deltaF_out_dev && deltas_dev && err_dev,
+             "wg_batch_moments: NULL argument");
+  wg_solver* s = b->s;
+  WG_ON_DEVICE(s->device);
+  WG_REQUIRE(s->haveGrid, "wg_batch_moments: grid not set");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (b->chebOf != deltaF_dev) {
+    wg_set_error("wg_batch_moments: call wg_batch_spectra on the same deltaF_dev first");
+    return WG_ERR_STATE;
+  }
+  b->chebOf = nullptr;
+  int rc = wg::bz_truncate(s->d, b->cheb, 0, 0, 0, err_dev, st, b->count, keep_dev);
+  if (rc) return rc;
+  if (roundtrip) {
+    rc = apply_stage(s, 1, b->cheb, deltaF_out_dev, st, b->count, b->bufA, b->bufB);
+    if (rc) return rc;
+  } else if (deltaF_out_dev != deltaF_dev) {
+    WG_CUDA(cudaMemcpyAsync(deltaF_out_dev, deltaF_dev, sizeof(double) * s->d.n * b->count, cudaMemcpyDeviceToDevice, st));
+  }
+  double* card = b->cheb;
+  rc = apply_stage(s, 2, deltaF_out_dev, card, st, b->count, b->bufA, b->bufB);
+  if (rc) return rc;
+  return wg::bz_moments(s->d, s->st, card, profiles_dev, deltas_dev, st, b->count);
+}
+
+int wg_lu_create_batched(int n, int batch, int device, wg_lu** out) {
+  WG_REQUIRE(out && n > 0 && batch >= 1, "wg_lu_create_batched: bad argument");
+  int rc = require_device(device);
+  if (rc) return rc;
+  WG_ON_DEVICE(device);
+  wg_lu* p = new wg_lu();
+  p->device = device;
+  rc = wg::lu_plan_create(n, &p->plan, batch);
+  if (rc) {
+    delete p;
+    return rc;
+  }
+  *out = p;
+  return WG_OK;
+}
+
+int wg_lu_factor_batched(wg_lu* p, double* A_dev, long long lda, long long strideA, int* ipiv_dev, int* info_dev,
+                         void* stream) {
+  WG_REQUIRE(p, "wg_lu_factor_batched: NULL plan");
+  WG_ON_DEVICE(p->device);
+  return wg::lu_factor(p->plan, A_dev, lda, ipiv_dev, info_dev, (cudaStream_t)stream, nullptr, strideA, 0);
+}
+
+int wg_lu_solve_batched(wg_lu* p, const double* LU_dev, long long lda, long long strideA, double* b_dev,
+                        long long strideB, void* stream) {
+  WG_REQUIRE(p, "wg_lu_solve_batched: NULL plan");
+  WG_ON_DEVICE(p->device);
+  return wg::lu_solve(p->plan, LU_dev, lda, b_dev, (cudaStream_t)stream, false, strideA, strideB);
 }
 
 int wg_lu_create(int n, int device, wg_lu** out) {

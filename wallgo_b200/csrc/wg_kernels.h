@@ -27,6 +27,7 @@ int lu_factor(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStr
 int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st, bool backwardOnly = false,
              long long strideA = 0, long long strideB = 0);
 void lu_set_tuning(int nb, int use_graph);
+void lu_set_wave_solve(int on);
 void lu_plan_set_tuning(LuPlan* p, int nb, int use_graph, int lookahead, int split, int hi_rest);
 void lu_set_debug(long long* dev_buf, int c0);
 void lu_set_lookahead(int on);

@@ -56,6 +56,7 @@ struct LuTuning {
   int hiRest = 8192;  // bulk work moves to the high-priority bulk stream once the trailing matrix is this small
   int leaf32 = 0;
   int forceWb = 0;    // developer knob: force the leaf width class (4: the 8-rows-per-thread variant)
+  int waveSolve = 1;  // triangular solves as two persistent wavefront launches (0: one launch per 128-row block)
 };
 static LuTuning g_tune;
 static long long g_tune_epoch = 1;
@@ -77,6 +78,10 @@ void lu_set_tuning(int nb, int use_graph) {
 }
 void lu_set_lookahead(int on) {
   g_tune.lookahead = on;
+  ++g_tune_epoch;
+}
+void lu_set_wave_solve(int on) {
+  g_tune.waveSolve = on;
   ++g_tune_epoch;
 }
 
@@ -922,6 +927,55 @@ __global__ void lu_rhs_perm_panel_kernel(double* __restrict__ b, const int* __re
 constexpr int TS_BS = 128;
 constexpr int TS_LD = TS_BS + 1;
 
+// Solve of one diagonal block held in shared memory (T: [bs][TS_LD], ys: right-hand side -> solution): 32-wide
+// sub-blocks, warp-shuffle substitution by warp 0, the block's other rows updated by all threads.  Shared by the
+// per-block step kernel and the wavefront kernel, so both produce the same bits.
+template <bool UPPER>
+__device__ __forceinline__ void trisolve_diag_block(const double* __restrict__ T, double* __restrict__ ys, int bs, int tid,
+                                                    int lane, int warp) {
+  const int nsb = (bs + 31) / 32;
+  for (int q = 0; q < nsb; ++q) {
+    const int sb = UPPER ? (nsb - 1 - q) * 32 : q * 32;
+    const int sw = min(32, bs - sb);
+    if (warp == 0) {
+      double t[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r) t[r] = (lane < sw && r < sw) ? T[(sb + lane) * TS_LD + sb + r] : 0.0;
+      double yi = lane < sw ? ys[sb + lane] : 0.0;
+      if (!UPPER) {
+#pragma unroll
+        for (int r = 0; r < 32; ++r) {
+          const double yr = __shfl_sync(0xffffffffu, yi, r);
+          if (lane > r) yi = fma(-t[r], yr, yi);
+        }
+      } else {
+        double dinv = 1.0;
+#pragma unroll
+        for (int r = 0; r < 32; ++r)
+          if (lane == r) dinv = t[r];
+        dinv = (lane < sw) ? 1.0 / dinv : 1.0;  // one reciprocal per lane, off the dependent chain
+#pragma unroll
+        for (int r = 31; r >= 0; --r) {
+          if (r < sw) {
+            if (lane == r) yi = yi * dinv;
+            const double yr = __shfl_sync(0xffffffffu, yi, r);
+            if (lane < r) yi = fma(-t[r], yr, yi);
+          }
+        }
+      }
+      if (lane < sw) ys[sb + lane] = yi;
+    }
+    __syncthreads();
+    // remaining rows of the block
+    for (int i = UPPER ? tid : sb + sw + tid; UPPER ? (i < sb) : (i < bs); i += blockDim.x) {
+      double s = ys[i];
+      for (int c = 0; c < sw; ++c) s = fma(-T[i * TS_LD + sb + c], ys[sb + c], s);
+      ys[i] = s;
+    }
+    __syncthreads();
+  }
+}
+
 template <bool UPPER>
 __global__ void __launch_bounds__(256) lu_trisolve_step_kernel(const double* __restrict__ LU, long long lda,
                                                                double* __restrict__ b, int n, int kprev,
@@ -986,49 +1040,112 @@ __global__ void __launch_bounds__(256) lu_trisolve_step_kernel(const double* __r
   }
   cp_async_wait<0>();
   __syncthreads();
-  const int nsb = (bs + 31) / 32;
-  for (int q = 0; q < nsb; ++q) {
-    const int sb = UPPER ? (nsb - 1 - q) * 32 : q * 32;
-    const int sw = min(32, bs - sb);
-    if (warp == 0) {
-      double t[32];
-#pragma unroll
-      for (int r = 0; r < 32; ++r) t[r] = (lane < sw && r < sw) ? T[(sb + lane) * TS_LD + sb + r] : 0.0;
-      double yi = lane < sw ? ys[sb + lane] : 0.0;
-      if (!UPPER) {
-#pragma unroll
-        for (int r = 0; r < 32; ++r) {
-          const double yr = __shfl_sync(0xffffffffu, yi, r);
-          if (lane > r) yi = fma(-t[r], yr, yi);
-        }
-      } else {
-        double dinv = 1.0;
-#pragma unroll
-        for (int r = 0; r < 32; ++r)
-          if (lane == r) dinv = t[r];
-        dinv = (lane < sw) ? 1.0 / dinv : 1.0;  // one reciprocal per lane, off the dependent chain
-#pragma unroll
-        for (int r = 31; r >= 0; --r) {
-          if (r < sw) {
-            if (lane == r) yi = yi * dinv;
-            const double yr = __shfl_sync(0xffffffffu, yi, r);
-            if (lane < r) yi = fma(-t[r], yr, yi);
-          }
-        }
-      }
-      if (lane < sw) ys[sb + lane] = yi;
-    }
-    __syncthreads();
-    // remaining rows of the block
-    const int i = UPPER ? tid : sb + sw + tid;
-    if (UPPER ? (i < sb) : (i < bs)) {
-      double s = ys[i];
-      for (int c = 0; c < sw; ++c) s = fma(-T[i * TS_LD + sb + c], ys[sb + c], s);
-      ys[i] = s;
-    }
-    __syncthreads();
-  }
+  trisolve_diag_block<UPPER>(T, ys, bs, tid, lane, warp);
   if (tid < bs) b[kb + tid] = ys[tid];
+}
+
+// Whole triangular solve in ONE persistent launch (wavefront over the 128-row blocks).  CTAs take row blocks
+// in solve order from an atomic ticket (so a block is only ever waited on by CTAs that started after its owner:
+// no co-residency requirement, no deadlock); the owner of block I streams its rows of L (or U) against the
+// already published parts of the solution -- most of that work happens long before block I is due -- then,
+// once `done` says block I-1 is published, applies it, solves the diagonal block from shared memory and
+// publishes its 128 values (st + __threadfence + release store of the counter).  The per-row arithmetic is
+// the step kernel's, in the same order (one 128-column dot product per earlier block, subtracted in solve
+// order; same diagonal solve), so both kernels give the same bits.  The factors are read exactly once:
+// 8*n^2/2 bytes per direction, HBM bound apart from the 128-step substitution chain of each diagonal block.
+// sync[0] = ticket, sync[1] = blocks published (per system and direction; zeroed before the launch).
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+template <bool UPPER>
+__global__ void __launch_bounds__(256, 1) lu_trisolve_wave_kernel(const double* __restrict__ LU, long long lda,
+                                                                  double* __restrict__ b, int n, int* __restrict__ sync,
+                                                                  long long sA, long long sV) {
+  LU += (long long)blockIdx.y * sA;   // system of the batch
+  b += (long long)blockIdx.y * sV;
+  sync += 4 * blockIdx.y + (UPPER ? 2 : 0);
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double* T = reinterpret_cast<double*>(smraw);  // [TS_BS][TS_LD] diagonal block
+  double* ys = T + TS_BS * TS_LD;                // [TS_BS] this block's right-hand side / solution
+  __shared__ int ticket;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nblk = (n + TS_BS - 1) / TS_BS;
+  constexpr int RPW = TS_BS / 8;   // rows per warp
+  constexpr int CPL = TS_BS / 32;  // columns per lane
+  int seen = 0;                    // blocks known to be published
+  for (;;) {
+    __syncthreads();               // previous block's use of `ticket`, T and ys is over
+    if (tid == 0) ticket = atomicAdd(&sync[0], 1);
+    __syncthreads();
+    const int q = ticket;          // position in solve order
+    if (q >= nblk) return;
+    const int blk = UPPER ? nblk - 1 - q : q;
+    const int kb = blk * TS_BS;
+    const int bs = min(TS_BS, n - kb);
+    {  // diagonal block -> shared memory, asynchronously (static data: no dependency)
+      const int c = tid & (TS_BS - 1);
+      for (int i = tid >> 7; i < bs; i += 2)
+        cp_async8(&T[i * TS_LD + c], LU + (long long)(kb + i) * lda + kb + c, c < bs);
+      cp_async_commit();
+    }
+    double acc[RPW];
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) acc[rr] = b[kb + min(warp * RPW + rr, bs - 1)];
+    for (int k = 0; k < q; ++k) {          // earlier blocks in solve order
+      const int pblk = UPPER ? nblk - 1 - k : k;
+      const int kp = pblk * TS_BS;
+      const int bsp = min(TS_BS, n - kp);
+      // the factor entries do not depend on the solution: all RPW*CPL loads of a lane are in flight before the wait
+      double v[RPW][CPL];
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) {
+        const double* row = LU + (long long)(kb + min(warp * RPW + rr, bs - 1)) * lda + kp;
+#pragma unroll
+        for (int u = 0; u < CPL; ++u) v[rr][u] = __ldcs(row + min(lane + 32 * u, bsp - 1));
+      }
+      if (k >= seen) {
+        if (lane == 0) {
+          int d = ld_acquire_gpu(&sync[1]);
+          while (d <= k) {
+            __nanosleep(20);
+            d = ld_acquire_gpu(&sync[1]);
+          }
+          seen = d;
+        }
+        seen = __shfl_sync(0xffffffffu, seen, 0);
+        __syncwarp();   // orders the other lanes' loads of the solution behind lane 0's acquire
+      }
+      double xv[CPL];
+#pragma unroll
+      for (int u = 0; u < CPL; ++u) xv[u] = (lane + 32 * u < bsp) ? __ldcg(b + kp + lane + 32 * u) : 0.0;
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) {
+        double sacc = 0.0;
+#pragma unroll
+        for (int u = 0; u < CPL; ++u)
+          if (lane + 32 * u < bsp) sacc = fma(v[rr][u], xv[u], sacc);
+        acc[rr] -= warp_sum(sacc);
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr)
+        if (warp * RPW + rr < bs) ys[warp * RPW + rr] = acc[rr];
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    trisolve_diag_block<UPPER>(T, ys, bs, tid, lane, warp);
+    if (tid < bs) b[kb + tid] = ys[tid];
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) st_release_gpu(&sync[1], q + 1);
+  }
 }
 
 // ------------------------------------------------------------------ host-side plan / scheduler
@@ -1045,6 +1162,8 @@ struct LuPlan {
   int *grpSrcTop = nullptr, *grpBDst = nullptr;
   int *permSrcTop = nullptr, *permBDst = nullptr, *permBSrc = nullptr, *permNBot = nullptr;
   int* posContent = nullptr;
+  int* solveSync = nullptr;                // [batch][4] ticket / published counters of the wavefront solves
+  int numSMs = 148;
   double *S = nullptr, *S2 = nullptr;      // row staging of the bulk permutation (256 x n each)
   double *Sc = nullptr, *Sc2 = nullptr;    // row staging of the chain permutation (256 x 256 each)
   cudaStream_t panelStream = nullptr;  // highest priority: the critical chain (next panel's columns + panel)
@@ -1074,16 +1193,20 @@ struct LuPlan {
   int* gipiv = nullptr;
   int* ginfo = nullptr;
   double* grhs = nullptr;
+  long long gsA = 0, gsV = 0;   // batch strides baked into the factorisation graph
   // forward-solve state while the factorisation is being enqueued with a fused right-hand side
   double* rhs = nullptr;
   int rhsPrev = -1, rhsPrevBs = 0;
-  // CUDA-graph cache of the triangular solves for one (factors, right-hand side) pair
-  cudaGraphExec_t solveExec = nullptr;
-  long long solveLaunches = 0;
-  const double* sLU = nullptr;
-  long long slda = 0;
-  double* sb = nullptr;
-  int sBackOnly = 0;
+  // CUDA-graph cache of the triangular solves: two (factors, right-hand side) pairs
+  struct SolveGraph {
+    cudaGraphExec_t exec = nullptr;
+    long long launches = 0, lda = 0, sA = 0, sV = 0, lastUse = 0;
+    const double* LU = nullptr;
+    double* b = nullptr;
+    int backOnly = 0;
+  };
+  SolveGraph solveGraphs[2];
+  long long solveUse = 0;
 };
 
 template <int W, int R>
@@ -1146,6 +1269,12 @@ static int lu_plan_fill(LuPlan* p, int n, int batch) {
   WG_CUDA(cudaMalloc(&p->permNBot, sizeof(int) * npanels * B));
   WG_CUDA(cudaMalloc(&p->posContent, sizeof(int) * n * B));
   WG_CUDA(cudaMemset(p->posContent, 0xff, sizeof(int) * n * B));
+  WG_CUDA(cudaMalloc(&p->solveSync, sizeof(int) * 4 * B));
+  {
+    int dev = 0;
+    WG_CUDA(cudaGetDevice(&dev));
+    WG_CUDA(cudaDeviceGetAttribute(&p->numSMs, cudaDevAttrMultiProcessorCount, dev));
+  }
   WG_CUDA(cudaMemset(p->permNBot, 0, sizeof(int) * npanels * B));
   const size_t sbytes = sizeof(double) * (size_t)256 * (size_t)n * B;
   WG_CUDA(cudaMalloc(&p->S, sbytes));
@@ -1176,9 +1305,11 @@ static int lu_plan_fill(LuPlan* p, int n, int batch) {
 
 static void lu_drop_graphs(LuPlan* p) {
   if (p->exec) cudaGraphExecDestroy(p->exec);
-  if (p->solveExec) cudaGraphExecDestroy(p->solveExec);
+  for (auto& c : p->solveGraphs) {
+    if (c.exec) cudaGraphExecDestroy(c.exec);
+    c.exec = nullptr;
+  }
   p->exec = nullptr;
-  p->solveExec = nullptr;
 }
 
 void lu_plan_destroy(LuPlan* p) {
@@ -1206,6 +1337,7 @@ void lu_plan_destroy(LuPlan* p) {
   cudaFree(p->permBSrc);
   cudaFree(p->permNBot);
   cudaFree(p->posContent);
+  cudaFree(p->solveSync);
   cudaFree(p->S);
   cudaFree(p->S2);
   cudaFree(p->Sc);
@@ -1406,6 +1538,8 @@ static int trisolve_configure() {
   if (wg_func_configured(reinterpret_cast<const void*>(lu_trisolve_step_kernel<false>), smem) < (long long)smem) {
     WG_CUDA(cudaFuncSetAttribute(lu_trisolve_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WG_CUDA(cudaFuncSetAttribute(lu_trisolve_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WG_CUDA(cudaFuncSetAttribute(lu_trisolve_wave_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WG_CUDA(cudaFuncSetAttribute(lu_trisolve_wave_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   return WG_OK;
 }
@@ -1632,11 +1766,12 @@ int lu_factor(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStr
   WG_REQUIRE(p->batch == 1 || strideA >= (long long)p->n * lda, "lu_factor: batch stride smaller than one operator");
   p->rhs = rhs;   // non-null: the forward solve L y = P rhs rides along (finish with lu_solve(..., backwardOnly))
   lu_sync_tuning(p);
-  if (p->bt.sA != strideA || p->bt.sV != strideRhs) lu_drop_graphs(p);   // strides are baked into a captured graph
   p->bt.sA = p->batch > 1 ? strideA : 0;
-  p->bt.sV = p->batch > 1 ? strideRhs : 0;
+  p->bt.sV = (p->batch > 1 && rhs) ? strideRhs : 0;
   if (!p->t.useGraph) return factor_enqueue(p, A, lda, ipiv, info, st);
-  if (!p->exec || p->gA != A || p->glda != lda || p->gipiv != ipiv || p->ginfo != info || p->grhs != rhs) {
+  // (the strides are baked into a captured graph, like the pointers)
+  if (!p->exec || p->gA != A || p->glda != lda || p->gipiv != ipiv || p->ginfo != info || p->grhs != rhs ||
+      p->gsA != p->bt.sA || p->gsV != p->bt.sV) {
     if (p->exec) {
       cudaGraphExecDestroy(p->exec);
       p->exec = nullptr;
@@ -1663,6 +1798,8 @@ int lu_factor(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStr
     p->gipiv = ipiv;
     p->ginfo = info;
     p->grhs = rhs;
+    p->gsA = p->bt.sA;
+    p->gsV = p->bt.sV;
   }
   WG_CUDA(cudaGraphLaunch(p->exec, st));
   g_wg_launches += p->graphLaunches;
@@ -1675,24 +1812,30 @@ int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t
              long long strideA, long long strideB) {
   WG_REQUIRE(p && LU && b && lda >= p->n, "lu_solve: bad arguments");
   lu_sync_tuning(p);
-  {
-    const long long sA = p->batch > 1 ? strideA : 0, sV = p->batch > 1 ? strideB : 0;
-    if (p->bt.sA != sA || p->bt.sV != sV) lu_drop_graphs(p);
-    p->bt.sA = sA;
-    p->bt.sV = sV;
-  }
+  p->bt.sA = p->batch > 1 ? strideA : 0;
+  p->bt.sV = p->batch > 1 ? strideB : 0;
   if (!p->t.useGraph) return solve_enqueue(p, LU, lda, b, st, backwardOnly);
-  if (!p->solveExec || p->sLU != LU || p->slda != lda || p->sb != b || p->sBackOnly != (int)backwardOnly) {
-    if (p->solveExec) {
-      cudaGraphExecDestroy(p->solveExec);
-      p->solveExec = nullptr;
+  // two cached graphs (least recently used is replaced): the solution vector and the refinement residual
+  // alternate as right-hand sides of the same factors
+  LuPlan::SolveGraph* g = nullptr;
+  for (auto& c : p->solveGraphs)
+    if (c.exec && c.LU == LU && c.lda == lda && c.b == b && c.backOnly == (int)backwardOnly && c.sA == p->bt.sA &&
+        c.sV == p->bt.sV)
+      g = &c;
+  if (!g) {
+    for (auto& c : p->solveGraphs)
+      if (!g && !c.exec) g = &c;
+    if (!g) g = p->solveGraphs[1].lastUse < p->solveGraphs[0].lastUse ? &p->solveGraphs[1] : &p->solveGraphs[0];
+    if (g->exec) {
+      cudaGraphExecDestroy(g->exec);
+      g->exec = nullptr;
     }
     cudaStream_t cs;
     WG_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
     WG_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
     const long long before = g_wg_launches;
     int rc = solve_enqueue(p, LU, lda, b, cs, backwardOnly);
-    p->solveLaunches = g_wg_launches - before;
+    g->launches = g_wg_launches - before;
     g_wg_launches = before;
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(cs, &graph);
@@ -1702,15 +1845,18 @@ int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t
       return rc;
     }
     WG_CUDA(e);
-    WG_CUDA(cudaGraphInstantiate(&p->solveExec, graph, 0));
+    WG_CUDA(cudaGraphInstantiate(&g->exec, graph, 0));
     cudaGraphDestroy(graph);
-    p->sLU = LU;
-    p->slda = lda;
-    p->sb = b;
-    p->sBackOnly = (int)backwardOnly;
+    g->LU = LU;
+    g->lda = lda;
+    g->b = b;
+    g->backOnly = (int)backwardOnly;
+    g->sA = p->bt.sA;
+    g->sV = p->bt.sV;
   }
-  WG_CUDA(cudaGraphLaunch(p->solveExec, st));
-  g_wg_launches += p->solveLaunches;
+  g->lastUse = ++p->solveUse;
+  WG_CUDA(cudaGraphLaunch(g->exec, st));
+  g_wg_launches += g->launches;
   return WG_OK;
 }
 
@@ -1725,6 +1871,18 @@ static int solve_enqueue(LuPlan* p, const double* LU, long long lda, double* b, 
     lu_rhs_perm_kernel<<<p->bt.count, 1024, 0, st>>>(b, p->permSrcTop, p->permBDst, p->permBSrc, p->permNBot, n, NB, p->bt.sV,
                                                      p->bt.sI, p->bt.sP);
     WG_LAUNCH_CHECK();
+  }
+  if (p->t.waveSolve) {
+    // two persistent launches: every CTA takes row blocks from a ticket counter and waits on the published count
+    WG_CUDA(cudaMemsetAsync(p->solveSync, 0, sizeof(int) * 4 * p->bt.count, st));
+    const dim3 grid(nblk < p->numSMs ? nblk : p->numSMs, p->bt.count);
+    if (!backwardOnly) {
+      lu_trisolve_wave_kernel<false><<<grid, 256, smem, st>>>(LU, lda, b, n, p->solveSync, p->bt.sA, p->bt.sV);
+      WG_LAUNCH_CHECK();
+    }
+    lu_trisolve_wave_kernel<true><<<grid, 256, smem, st>>>(LU, lda, b, n, p->solveSync, p->bt.sA, p->bt.sV);
+    WG_LAUNCH_CHECK();
+    return WG_OK;
   }
   for (int q = 0; q < nblk && !backwardOnly; ++q) {
     const int kb = q * TS_BS;

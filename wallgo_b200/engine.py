@@ -49,8 +49,9 @@ class BoltzmannEngine:
         self.nspec = self.M1 + 2 * self.N1
         self.spectra = torch.empty(self.nspec, dtype=f64, device=self.dev)
         self.spectra_host = torch.empty(self.nspec, dtype=f64).pin_memory()
-        # [ deltaF_out (n) | deltas (4 P M1) | err (4 P) ] contiguous so one D2H copy returns everything
-        self.nout = self.n + 4 * self.P * self.M1 + 4 * self.P
+        # [ deltaF_out (n) | deltas (4 P M1) | err (4 P) | refinement stats (2) ] contiguous so one D2H copy
+        # returns everything
+        self.nout = self.n + 4 * self.P * self.M1 + 4 * self.P + 2
         self.out = torch.empty(self.nout, dtype=f64, device=self.dev)
         self.out_host = torch.empty(self.nout, dtype=f64).pin_memory()
         self.dF_in = torch.empty(self.n, dtype=f64, device=self.dev)
@@ -216,6 +217,16 @@ class BoltzmannEngine:
         check(self.lib.wg_solve(self.h, A.data_ptr(), A.stride(0), b.data_ptr(), self._stream()), "wg_solve")
         return b
 
+    def refine(self, vw: float, collisionMultiplier: float = 1.0, x=None):
+        """One step of mixed-precision iterative refinement of x (default: the solution in self.S) with the
+        current factors (wg_refine); max|correction| and max|x| land in the last two entries of self.out."""
+        x = self.S if x is None else x
+        A = self._ensure_A()
+        check(self.lib.wg_refine(self.h, self.prof.data_ptr(), float(vw), float(collisionMultiplier), A.data_ptr(),
+                                 A.stride(0), x.data_ptr(), self.out[self.nout - 2:].data_ptr(), self._stream()),
+              "wg_refine")
+        return x
+
     def info(self) -> int:
         v = C.c_int(0)
         check(self.lib.wg_info(self.h, self._stream(), C.byref(v)), "wg_info")
@@ -246,7 +257,8 @@ class BoltzmannEngine:
         n, pm = self.n, 4 * self.P * self.M1
         dF = h[:n].reshape(self.P, self.M1, self.N1, self.N1).copy()
         deltas = h[n:n + pm].reshape(4, self.P, self.M1).copy()
-        err = h[n + pm:].reshape(self.P, 4).copy()
+        err = h[n + pm:n + pm + 4 * self.P].reshape(self.P, 4).copy()
+        self.last_refinement = (float(h[-2]), float(h[-1]))   # (max|correction|, max|x|) of the last refine()
         return dF, deltas, err
 
     def collision_apply(self, x, y):
@@ -279,10 +291,122 @@ class BoltzmannEngine:
               "wg_assemble_factor_solve_batched")
 
     # ------------------------------------------------------------------ fused device step (bench)
-    def step_device(self, vw: float, collisionMultiplier: float, keep, roundtrip: bool = True):
-        """assemble -> LU -> solve -> spectra -> truncate/moments, inputs already in HBM, no host sync."""
+    def step_device(self, vw: float, collisionMultiplier: float, keep, roundtrip: bool = True, refine: bool = True):
+        """assemble -> LU -> solve -> refinement step -> spectra -> truncate/moments, inputs already in HBM, no
+        host sync."""
         self.assemble(vw, collisionMultiplier)
         self.factor()
         self.solve()
+        if refine:
+            self.refine(vw, collisionMultiplier)
         self.spectra_async(self.S)
         self.moments_async(self.S, keep, roundtrip)
+
+
+class BatchEngine:
+    """`count` systems of one engine's shape advanced in LOCK STEP by every kernel launch (wg_batch_*): the
+    system index is a grid dimension, so one launch sequence / one CUDA graph serves the whole batch.  Shares
+    the parent's static tables and collision tensor; owns operators, vectors and pinned staging for `count`
+    systems and its own stream.  Per-system results are bit-identical to BoltzmannEngine's."""
+
+    def __init__(self, parent: BoltzmannEngine, count: int):
+        torch = parent.torch
+        self.torch, self.lib, self.parent, self.count = torch, parent.lib, parent, int(count)
+        self.dev = parent.dev
+        h = C.c_void_p()
+        check(self.lib.wg_batch_create(parent.h, self.count, C.byref(h)), "wg_batch_create")
+        self.h = h
+        B, n, f64 = self.count, parent.n, torch.float64
+        self.n, self.nprof, self.nspec, self.nout = n, parent.nprof, parent.nspec, parent.nout
+        self.strideA = n * n + (-(n * n)) % 4
+        self.A = torch.empty(B * self.strideA, dtype=f64, device=self.dev)
+        self.S = torch.empty((B, n), dtype=f64, device=self.dev)
+        # [ profiles | vw ] per system in one pinned block -> one H2D copy per batch
+        self.inp_host = torch.zeros((B, self.nprof + 1), dtype=f64).pin_memory()
+        self.inp = torch.empty((B, self.nprof + 1), dtype=f64, device=self.dev)
+        self.prof = torch.empty((B, self.nprof), dtype=f64, device=self.dev)
+        self.vw = torch.empty(B, dtype=f64, device=self.dev)
+        self.spectra = torch.empty((B, self.nspec), dtype=f64, device=self.dev)
+        self.spectra_host = torch.empty((B, self.nspec), dtype=f64).pin_memory()
+        self.keep_host = torch.zeros((B, 3), dtype=torch.int32).pin_memory()
+        self.keep = torch.zeros((B, 3), dtype=torch.int32, device=self.dev)
+        pm, pe = 4 * parent.P * parent.M1, 4 * parent.P
+        self.dF = torch.empty((B, n), dtype=f64, device=self.dev)
+        self.deltas = torch.empty((B, pm), dtype=f64, device=self.dev)
+        self.err = torch.empty((B, pe), dtype=f64, device=self.dev)
+        self.dF_host = torch.empty((B, n), dtype=f64).pin_memory()
+        self.deltas_host = torch.empty((B, pm), dtype=f64).pin_memory()
+        self.err_host = torch.empty((B, pe), dtype=f64).pin_memory()
+        self.refstats = torch.zeros((B, 2), dtype=f64, device=self.dev)
+        self.refstats_host = torch.zeros((B, 2), dtype=f64).pin_memory()
+        self.info_host = (C.c_int * B)()
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self._sp = C.c_void_p(self.stream.cuda_stream)
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.wg_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_system(self, i, T, v, msq, dxidchi, vw):
+        """Host staging of system i's background (pinned memory; nothing is enqueued)."""
+        L = self.parent.M + 1
+        P = self.parent.P
+        row = self.inp_host.numpy()[i]
+        row[0:L] = T
+        row[L:2 * L] = v
+        row[2 * L:(2 + P) * L] = np.asarray(msq, dtype=np.float64).reshape(-1)
+        row[(2 + P) * L:self.nprof] = dxidchi
+        row[self.nprof] = vw
+
+    def solve_async(self, collisionMultiplier: float, refine: bool = True):
+        """One H2D copy, then assemble + LU + triangular solves (+ one refinement step) + spectra of all systems,
+        spectra D2H; returns an event that fires when the spectra are on the host."""
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            self.inp.copy_(self.inp_host, non_blocking=True)
+            self.prof.copy_(self.inp[:, :self.nprof])
+            self.vw.copy_(self.inp[:, self.nprof])
+            n, sA = self.n, self.strideA
+            check(self.lib.wg_batch_assemble(self.h, self.prof.data_ptr(), self.vw.data_ptr(), float(collisionMultiplier),
+                                             3, self.A.data_ptr(), n, sA, self.S.data_ptr(), self._sp), "wg_batch_assemble")
+            check(self.lib.wg_batch_factor(self.h, self.A.data_ptr(), n, sA, self._sp), "wg_batch_factor")
+            check(self.lib.wg_batch_solve(self.h, self.A.data_ptr(), n, sA, self.S.data_ptr(), self._sp), "wg_batch_solve")
+            if refine:
+                check(self.lib.wg_batch_refine(self.h, self.prof.data_ptr(), self.vw.data_ptr(), float(collisionMultiplier),
+                                               self.A.data_ptr(), n, sA, self.S.data_ptr(), self.refstats.data_ptr(),
+                                               self._sp), "wg_batch_refine")
+            check(self.lib.wg_batch_spectra(self.h, self.S.data_ptr(), self.spectra.data_ptr(), self._sp), "wg_batch_spectra")
+            self.spectra_host.copy_(self.spectra, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return ev
+
+    def moments_async(self, keeps, roundtrip: bool):
+        """keeps: per system the three kept-coefficient counts; truncation + back-transform + moments of all
+        systems, results D2H; returns an event."""
+        torch = self.torch
+        kh = self.keep_host.numpy()
+        kh[:len(keeps)] = np.asarray(keeps, dtype=np.int32).reshape(-1, 3)
+        with torch.cuda.stream(self.stream):
+            self.keep.copy_(self.keep_host, non_blocking=True)
+            check(self.lib.wg_batch_moments(self.h, self.S.data_ptr(), self.prof.data_ptr(), self.keep.data_ptr(),
+                                            1 if roundtrip else 0, self.dF.data_ptr(), self.deltas.data_ptr(),
+                                            self.err.data_ptr(), self._sp), "wg_batch_moments")
+            self.dF_host.copy_(self.dF, non_blocking=True)
+            self.deltas_host.copy_(self.deltas, non_blocking=True)
+            self.err_host.copy_(self.err, non_blocking=True)
+            self.refstats_host.copy_(self.refstats, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        return ev
+
+    def infos(self):
+        check(self.lib.wg_batch_info(self.h, self._sp, self.info_host), "wg_batch_info")
+        return list(self.info_host)
