@@ -27,8 +27,11 @@ if ROOT not in sys.path:
 
 WORKLOADS = {  # BASELINE.json configs -> (P, M, N)
     "cfg1": (1, 20, 11), "cfg2a": (1, 40, 21), "cfg2b": (2, 40, 21), "cfg3": (3, 30, 11), "cfg4": (4, 30, 11),
-    # configs[4] (P=4, M=64, N=31) needs 411 GB; the largest member of that family that fits one B200:
-    "cfg5fit": (4, 64, 21),
+    # configs[4] (P=4, M=64, N=31) needs 411 GB.  The member of that family that keeps the N=31 momentum grid and
+    # fits one B200: M=32, n = 111600, operator 99.6 GB; and the M=64 member at N=21 (81 GB)
+    "cfg5fit": (4, 32, 31), "cfg5fit21": (4, 64, 21),
+    # the literal configs[4]: assembled in row panels that are never resident together (--workload cfg5stream)
+    "cfg5stream": (4, 64, 31),
 }
 METRIC = "Boltzmann solves/sec (assemble+LU+moments)"
 
@@ -424,6 +427,320 @@ def run_scan_boltzmann_only(a, world, rank, local):
     return out
 
 
+def run_stream(a, rank, world, local):
+    """BASELINE configs[4] as written (P=4, M=64, N=31: n = 226800, a 411 GB operator) cannot be resident on one
+    B200.  This mode generates it anyway, in row panels of `--panel-groups` (species, position) groups
+    (q = 900 rows x n columns each) written round-robin into two panel buffers -- the access pattern of an
+    out-of-core consumer -- and reports the assembly rate against the HBM write roofline.  One step = the whole
+    operator once.  Multi-GPU: every rank streams its own operator (weak scaling, no collective)."""
+    import torch
+    import torch.distributed as dist
+
+    import wallgo_b200 as wb
+    from wallgo_b200 import _lib, synthetic
+    from wallgo_b200._lib import check
+
+    lib = _lib.load()          # (device and process group were set up by run_b200)
+    P, M, N = WORKLOADS[a.workload]
+    K, W = a.steps, a.warmup
+    grid = synthetic.makeGrid(M, N)
+    particles = synthetic.makeParticles(P)
+    solver = wb.BoltzmannSolver(grid, device=local)
+    solver.updateParticleList(particles)
+    solver.setCollisionArray(synthetic.makeCollision(grid, particles))
+    solver.setBackground(synthetic.makeBackground(grid, velocityMid=-0.45))
+    eng = solver._getEngine()
+    solver._uploadBackground(eng)
+    n, q, dev = eng.n, eng.q, eng.dev
+    G = a.panel_groups
+    groups = P * (M - 1)
+    panels = [torch.empty((G * q, n), dtype=torch.float64, device=dev) for _ in range(2)]
+    sums = torch.zeros(1, dtype=torch.float64, device=dev)
+    vw, mult = float(solver.background.velocityWall), 1.0
+    st = eng._stream()
+
+    def one_pass(check_sum=False):
+        for i, g0 in enumerate(range(0, groups, G)):
+            ng = min(G, groups - g0)
+            pnl = panels[i % 2]
+            check(lib.wg_assemble_rows(eng.h, eng.prof.data_ptr(), vw, mult, 3, g0, ng, pnl.data_ptr(), n,
+                                       eng.S.data_ptr(), st), "wg_assemble_rows")
+            if check_sum:
+                sums.add_(pnl[:ng * q].sum())
+
+    for _ in range(W):
+        one_pass()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.wg_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        one_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    launches = lib.wg_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    # end to end: the same pass with every panel reduced to a checksum that is read back (a consumer touching
+    # every byte); host buffers in: the background profiles
+    t0 = time.perf_counter()
+    solver._uploadBackground(eng)
+    one_pass(check_sum=True)
+    total = float(sums.item())
+    e2e_s = time.perf_counter() - t0
+    if rank == 0:
+        hbm_peak, hbm_src = measured_peaks()
+        bytes_pass = 8.0 * n * n
+        gbs = K * bytes_pass / (ms * 1e-3) / 1e9
+        print(json.dumps({
+            "metric": "operator assembly GB/s (streamed row panels)", "value": world * gbs, "unit": "GB/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"cfg5stream: P={P} M={M} N={N} n={n}: the literal BASELINE configs[4] operator "
+                                   f"({bytes_pass / 1e9:.0f} GB) generated in {wg_cdiv(groups, G)} row panels of {G * q} rows "
+                                   f"({8.0 * G * q * n / 1e9:.1f} GB each, two buffers, never resident together)",
+                       "l2": "every panel is far larger than the 126 MB L2"},
+            "roofline": {"kernel": "wg_assemble_kernel (row-panel mode)", "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                         "algorithmic": "8 n^2 bytes written per pass / CUDA-event time of the pass"},
+            "e2e": {"value": bytes_pass / e2e_s / 1e9, "unit": "GB/s", "h2d_bytes_per_step": int(eng.nprof * 8),
+                    "d2h_bytes_per_step": 8, "note": "one pass with every panel summed on the device and the checksum "
+                                                     "read back", "checksum": total},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "cpu_baseline": {"value": None, "unit": "GB/s", "cores": os.cpu_count(), "kind": "reference",
+                             "sample": "skipped: buildLinearEquations materialises the 411 GB operator in host RAM"}}),
+            flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def wg_cdiv(a, b):
+    return (a + b - 1) // b
+
+
+def run_small(a, rank, world, local, lib, fp64_peak_fn):
+    """Small systems (n <= BoltzmannSolver.STRIDED_MAX_N; BASELINE configs[0], n = 1900): the strided-batch path.
+    One step = one lock-step batch of `--batch` independent systems (assemble + batched LU + solves + refinement
+    + truncation + moments, every kernel launched once for the whole batch), two batches in flight on two streams.
+    value = systems/s with all inputs resident in HBM; e2e = BoltzmannSolver.getDeltasBatch with host buffers."""
+    import torch
+    import torch.distributed as dist
+
+    import wallgo_b200 as wb
+    from wallgo_b200.engine import BatchEngine
+
+    P, M, N = WORKLOADS[a.workload]
+    K, W, B = a.steps, a.warmup, a.batch
+    nsys = B * (K + W)
+    grid, particles, coll, bgs = build_inputs(P, M, N, nsys, rank)
+    solver = wb.BoltzmannSolver(grid, device=local)
+    solver.updateParticleList(particles)
+    solver.setCollisionArray(coll)
+    solver.setBackground(bgs[0])
+    eng = solver._getEngine()
+    n, nprof, dev = eng.n, eng.nprof, eng.dev
+    fp64_peak = fp64_peak_fn(dev)
+    bes = [BatchEngine(eng, B), BatchEngine(eng, B)]
+    inp = np.empty((K + W, B, nprof + 1))
+    L = M + 1
+    for i, bg in enumerate(bgs):
+        solver.setBackground(bg)
+        b = solver.background
+        row = inp[i // B, i % B]
+        row[:L] = b.temperatureProfile
+        row[L:2 * L] = b.velocityProfile
+        row[2 * L:(2 + P) * L] = solver._msq(b.fieldProfiles).reshape(-1)
+        row[(2 + P) * L:nprof] = grid.dxidchi
+        row[nprof] = float(b.velocityWall)
+    inp_d = torch.from_numpy(inp).to(dev)
+    keep = torch.tensor([[M - 1, N - 1, N - 1]] * B, dtype=torch.int32, device=dev)
+    from wallgo_b200._lib import check
+
+    def step(be, i, rec=None):
+        with torch.cuda.stream(be.stream):
+            be.prof.copy_(inp_d[i, :, :nprof])
+            be.vw.copy_(inp_d[i, :, nprof])
+            sp, sA = be._sp, be.strideA
+            if rec:
+                rec[0].record(be.stream)
+            check(lib.wg_batch_assemble(be.h, be.prof.data_ptr(), be.vw.data_ptr(), 1.0, 3, be.A.data_ptr(), n, sA,
+                                        be.S.data_ptr(), sp), "wg_batch_assemble")
+            if rec:
+                rec[1].record(be.stream)
+            check(lib.wg_batch_factor(be.h, be.A.data_ptr(), n, sA, sp), "wg_batch_factor")
+            if rec:
+                rec[2].record(be.stream)
+            check(lib.wg_batch_solve(be.h, be.A.data_ptr(), n, sA, be.S.data_ptr(), sp), "wg_batch_solve")
+            if rec:
+                rec[3].record(be.stream)
+            if solver.refinementSteps:
+                check(lib.wg_batch_refine(be.h, be.prof.data_ptr(), be.vw.data_ptr(), 1.0, be.A.data_ptr(), n, sA,
+                                          be.S.data_ptr(), be.refstats.data_ptr(), sp), "wg_batch_refine")
+            if rec:
+                rec[4].record(be.stream)
+            check(lib.wg_batch_spectra(be.h, be.S.data_ptr(), be.spectra.data_ptr(), sp), "wg_batch_spectra")
+            check(lib.wg_batch_moments(be.h, be.S.data_ptr(), be.prof.data_ptr(), keep.data_ptr(), 1, be.dF.data_ptr(),
+                                       be.deltas.data_ptr(), be.err.data_ptr(), sp), "wg_batch_moments")
+            if rec:
+                rec[5].record(be.stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for i in range(W):
+        step(bes[i % 2], i)
+    torch.cuda.synchronize()
+    rec = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+    step(bes[0], 0, rec)
+    torch.cuda.synchronize()
+    stage = [rec[j].elapsed_time(rec[j + 1]) for j in range(5)]
+    sampler = ClockSampler(local)
+    barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    l0 = lib.wg_launch_count()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cur = torch.cuda.current_stream(dev)
+    start.record(cur)
+    for be in bes:
+        be.stream.wait_event(start)
+    for i in range(K):
+        step(bes[i % 2], W + i)
+    for be in bes:
+        done = torch.cuda.Event()
+        done.record(be.stream)
+        cur.wait_event(done)
+    end.record(cur)
+    torch.cuda.synchronize()
+    launches = lib.wg_launch_count() - l0
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = start.elapsed_time(end)
+    for be in bes:
+        assert not any(be.infos()), "singular operator in the benchmark"
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * K * B / (ms / 1e3)
+    for be in bes:
+        be.close()
+    # ---- end to end through the public class, host buffers
+    solver.getDeltasBatch(bgs[:2 * B])
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    allres = solver.getDeltasBatch(bgs[W * B:])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = world * K * B / e2e_s
+    t0 = time.perf_counter()
+    for i in range(5):
+        solver.setBackground(bgs[i])
+        solver.getDeltas()
+    seq_ms = (time.perf_counter() - t0) / 5 * 1e3
+    if rank != 0:
+        return
+    lu_flops = 2.0 / 3.0 * float(n) ** 3
+    lu_tf = K * B * lu_flops / (ms * 1e-3) / 1e12
+    hbm_peak, hbm_src = measured_peaks()
+    line = {
+        "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{a.workload}: P={P} M={M} N={N} n={n}; one step = one lock-step strided batch of {B} "
+                               "independent systems (wg_batch_*: every kernel launched once per batch), two batches in flight",
+                   "l2": f"batch operators {8.0 * n * n * B / 1e9:.2f} GB per batch >> 126 MB L2",
+                   "batch": B, "refinement_steps": int(solver.refinementSteps),
+                   "parallelism": f"{world} x independent batches, no collective inside a solve"},
+        "stages_ms_one_batch": {"assemble": stage[0], "lu_factor": stage[1], "tri_solves": stage[2], "refinement_step": stage[3],
+                                "spectra_moments": stage[4], "note": f"one batch of {B} systems alone on the GPU"},
+        "latency_ms_sequential_getDeltas": seq_ms,
+        "roofline": {"kernel": "whole batched LU (lock-step: leaf panels, TRSM, DMMA trailing updates of all systems)",
+                     "bound": "tensor", "achieved": lu_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": lu_tf / fp64_peak,
+                     "traffic": None,
+                     "algorithmic": "steps * batch * 2/3 n^3 LU flops / CUDA-event duration of the whole timed region "
+                                    "(assembly, solves, refinement and moments count as overhead)",
+                     "lu_alone": {"achieved": B * lu_flops / (stage[1] * 1e-3) / 1e12, "unit": "TFLOP/s",
+                                  "note": "wg_batch_factor of one batch alone"},
+                     "peak_source": "measured in this run: torch.matmul (cuBLAS DGEMM) fp64 8192^3 best of 5; "
+                                    "MEASURED_PEAKS.json has no FP64 entry"},
+        "roofline_assembly": {"kernel": "wg_assemble_kernel (batched)", "bound": "hbm",
+                              "achieved": B * (8.0 * n * n + 8.0 * n) / (stage[0] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                              "frac": B * (8.0 * n * n + 8.0 * n) / (stage[0] * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                              "peak_source": hbm_src},
+        "e2e": {"value": e2e, "unit": "solves/s", "h2d_bytes_per_step": int(B * (nprof + 1) * 8 + B * 12),
+                "d2h_bytes_per_step": int(B * (eng.nspec + eng.nout) * 8 + B * 4)},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    res = allres[-1]
+    assert np.all(np.isfinite(res.Deltas.Delta00.coefficients))
+    if world == 1 and not a.no_cpu_baseline and reference_available():
+        import contextlib
+        from oracle import ref_drivers as rd
+        from wallgo_b200 import dropin
+        ts = []
+        with contextlib.redirect_stdout(sys.stderr):
+            for i in range(12):
+                vmid = -0.3 - 0.4 * (i % 97) / 97.0
+                t, rres, (rsolver, rgrid, rbg, rparts) = reference_one_solve(P, M, N, vmid, want_solver=True)
+                ts.append(t["total_s"])
+            new = dropin.makeDropInClass()(rgrid, rsolver.basisM, rsolver.basisN, rsolver.derivatives,
+                                           rsolver.collisionMultiplier, rsolver.truncationOption, device=local)
+            new.updateParticleList(rparts)
+            new.setBackground(rbg)
+            new.setCollisionArray(rsolver.collisionArray)
+            gres = new.getDeltas()
+            Dr, Dg = rd.deltas_table(rres), rd.deltas_table(gres)
+        line["cpu_baseline"] = {"value": 1.0 / float(np.mean(ts[2:])), "unit": "solves/s", "cores": os.cpu_count(),
+                                "kind": "reference",
+                                "sample": f"10 full solves of the same workload by the unmodified reference class "
+                                          f"(oracle/_ref), mean {np.mean(ts[2:]):.3f}s each, NumPy {np.__version__}, "
+                                          f"BLAS {blas_info()}"}
+        line["parity"] = {
+            "against": "the same system solved by the reference class on the host and by the CUDA path",
+            "max_rel_deltaF": float(np.max(np.abs(gres.deltaF - rres.deltaF)) / np.max(np.abs(rres.deltaF))),
+            "max_rel_Deltas": float(max(np.max(np.abs(Dg[i] - Dr[i])) / np.max(np.abs(Dr[i])) for i in range(4))),
+            "flags_equal": bool(tuple(gres.truncatedTail) == tuple(rres.truncatedTail)
+                                and tuple(gres.spectralPeaks) == tuple(rres.spectralPeaks)), "tolerance": 1e-10}
+    print(json.dumps(line), flush=True)
+
+
+def measure_fp64_peak(dev):
+    """cuBLAS DGEMM through torch.matmul, 8192^3, best of 5: the denominator of the LU rooflines."""
+    import torch
+
+    x = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    y = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    torch.matmul(x, y)
+    best = 1e9
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(x, y)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    del x, y
+    torch.cuda.empty_cache()
+    return 2.0 * 8192.0 ** 3 / (best * 1e-3) / 1e12
+
+
 def run_b200(a):
     import torch
     import torch.distributed as dist
@@ -449,6 +766,13 @@ def run_b200(a):
     if a.bulk_hi >= 0:
         lib.wg_set_bulk_priority_rest(a.bulk_hi)
     P, M, N = WORKLOADS[a.workload]
+    if a.workload == "cfg5stream":
+        return run_stream(a, rank, world, local)
+    if P * (M - 1) * (N - 1) ** 2 <= wb.BoltzmannSolver.STRIDED_MAX_N and a.batch > 0:
+        run_small(a, rank, world, local, lib, measure_fp64_peak)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     K, W = a.steps, a.warmup
     nsys = K + W
     grid, particles, coll, bgs = build_inputs(P, M, N, nsys, rank)
@@ -543,7 +867,8 @@ def run_b200(a):
         for i in range(W):
             step(e, i)
     torch.cuda.synchronize()
-    nsolo = min(3, K)
+    big = 8.0 * n * n > 40e9          # tens of seconds per step: one sample of each diagnostic pass is enough
+    nsolo = 1 if big else min(3, K)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(nsolo)]
     import ctypes as C
     gms, gfl, gcnt = C.c_double(0), C.c_double(0), C.c_int(0)
@@ -564,7 +889,8 @@ def run_b200(a):
     stage = np.array([[e[j].elapsed_time(e[j + 1]) for j in range(4)] for e in evs]).mean(axis=0)
     # the same with factorisation and triangular solves as separate calls (comparable with LAPACK getrf / getrs)
     evu = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
-    step(engines[0], W, evu)
+    if not big:
+        step(engines[0], W, evu)
     step(engines[0], W, evu)
     torch.cuda.synchronize()
     unfused = [evu[j].elapsed_time(evu[j + 1]) for j in range(4)]
@@ -616,7 +942,7 @@ def run_b200(a):
     # ---- end to end through the public class, host buffers in and out
     for e, pr in zip(engines, own_prof):
         e.prof = pr
-    solver.getDeltasBatch(bgs[:min(W, 2 * C_)], concurrency=C_)
+    solver.getDeltasBatch(bgs[:(1 if big else min(W, 2 * C_))], concurrency=C_)
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -626,11 +952,12 @@ def run_b200(a):
     res = allres[-1]
     # sequential getDeltas() latency (one system at a time), for reference
     t0 = time.perf_counter()
-    for i in range(min(3, K)):
+    nseq = 1 if big else min(3, K)
+    for i in range(nseq):
         solver.setBackground(bgs[W + i])
         solver.getDeltas()
     torch.cuda.synchronize()
-    seq_ms = (time.perf_counter() - t0) / min(3, K) * 1e3
+    seq_ms = (time.perf_counter() - t0) / nseq * 1e3
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -777,7 +1104,12 @@ def main():
     ap.add_argument("--stagger", type=float, default=-1.0, help="developer knob: seconds between slot starts")
     ap.add_argument("--fused", type=int, default=0, help="developer knob: 1 = wg_factor_solve, 0 = wg_factor + wg_solve (shipped path)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--scan-points", type=int, default=256, help="vw-scan points of the secondary metric (0: skip)")
+    ap.add_argument("--batch", type=int, default=64,
+                    help="small systems (cfg1): systems per lock-step strided batch (0: the slot-pool path instead)")
+    ap.add_argument("--panel-groups", type=int, default=6,
+                    help="cfg5stream: (species, position) row groups per panel (6 x 900 rows x 226800 columns = 9.8 GB)")
+    ap.add_argument("--scan-points", type=int, default=None,
+                    help="vw-scan points of the secondary metric (default: 256 with the headline workload, 0 = skip otherwise)")
     ap.add_argument("--scan-workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--scan-model", default="idm", choices=sorted(SCAN_MODELS))
     ap.add_argument("--scan-workers", type=int, default=-1, help="host processes per rank for the scan (-1: auto, 0: in-process)")
@@ -786,6 +1118,8 @@ def main():
     ap.add_argument("--ref-scan-points", type=int, default=2, help="scan points the reference arm times (0: skip)")
     ap.add_argument("--ref-budget-s", type=float, default=150.0)
     a = ap.parse_args()
+    if a.scan_points is None:
+        a.scan_points = 256 if a.workload == "cfg2a" else 0
     a.warmup = max(a.warmup, 3) if a.impl == "b200" else a.warmup
     if a.impl == "reference":
         # torchrun exports OMP_NUM_THREADS=1; the CPU arm must use every host core, and BLAS reads the

@@ -110,6 +110,12 @@ int wg_interpolate_collision(int device, int P, int NF, int NT, const double* Lz
  * `liouville` and `collision` arrays that buildLinearEquations also returns, boltzmann.py:820). */
 int wg_assemble(wg_solver* s, const double* profiles_dev, double vw, double collisionMultiplier, int parts,
                 double* A_dev, long long lda, double* S_dev, void* stream);
+/* Row-panel form of wg_assemble for operators that do not fit in memory (BASELINE configs[4]: P=4, M=64, N=31 is
+ * 411 GB): writes the rows of the (species, position) groups [group0, group0+ngroups) -- q = (N-1)^2 rows each,
+ * group g = a*(M-1)+alpha -- into panel_dev (ngroups*q x lda), exactly the bytes wg_assemble writes there; the
+ * source S_dev (n) is written in full by every call.  A consumer streams the operator panel by panel. */
+int wg_assemble_rows(wg_solver* s, const double* profiles_dev, double vw, double collisionMultiplier, int parts,
+                     int group0, int ngroups, double* panel_dev, long long lda, double* S_dev, void* stream);
 /* np.linalg.solve(operator, source) (boltzmann.py:283): LU in place with row partial pivoting ... */
 int wg_factor(wg_solver* s, double* A_dev, long long lda, void* stream);
 /* Both in one call, the way np.linalg.solve is used: the forward solve L y = P b rides along inside the

@@ -594,7 +594,7 @@ def _lu_batched(env, As, bs, pad=0, graph=None):
     return LUs, ipiv.cpu().numpy().reshape(B, n), info.cpu().numpy(), bd.cpu().numpy()
 
 
-@pytest.mark.parametrize("n,B,pad", [(37, 5, 0), (300, 7, 0), (513, 3, 2), (1900, 6, 0), (700, 40, 0)])
+@pytest.mark.parametrize("n,B,pad", [(37, 5, 0), (300, 7, 0), (513, 3, 2), (1900, 6, 0), (700, 40, 0), (1100, 60, 0)])
 def test_lu_batched_is_bit_identical_to_single(env, n, B, pad):
     """Every system of a lock-step batch gets exactly the factors, pivots and solution of the single-system
     path (same kernels, the batch is only a grid dimension) and agrees with LAPACK."""

@@ -21,7 +21,7 @@ for B in Bs:
         _lib.check(lib.wg_lu_factor_batched(plan, A.data_ptr(), n, n * n, ipiv.data_ptr(), info.data_ptr(), st))
     A.copy_(A0); run(); torch.cuda.synchronize()
     ts = []
-    for it in range(4):
+    for it in range(int(os.environ.get('BATCH_PROBE_ITERS', '4'))):
         A.copy_(A0); torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); run(); e1.record(); torch.cuda.synchronize()
@@ -33,7 +33,7 @@ for B in Bs:
     _lib.check(lib.wg_lu_solve_batched(plan, A.data_ptr(), n, n * n, x.data_ptr(), n, st)); e1.record(); torch.cuda.synchronize()
     tsolve = e0.elapsed_time(e1)
     res = (torch.bmm(A0, x.unsqueeze(2)).squeeze(2) - b).abs().max().item()
-    t = min(ts)
+    t = min(ts) if ts else float('nan')
     print(f"n={n} B={B} factor {t:.3f} ms  -> {B / t * 1e3:.0f} systems/s, {B * 2 / 3 * n ** 3 / t / 1e9:.2f} TFLOP/s; solve {tsolve:.3f} ms; "
           f"residual {res:.2e} info {int(info.abs().max())}", flush=True)
     lib.wg_lu_destroy(plan)

@@ -32,7 +32,12 @@ for case in range(ncases):
     solver.updateParticleList(parts)
     solver.setBackground(FixtureBackground(g))
     solver.setCollisionArray(wb.CollisionArray(grid, basisN, parts, pb.collision))
-    ref = bo.get_deltas(pb, None, option)
+    # reference answer: the EXTENDED-PRECISION solution of the assembled system pushed through the oracle's
+    # truncation + moments (LAPACK's own FP64 solve is off by cond * eps, up to 4e-11 in this fuzz: a yardstick
+    # no more accurate than the thing measured).  The device applies one mixed-precision refinement step (wg_refine).
+    A_ref, b_ref = bo.assemble(pb)
+    xExt, xLap = bo.solve_extended(A_ref, b_ref)
+    ref = bo.get_deltas(pb, xExt.reshape(P, M - 1, N - 1, N - 1), option)
     res = solver.getDeltas()
     e = relmax(res.deltaF, ref["deltaF"])
     D = np.stack([res.Deltas.Delta00.coefficients, res.Deltas.Delta02.coefficients, res.Deltas.Delta20.coefficients,
@@ -65,15 +70,6 @@ for case in range(ncases):
     for msg in extra:
         bad += 1
         print("  MISMATCH", msg)
-    if same and (e > 1e-10 or ed > 1e-10) and e < 1e-7:
-        # an ill-conditioned operator (tiny collision multiplier): two backward-stable solvers legitimately differ by
-        # cond * eps.  Accept when the solution BEFORE truncation satisfies the assembled system to working precision.
-        A_ref, b_ref = bo.assemble(pb)
-        x = solver.solveBoltzmannEquations().reshape(-1)
-        berr = np.max(np.abs(A_ref @ x - b_ref)) / (np.max(np.sum(np.abs(A_ref), axis=1)) * np.max(np.abs(x)) + np.max(np.abs(b_ref)))
-        print(f"  note: deviation deltaF {e:.2e} Deltas {ed:.2e} with backward error {berr:.1e} (ill-conditioned operator)")
-        if berr < 1e-14:
-            continue
     if not same or e > 1e-10 or ed > 1e-10:
         bad += 1
         print(f"  MISMATCH deltaF {e:.2e} Deltas {ed:.2e} flags {res.truncatedTail} vs {ref['truncatedTail']} peaks {res.spectralPeaks} vs {ref['spectralPeaks']}")

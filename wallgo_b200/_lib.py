@@ -35,6 +35,7 @@ SYMBOLS = {
     "wg_set_collision": (C.c_int, [_vp, _vp, C.c_int]),
     "wg_interpolate_collision": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _hd, _hd, _hd, _hd]),
     "wg_assemble": (C.c_int, [_vp, _dp, C.c_double, C.c_double, C.c_int, _dp, C.c_longlong, _dp, _vp]),
+    "wg_assemble_rows": (C.c_int, [_vp, _dp, C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, _dp, C.c_longlong, _dp, _vp]),
     "wg_factor": (C.c_int, [_vp, _dp, C.c_longlong, _vp]),
     "wg_factor_solve": (C.c_int, [_vp, _dp, C.c_longlong, _dp, _vp]),
     "wg_solve": (C.c_int, [_vp, _dp, C.c_longlong, _dp, _vp]),

@@ -169,13 +169,17 @@ __global__ void __launch_bounds__(512, WG_ASM_MINB) wg_assemble_kernel(BzDims d,
                                                           const double* __restrict__ w1,
                                                           const double* __restrict__ w2,
                                                           const double* __restrict__ cT2,
-                                                          double* __restrict__ A, long long lda, long long sA) {
+                                                          double* __restrict__ A, long long lda, long long sA,
+                                                          int y0) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int q = d.q, M1 = d.M1, P = d.P;
   w1 += (long long)blockIdx.z * d.n;
   w2 += (long long)blockIdx.z * d.n;
   cT2 += (long long)blockIdx.z * M1;
   A += (long long)blockIdx.z * sA;
+  // row-panel mode: the grid covers the (species, position) row groups [y0, y0 + gridDim.y) and A points at
+  // the first row of the panel (the whole operator: y0 = 0)
+  A -= (long long)y0 * q * lda;
   double* K1s = reinterpret_cast<double*>(smraw);  // [R][q]
   double* K2s = K1s + R * q;                       // [R][q]
   double* Cs = K2s + R * q;                        // [R][P*q]
@@ -183,7 +187,8 @@ __global__ void __launch_bounds__(512, WG_ASM_MINB) wg_assemble_kernel(BzDims d,
   double* tch = dch + M1;                          // [M1]
   __shared__ __align__(8) uint64_t bar;
 
-  const int a = blockIdx.y / M1, al = blockIdx.y % M1;
+  const int by = blockIdx.y + y0;
+  const int a = by / M1, al = by % M1;
   const int bg0 = blockIdx.x * R;
   const long long r0 = ((long long)a * M1 + al) * q + bg0;
   const int tid = threadIdx.x;
@@ -711,8 +716,10 @@ void bz_set_asm_wide(int on) { g_asm_wide = on; }
 
 int bz_assemble(const BzDims& d, const BzStatic& s, const double* prof, double vw, double collMult, int parts,
                 double* derivs, double* w1, double* w2, double* cT2, double* A, long long lda, double* S,
-                cudaStream_t st, const BzBatch& bb) {
+                cudaStream_t st, const BzBatch& bb, int y0, int ny) {
   WG_REQUIRE(d.q % 4 == 0, "assemble: (N-1)^2 must be a multiple of 4 (N odd)");
+  if (ny < 0) ny = d.P * d.M1 - y0;
+  WG_REQUIRE(y0 >= 0 && ny >= 1 && y0 + ny <= d.P * d.M1, "assemble: row-group range out of bounds");
   WG_REQUIRE(lda % 2 == 0 && bb.sA % 2 == 0 && reinterpret_cast<uintptr_t>(A) % 16 == 0,
              "assemble: A must be 16B aligned, lda and the batch stride even");
   const int nprof = (2 + d.P) * (d.M + 1) + d.M1;
@@ -733,16 +740,16 @@ int bz_assemble(const BzDims& d, const BzStatic& s, const double* prof, double v
     WG_CUDA(cudaFuncSetAttribute(wg_assemble_kernel<R, 4>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared));
   }
-  dim3 grid(d.q / R, d.P * d.M1, bb.count);
+  dim3 grid(d.q / R, ny, bb.count);
   const bool wide = g_asm_wide && d.q % 4 == 0 && lda % 4 == 0 && bb.sA % 4 == 0 && reinterpret_cast<uintptr_t>(A) % 32 == 0;
   const int per = wide ? 4 : 2;
   int threads = ((d.q / per + 31) / 32) * 32;
   if (threads > 512) threads = 512;
   if (threads < 64) threads = 64;
   if (wide)
-    wg_assemble_kernel<R, 4><<<grid, threads, smem, st>>>(d, s.K1, s.K2, s.Coll, s.Tchi, s.Dchi, w1, w2, cT2, A, lda, bb.sA);
+    wg_assemble_kernel<R, 4><<<grid, threads, smem, st>>>(d, s.K1, s.K2, s.Coll, s.Tchi, s.Dchi, w1, w2, cT2, A, lda, bb.sA, y0);
   else
-    wg_assemble_kernel<R, 2><<<grid, threads, smem, st>>>(d, s.K1, s.K2, s.Coll, s.Tchi, s.Dchi, w1, w2, cT2, A, lda, bb.sA);
+    wg_assemble_kernel<R, 2><<<grid, threads, smem, st>>>(d, s.K1, s.K2, s.Coll, s.Tchi, s.Dchi, w1, w2, cT2, A, lda, bb.sA, y0);
   WG_LAUNCH_CHECK();
   return WG_OK;
 }

@@ -37,7 +37,7 @@ int bz_build_kron(const BzDims& d, const double* Trz, const double* Drz, const d
 void bz_set_asm_wide(int on);
 int bz_assemble(const BzDims& d, const BzStatic& s, const double* prof, double vw, double collMult, int parts,
                 double* derivs, double* w1, double* w2, double* cT2, double* A, long long lda, double* S,
-                cudaStream_t st, const BzBatch& bb = BzBatch());
+                cudaStream_t st, const BzBatch& bb = BzBatch(), int y0 = 0, int ny = -1);
 int bz_residual(const BzDims& d, const BzStatic& s, const double* prof, double vw, double collMult, double* derivs,
                 double* w1, double* w2, double* cT2, const double* x, double* Ssrc, double* r, cudaStream_t st,
                 const BzBatch& bb = BzBatch());

@@ -394,6 +394,20 @@ int wg_assemble(wg_solver* s, const double* profiles_dev, double vw, double coll
   return rc;
 }
 
+int wg_assemble_rows(wg_solver* s, const double* profiles_dev, double vw, double collisionMultiplier, int parts,
+                     int group0, int ngroups, double* panel_dev, long long lda, double* S_dev, void* stream) {
+  WG_REQUIRE(s && profiles_dev && panel_dev && S_dev, "wg_assemble_rows: NULL argument");
+  WG_ON_DEVICE(s->device);
+  if (!(s->haveGrid && s->haveTables && s->haveColl && s->haveStat)) {
+    wg_set_error("wg_assemble_rows: grid, statistics, tables and collision tensor must be set first");
+    return WG_ERR_STATE;
+  }
+  WG_REQUIRE(lda >= s->d.n, "wg_assemble_rows: lda < n");
+  WG_REQUIRE(group0 >= 0 && ngroups >= 1 && group0 + ngroups <= s->d.P * s->d.M1, "wg_assemble_rows: group range out of bounds");
+  return wg::bz_assemble(s->d, s->st, profiles_dev, vw, collisionMultiplier, parts, s->derivs, s->w1, s->w2, s->cT2,
+                         panel_dev, lda, S_dev, (cudaStream_t)stream, wg::BzBatch(), group0, ngroups);
+}
+
 int wg_factor(wg_solver* s, double* A_dev, long long lda, void* stream) {
   WG_REQUIRE(s && A_dev, "wg_factor: NULL argument");
   WG_ON_DEVICE(s->device);

@@ -1384,7 +1384,10 @@ static int leaf(FactorCtx& c, int c0, int w, int pc0, int pc1) {
   const int nb_ = c.p->bt.count;
   if (c.wb == 32) return launch_leaf<32, 1>(pa, pick_cl(PT), nb_, c.st);
   if (c.wb == 16) {
-    if (m <= c.p->maxCL * PT) return launch_leaf<16, 1>(pa, pick_cl(PT), nb_, c.st);
+    // a lock-step batch whose one-row-per-thread clusters would not be co-resident (one leaf CTA per SM) takes
+    // two rows per thread: half the CTAs per system, one wave instead of two
+    const bool oneWave = nb_ == 1 || nb_ * pick_cl(PT) <= c.p->numSMs || m <= PT;
+    if (m <= c.p->maxCL * PT && oneWave) return launch_leaf<16, 1>(pa, pick_cl(PT), nb_, c.st);
     return launch_leaf<16, 2>(pa, pick_cl(PT * 2), nb_, c.st);
   }
   if (c.wb == 2) return launch_leaf<2, 16>(pa, pick_cl(PT * 16), nb_, c.st);  // up to 131072 rows: 16 rows x 2 columns per thread
