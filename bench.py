@@ -47,6 +47,30 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def profile_traffic(stem):
+    """DRAM read+write bytes of one launch of a kernel, parsed from the committed `ncu --set full` summary
+    profiles/rNN_ncu_full_<stem>.csv of the newest round that has one (first launch column).  Returns
+    (bytes, file name) or (None, None): the number is never a literal in this file."""
+    import glob
+    import re
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"r[0-9][0-9]_ncu_full_{stem}.csv")))
+    if not files:
+        return None, None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    total = 0.0
+    found = 0
+    try:
+        for ln in open(files[-1]):
+            m = re.match(r"dram__bytes_(read|write)\.sum,([A-Za-z]+),([0-9.eE+-]+)", ln)
+            if m:
+                total += float(m.group(3)) * unit[m.group(2)]
+                found += 1
+    except (OSError, KeyError, ValueError):
+        return None, None
+    return (total, os.path.basename(files[-1])) if found == 2 else (None, None)
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -1000,13 +1024,14 @@ def run_b200(a):
             "roofline": {"kernel": "dgemm_sub_kernel<128,64,16,2,2,3> (trailing update of the LU, DMMA.8x8x4)",
                          "bound": "tensor", "achieved": gemm_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": gemm_tf / fp64_peak,
-                         "traffic": 4.24e9 if (P, M, N) == (1, 40, 21) else None,
+                         "traffic": profile_traffic("dgemm_128x64_2cta")[0] if (P, M, N) == (1, 40, 21) else None,
+                         "traffic_source": profile_traffic("dgemm_128x64_2cta")[1],
                          "launches_timed": gcnt.value, "ms_timed": gms.value,
                          "algorithmic": "2*M*N*K flops of every trailing-update launch / its CUDA-event duration on the "
                                         "launching stream, summed over one solo factorisation on plain streams with the "
                                         "bulk columns unsplit (the look-ahead chain runs beside it); "
-                                        "traffic = dram read+write of the first-step launch (15344^2 x 256) from "
-                                        "profiles/r01_ncu_full_dgemm_128x64_2cta.csv vs 3.83e9 algorithmic",
+                                        "traffic = dram read+write of the first-step launch (15344^2 x 256) parsed from "
+                                        "the ncu --set full summary under profiles/ (traffic_source) vs 3.83e9 algorithmic",
                          "peak_source": "measured in this run: torch.matmul (cuBLAS DGEMM) fp64 8192^3 best of 5; "
                                         "MEASURED_PEAKS.json has no FP64 entry"},
             "roofline_lu": {"kernel": "whole blocked LU (all kernels)", "bound": "tensor",
@@ -1018,7 +1043,8 @@ def run_b200(a):
                                         "(assembly, solves and moments count as overhead)"},
             "roofline_assembly": {"kernel": "wg_assemble_kernel", "bound": "hbm", "achieved": asm_gbs, "peak": hbm_peak,
                                   "unit": "GB/s", "frac": asm_gbs / hbm_peak,
-                                  "traffic": 1.935e9 if (P, M, N) == (1, 40, 21) else None, "peak_source": hbm_src,
+                                  "traffic": profile_traffic("assemble")[0] if (P, M, N) == (1, 40, 21) else None,
+                                  "traffic_source": profile_traffic("assemble")[1], "peak_source": hbm_src,
                                   "algorithmic": "8n^2+8n bytes written per solve / mean CUDA-event time of wg_assemble"},
             "e2e": {"value": e2e, "unit": "solves/s", "h2d_bytes_per_step": int(nprof * 8),
                     "d2h_bytes_per_step": int((eng.nspec + eng.nout) * 8 + 4)},

@@ -927,50 +927,105 @@ __global__ void lu_rhs_perm_panel_kernel(double* __restrict__ b, const int* __re
 constexpr int TS_BS = 128;
 constexpr int TS_LD = TS_BS + 1;
 
-// Solve of one diagonal block held in shared memory (T: [bs][TS_LD], ys: right-hand side -> solution): 32-wide
-// sub-blocks, warp-shuffle substitution by warp 0, the block's other rows updated by all threads.  Shared by the
-// per-block step kernel and the wavefront kernel, so both produce the same bits.
+// Solve of one 128-row diagonal block held in shared memory (T: [bs][TS_LD], ys: right-hand side -> solution),
+// organised for LATENCY: the solve sits on the critical path of the whole triangular solve.
+//  * Lower (unit) triangle: the four 32x32 diagonal sub-blocks are inverted beforehand (trisolve_prepare, off the
+//    critical path: the factors are static) so each sub-block costs one 32x32 matrix-vector product instead of a
+//    32-step dependent substitution.  L's sub-blocks are unit triangular with multipliers bounded by 1 (partial
+//    pivoting), so their inverses are benign; the solution is refined afterwards anyway (wg_refine).
+//  * Upper triangle: the diagonal sub-blocks carry the conditioning of the matrix, so they are solved by
+//    substitution (warp shuffle), with every row pre-scaled by the reciprocal of its diagonal entry so that the
+//    dependent chain per unknown is one shuffle + one FMA.
+//  * Between sub-blocks the remaining rows are updated by pairs of threads (16 columns each, two FMA chains).
+// Shared by the per-block step kernel and the wavefront kernel, so both produce the same bits.
+constexpr int TS_LI = 33;   // leading dimension of an inverted 32x32 sub-block
+constexpr size_t TS_SMEM = (size_t)(TS_BS * TS_LD + 2 * TS_BS + 4 * 32 * TS_LI) * sizeof(double);
+
+// Linv[w] = inverse of the w-th diagonal 32x32 sub-block of the unit lower triangle of T (warps 0..3)
+__device__ __forceinline__ void trisolve_prepare_lower(const double* __restrict__ T, double* __restrict__ Linv, int bs,
+                                                       int lane, int warp) {
+  if (warp >= 4) return;
+  const int sb = warp * 32;
+  if (sb >= bs) return;
+  // lane j builds column j of X = L^-1:  x[r] = delta_rj - sum_{c<r} L[r][c] x[c]
+  double x[32];
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    double acc = (r == lane) ? 1.0 : 0.0;
+    if (sb + r < bs) {
+#pragma unroll
+      for (int c = 0; c < r; ++c) acc = fma(-T[(sb + r) * TS_LD + sb + c], x[c], acc);
+    }
+    x[r] = acc;
+    Linv[(warp * 32 + r) * TS_LI + lane] = acc;
+  }
+}
+
 template <bool UPPER>
-__device__ __forceinline__ void trisolve_diag_block(const double* __restrict__ T, double* __restrict__ ys, int bs, int tid,
-                                                    int lane, int warp) {
+__device__ __forceinline__ void trisolve_diag_block(const double* __restrict__ T, const double* __restrict__ Linv,
+                                                    double* __restrict__ ys, int bs, int tid, int lane, int warp) {
   const int nsb = (bs + 31) / 32;
   for (int q = 0; q < nsb; ++q) {
     const int sb = UPPER ? (nsb - 1 - q) * 32 : q * 32;
     const int sw = min(32, bs - sb);
     if (warp == 0) {
-      double t[32];
-#pragma unroll
-      for (int r = 0; r < 32; ++r) t[r] = (lane < sw && r < sw) ? T[(sb + lane) * TS_LD + sb + r] : 0.0;
-      double yi = lane < sw ? ys[sb + lane] : 0.0;
       if (!UPPER) {
+        // y = Linv * r : row `lane`, four independent FMA chains over the 32 columns
+        const double* li = Linv + (sb + lane) * TS_LI;
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          p0 = fma(li[c], (c < sw) ? ys[sb + c] : 0.0, p0);
+          p1 = fma(li[c + 1], (c + 1 < sw) ? ys[sb + c + 1] : 0.0, p1);
+          p2 = fma(li[c + 2], (c + 2 < sw) ? ys[sb + c + 2] : 0.0, p2);
+          p3 = fma(li[c + 3], (c + 3 < sw) ? ys[sb + c + 3] : 0.0, p3);
+        }
+        const double yi = (p0 + p1) + (p2 + p3);
+        __syncwarp();
+        if (lane < sw) ys[sb + lane] = yi;
+      } else {
+        double t[32];
+        double dg = 1.0;
 #pragma unroll
         for (int r = 0; r < 32; ++r) {
-          const double yr = __shfl_sync(0xffffffffu, yi, r);
-          if (lane > r) yi = fma(-t[r], yr, yi);
+          t[r] = (lane < sw && r < sw) ? T[(sb + lane) * TS_LD + sb + r] : 0.0;
+          if (lane == r) dg = t[r];
         }
-      } else {
-        double dinv = 1.0;
+        const double dinv = (lane < sw) ? 1.0 / dg : 1.0;
 #pragma unroll
-        for (int r = 0; r < 32; ++r)
-          if (lane == r) dinv = t[r];
-        dinv = (lane < sw) ? 1.0 / dinv : 1.0;  // one reciprocal per lane, off the dependent chain
+        for (int r = 0; r < 32; ++r) t[r] *= dinv;     // row scaled by 1/diagonal: off the dependent chain
+        double zi = (lane < sw ? ys[sb + lane] : 0.0) * dinv;
 #pragma unroll
         for (int r = 31; r >= 0; --r) {
           if (r < sw) {
-            if (lane == r) yi = yi * dinv;
-            const double yr = __shfl_sync(0xffffffffu, yi, r);
-            if (lane < r) yi = fma(-t[r], yr, yi);
+            const double yr = __shfl_sync(0xffffffffu, zi, r);
+            if (lane < r) zi = fma(-t[r], yr, zi);
           }
         }
+        if (lane < sw) ys[sb + lane] = zi;
       }
-      if (lane < sw) ys[sb + lane] = yi;
     }
     __syncthreads();
-    // remaining rows of the block
-    for (int i = UPPER ? tid : sb + sw + tid; UPPER ? (i < sb) : (i < bs); i += blockDim.x) {
-      double s = ys[i];
-      for (int c = 0; c < sw; ++c) s = fma(-T[i * TS_LD + sb + c], ys[sb + c], s);
-      ys[i] = s;
+    // remaining rows of the block: two threads per row, 16 columns each (at most 96 rows: one pass of 256 threads)
+    {
+      const int nrem = UPPER ? sb : bs - sb - sw;
+      const int rr = tid >> 1, half = tid & 1;
+      const bool act = rr < nrem;
+      const int i = UPPER ? rr : sb + sw + rr;
+      double sum = 0.0;
+      if (act) {
+        const double* trow = T + i * TS_LD + sb + 16 * half;
+        const double* yv = ys + sb + 16 * half;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < 16; c += 2) {
+          if (16 * half + c < sw) s0 = fma(trow[c], yv[c], s0);
+          if (16 * half + c + 1 < sw) s1 = fma(trow[c + 1], yv[c + 1], s1);
+        }
+        sum = s0 + s1;
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      if (act && half == 0) ys[i] -= sum;
     }
     __syncthreads();
   }
@@ -987,6 +1042,7 @@ __global__ void __launch_bounds__(256) lu_trisolve_step_kernel(const double* __r
   double* T = reinterpret_cast<double*>(smraw);  // [TS_BS][TS_LD]
   double* xs = T + TS_BS * TS_LD;                // [TS_BS] previous block's solution
   double* ys = xs + TS_BS;                       // [TS_BS] this block's right-hand side / solution
+  double* Linv = ys + TS_BS;                     // [4][32][TS_LI] inverted diagonal sub-blocks (forward solve)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (kprev >= 0)
     for (int c = tid; c < bsprev; c += 256) xs[c] = b[kprev + c];
@@ -1040,7 +1096,11 @@ __global__ void __launch_bounds__(256) lu_trisolve_step_kernel(const double* __r
   }
   cp_async_wait<0>();
   __syncthreads();
-  trisolve_diag_block<UPPER>(T, ys, bs, tid, lane, warp);
+  if (!UPPER) {
+    trisolve_prepare_lower(T, Linv, bs, lane, warp);
+    __syncthreads();
+  }
+  trisolve_diag_block<UPPER>(T, Linv, ys, bs, tid, lane, warp);
   if (tid < bs) b[kb + tid] = ys[tid];
 }
 
@@ -1073,6 +1133,7 @@ __global__ void __launch_bounds__(256, 1) lu_trisolve_wave_kernel(const double* 
   extern __shared__ __align__(16) unsigned char smraw[];
   double* T = reinterpret_cast<double*>(smraw);  // [TS_BS][TS_LD] diagonal block
   double* ys = T + TS_BS * TS_LD;                // [TS_BS] this block's right-hand side / solution
+  double* Linv = ys + 2 * TS_BS;                 // [4][32][TS_LI] inverted diagonal sub-blocks (forward solve)
   __shared__ int ticket;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nblk = (n + TS_BS - 1) / TS_BS;
@@ -1097,6 +1158,11 @@ __global__ void __launch_bounds__(256, 1) lu_trisolve_wave_kernel(const double* 
     double acc[RPW];
 #pragma unroll
     for (int rr = 0; rr < RPW; ++rr) acc[rr] = b[kb + min(warp * RPW + rr, bs - 1)];
+    if (!UPPER) {   // invert the diagonal sub-blocks now, long before this block is due
+      cp_async_wait<0>();
+      __syncthreads();
+      trisolve_prepare_lower(T, Linv, bs, lane, warp);
+    }
     for (int k = 0; k < q; ++k) {          // earlier blocks in solve order
       const int pblk = UPPER ? nblk - 1 - k : k;
       const int kp = pblk * TS_BS;
@@ -1113,7 +1179,7 @@ __global__ void __launch_bounds__(256, 1) lu_trisolve_wave_kernel(const double* 
         if (lane == 0) {
           int d = ld_acquire_gpu(&sync[1]);
           while (d <= k) {
-            __nanosleep(20);
+            if (k + 1 < q) __nanosleep(40);   // the block right before this one is polled without a pause
             d = ld_acquire_gpu(&sync[1]);
           }
           seen = d;
@@ -1140,10 +1206,9 @@ __global__ void __launch_bounds__(256, 1) lu_trisolve_wave_kernel(const double* 
     }
     cp_async_wait<0>();
     __syncthreads();
-    trisolve_diag_block<UPPER>(T, ys, bs, tid, lane, warp);
+    trisolve_diag_block<UPPER>(T, Linv, ys, bs, tid, lane, warp);
     if (tid < bs) b[kb + tid] = ys[tid];
-    __threadfence();
-    __syncthreads();
+    __syncthreads();               // every thread's store precedes thread 0's release (cumulative at gpu scope)
     if (tid == 0) st_release_gpu(&sync[1], q + 1);
   }
 }
@@ -1537,7 +1602,7 @@ static int apply_perm(LuPlan* p, double* A, long long lda, ColMap cm, int k, int
 }
 
 static int trisolve_configure() {
-  const size_t smem = (size_t)(TS_BS * TS_LD + 2 * TS_BS) * sizeof(double);
+  const size_t smem = TS_SMEM;
   if (wg_func_configured(reinterpret_cast<const void*>(lu_trisolve_step_kernel<false>), smem) < (long long)smem) {
     WG_CUDA(cudaFuncSetAttribute(lu_trisolve_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     WG_CUDA(cudaFuncSetAttribute(lu_trisolve_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1572,7 +1637,7 @@ static int rhs_panel(LuPlan* p, const double* LU, long long lda, int k, int nb, 
   WG_CUDA(launch_prio(lu_rhs_perm_panel_kernel, dim3(p->bt.count), dim3(1024), 0, st, p->rhs, p->permSrcTop, p->permBDst,
                       p->permBSrc, p->permNBot + pnl, k, nb, p->bt.sV, p->bt.sI, p->bt.sP));
   WG_LAUNCH_CHECK();
-  const size_t smem = (size_t)(TS_BS * TS_LD + 2 * TS_BS) * sizeof(double);
+  const size_t smem = TS_SMEM;
   for (int kb = k; kb < k + nb; kb += TS_BS) {
     const int bs = TS_BS < k + nb - kb ? TS_BS : k + nb - kb;
     const int rest = n - kb - bs;
@@ -1867,7 +1932,7 @@ static int solve_enqueue(LuPlan* p, const double* LU, long long lda, double* b, 
   const int n = p->n, NB = p->t.nb;
   int rcc = trisolve_configure();
   if (rcc) return rcc;
-  const size_t smem = (size_t)(TS_BS * TS_LD + 2 * TS_BS) * sizeof(double);
+  const size_t smem = TS_SMEM;
   const int nblk = wg_cdiv(n, TS_BS);
   int kprev = -1, bsprev = 0;
   if (!backwardOnly) {
