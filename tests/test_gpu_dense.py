@@ -630,27 +630,30 @@ def test_lu_batched_singular_member(env):
 
 @pytest.mark.parametrize("n", [1, 31, 128, 129, 300, 1900, 5000])
 def test_trisolve_wavefront_equals_block_steps(env, n):
-    """The persistent wavefront form of the triangular solves (two launches, ticket + published counter) gives
-    the bits of the one-launch-per-block form, on streams and as a graph, run after run; and solves the system."""
+    """The persistent wavefront form of the triangular solves (two launches, ticket + published counter, diagonal
+    blocks applied through their inverses) is reproducible bit for bit on streams and as a graph, run after run;
+    it agrees with the one-launch-per-block substitution form to rounding, and solves the system."""
     torch, lib, _ = env
     rng = np.random.default_rng(11 * n + 1)
     A = rng.standard_normal((n, n))
     b = rng.standard_normal(n)
-    outs = []
+    outs = {}
     try:
-        for wave, graph in ((1, 1), (0, 1), (1, 0), (1, 1)):
+        for key, (wave, graph) in enumerate(((1, 1), (0, 1), (1, 0), (1, 1))):
             lib.wg_debug_wave_solve(wave)
             lib.wg_set_tuning(256, graph)
             LU, ipiv, info, x = _lu(env, A, b)
             assert info == 0
-            outs.append(x)
+            outs[key] = x
     finally:
         lib.wg_debug_wave_solve(1)
         lib.wg_set_tuning(256, 1)
-    for x in outs[1:]:
-        assert np.array_equal(outs[0], x)
+    assert np.array_equal(outs[0], outs[2]) and np.array_equal(outs[0], outs[3])
     xr = np.linalg.solve(A, b)
-    assert np.max(np.abs(outs[0] - xr)) / np.max(np.abs(xr)) < 1e-9
+    scale = np.max(np.abs(xr))
+    assert np.max(np.abs(outs[0] - outs[1])) / scale < 1e-9
+    assert np.max(np.abs(outs[0] - xr)) / scale < 1e-9
+    assert np.max(np.abs(outs[1] - xr)) / scale < 1e-9
 
 
 def test_trisolve_wavefront_many_right_hand_sides(env):

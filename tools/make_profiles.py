@@ -1,8 +1,10 @@
-"""Turns the ncu outputs brought back in gpurun_out/ into the tracked summaries under profiles/."""
+"""Turns the ncu outputs brought back in gpurun_out/ into the tracked summaries under profiles/.
+    python tools/make_profiles.py raw <report.ncu-rep in gpurun_out> <name under profiles/>
+    python tools/make_profiles.py launches <launch list .csv in gpurun_out> <prefix under profiles/>
+    python tools/make_profiles.py r01        (the round-1 set)"""
 import collections, csv, gzip, os, re, shutil, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 G = os.path.join(ROOT, "gpurun_out"); P = os.path.join(ROOT, "profiles")
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 
 def launch_list(src, dst_prefix):
     path = os.path.join(G, src)
@@ -39,15 +41,27 @@ def raw_page(rep, dst):
         w = csv.writer(f); w.writerow(["metric", "unit"] + [f"launch{j}" for j in range(len(rows) - 2)])
         for i in idx: w.writerow([hdr[i], units[i]] + [r[i] for r in rows[2:]])
 
-launch_list("launches_r1c_cfg2a.csv", f"{tag}_cfg2a")
-raw_page("prof_gemm_r1_v1.ncu-rep", f"{tag}_ncu_full_dgemm_128x64_2cta.csv")
-raw_page("prof_gemm_r1.ncu-rep", f"{tag}_ncu_full_dgemm_128x128_1cta.csv")
-raw_page("prof_assemble_r1.ncu-rep", f"{tag}_ncu_full_assemble.csv")
-raw_page("prof_leaf_r3.ncu-rep", f"{tag}_ncu_full_panel_leaf.csv")
-raw_page("prof_trsm_r1.ncu-rep", f"{tag}_ncu_full_trsm_strip.csv")
-raw_page("prof_trisolve_r1.ncu-rep", f"{tag}_ncu_full_trisolve_step.csv")
-raw_page("prof_moments_r1.ncu-rep", f"{tag}_ncu_full_truncation_moments.csv")
-raw_page("prof_perm_r1.ncu-rep", f"{tag}_ncu_full_perm_gather.csv")
-for f in ("bench_1gpu.json", "leaf_timing.log"):
-    if os.path.exists(os.path.join(G, f)): shutil.copy(os.path.join(G, f), os.path.join(P, f"{tag}_{f}"))
-print(sorted(os.listdir(P)))
+def round1(tag="r01"):
+    launch_list("launches_r1c_cfg2a.csv", f"{tag}_cfg2a")
+    raw_page("prof_gemm_r1_v1.ncu-rep", f"{tag}_ncu_full_dgemm_128x64_2cta.csv")
+    raw_page("prof_gemm_r1.ncu-rep", f"{tag}_ncu_full_dgemm_128x128_1cta.csv")
+    raw_page("prof_assemble_r1.ncu-rep", f"{tag}_ncu_full_assemble.csv")
+    raw_page("prof_leaf_r3.ncu-rep", f"{tag}_ncu_full_panel_leaf.csv")
+    raw_page("prof_trsm_r1.ncu-rep", f"{tag}_ncu_full_trsm_strip.csv")
+    raw_page("prof_trisolve_r1.ncu-rep", f"{tag}_ncu_full_trisolve_step.csv")
+    raw_page("prof_moments_r1.ncu-rep", f"{tag}_ncu_full_truncation_moments.csv")
+    raw_page("prof_perm_r1.ncu-rep", f"{tag}_ncu_full_perm_gather.csv")
+    for f in ("bench_1gpu.json", "leaf_timing.log"):
+        if os.path.exists(os.path.join(G, f)): shutil.copy(os.path.join(G, f), os.path.join(P, f"{tag}_{f}"))
+
+
+if __name__ == "__main__":
+    if len(sys.argv) == 4 and sys.argv[1] == "raw":
+        raw_page(sys.argv[2], sys.argv[3])
+    elif len(sys.argv) == 4 and sys.argv[1] == "launches":
+        launch_list(sys.argv[2], sys.argv[3])
+    elif len(sys.argv) == 2 and sys.argv[1] == "r01":
+        round1()
+    else:
+        sys.exit(__doc__)
+    print(sorted(os.listdir(P)))

@@ -1123,18 +1123,109 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
 }
 
+// Inverses of the 128 x 128 diagonal blocks of L (unit lower) and U, computed once per factorisation (one CTA per
+// block and triangle; thread j builds column j of the inverse by substitution, columns live in shared memory).
+// With them the diagonal step of the wavefront solve is one 128 x 128 matrix-vector product instead of a 128-step
+// dependent substitution -- the same device cuBLAS / MAGMA use for their triangular solves (trtri of the diagonal
+// blocks).  The inverse-based solve is not componentwise backward stable the way substitution is; the error it
+// adds is of the order cond(block) * eps and is removed, with the LU's own cond(A) * eps, by the refinement step
+// that follows every solve (wg_refine).  dinv: [system][block][triangle (0 = L, 1 = U)][128][128], rows and columns
+// beyond a short last block are those of the identity.
+__global__ void __launch_bounds__(256) lu_diag_invert_kernel(const double* __restrict__ LU, long long lda, int n,
+                                                             double* __restrict__ dinv, long long sA, long long sD) {
+  // One CTA per diagonal block, both triangles at once and in place in shared memory (LAPACK dtrti2 order):
+  // threads 0..127 own the rows of L^-1 (columns right to left), threads 128..255 the rows of U^-1 (columns left
+  // to right).  In step s a thread reads only its own row and the original column, which is parked in `col`.
+  extern __shared__ __align__(16) unsigned char smraw[];
+  double* T = reinterpret_cast<double*>(smraw);   // [TS_BS][TS_LD]
+  double* col = T + TS_BS * TS_LD;                // [2 parities][2 triangles][TS_BS]
+  const int blk = blockIdx.x;
+  LU += (long long)blockIdx.y * sA;
+  double* out = dinv + (long long)blockIdx.y * sD + (long long)blk * 2 * TS_BS * TS_BS;
+  const int kb = blk * TS_BS;
+  const int bs = min(TS_BS, n - kb);
+  const int tid = threadIdx.x;
+  for (int e = tid; e < TS_BS * TS_BS; e += 256) {
+    const int r = e >> 7, c = e & (TS_BS - 1);
+    T[r * TS_LD + c] = (r < bs && c < bs) ? LU[(long long)(kb + r) * lda + kb + c] : (r == c ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  const bool up = tid >= TS_BS;
+  const int i = tid & (TS_BS - 1);
+  double* row = T + i * TS_LD;
+  if (up) row[i] = 1.0 / row[i];      // X_ii of the upper triangle (own row, read by nobody else before the barrier)
+  __syncthreads();
+  for (int s = 0; s < TS_BS - 1; ++s) {
+    double* cl = col + (s & 1) * 2 * TS_BS + (up ? TS_BS : 0);
+    const int j = up ? 1 + s : TS_BS - 2 - s;
+    if (up ? (i < j) : (i > j)) cl[i] = row[j];
+    __syncthreads();
+    if (!up) {
+      if (i > j) {   // x_i = -( l_i + sum_{j < c < i} X[i][c] l_c )
+        double a0 = cl[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int c = j + 1;
+        for (; c + 7 < i; c += 8) {      // loads of eight terms in flight, four FMA chains
+          const double r0 = row[c], r1 = row[c + 1], r2 = row[c + 2], r3 = row[c + 3];
+          const double r4 = row[c + 4], r5 = row[c + 5], r6 = row[c + 6], r7 = row[c + 7];
+          a0 = fma(r0, cl[c], a0);
+          a1 = fma(r1, cl[c + 1], a1);
+          a2 = fma(r2, cl[c + 2], a2);
+          a3 = fma(r3, cl[c + 3], a3);
+          a0 = fma(r4, cl[c + 4], a0);
+          a1 = fma(r5, cl[c + 5], a1);
+          a2 = fma(r6, cl[c + 6], a2);
+          a3 = fma(r7, cl[c + 7], a3);
+        }
+        for (; c < i; ++c) a0 = fma(row[c], cl[c], a0);
+        row[j] = -((a0 + a1) + (a2 + a3));
+      }
+    } else {
+      if (i < j) {   // x_i = -( sum_{i <= c < j} X[i][c] u_c ) * X_jj
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int c = i;
+        for (; c + 7 < j; c += 8) {
+          const double r0 = row[c], r1 = row[c + 1], r2 = row[c + 2], r3 = row[c + 3];
+          const double r4 = row[c + 4], r5 = row[c + 5], r6 = row[c + 6], r7 = row[c + 7];
+          a0 = fma(r0, cl[c], a0);
+          a1 = fma(r1, cl[c + 1], a1);
+          a2 = fma(r2, cl[c + 2], a2);
+          a3 = fma(r3, cl[c + 3], a3);
+          a0 = fma(r4, cl[c + 4], a0);
+          a1 = fma(r5, cl[c + 5], a1);
+          a2 = fma(r6, cl[c + 6], a2);
+          a3 = fma(r7, cl[c + 7], a3);
+        }
+        for (; c < j; ++c) a0 = fma(row[c], cl[c], a0);
+        row[j] = -((a0 + a1) + (a2 + a3)) * T[j * TS_LD + j];
+      }
+    }
+    // (the other parity of `col` is written next; this one is not touched again before the barrier after that)
+  }
+  __syncthreads();
+  for (int e = tid; e < TS_BS * TS_BS; e += 256) {
+    const int r = e >> 7, c = e & (TS_BS - 1);
+    const double v = T[r * TS_LD + c];
+    out[e] = c < r ? v : (c == r ? 1.0 : 0.0);
+    out[TS_BS * TS_BS + e] = c >= r ? v : 0.0;
+  }
+}
+
 template <bool UPPER>
 __global__ void __launch_bounds__(256, 1) lu_trisolve_wave_kernel(const double* __restrict__ LU, long long lda,
                                                                   double* __restrict__ b, int n, int* __restrict__ sync,
-                                                                  long long sA, long long sV) {
+                                                                  const double* __restrict__ dinv, long long sA,
+                                                                  long long sV, long long sD, int ablate) {
+  // ablate: developer timing probe (wrong results when non-zero): 1 skip the diagonal step, 2 do not wait for
+  // published blocks, 8 skip the streaming products
   LU += (long long)blockIdx.y * sA;   // system of the batch
   b += (long long)blockIdx.y * sV;
+  dinv += (long long)blockIdx.y * sD;
   sync += 4 * blockIdx.y + (UPPER ? 2 : 0);
   extern __shared__ __align__(16) unsigned char smraw[];
-  double* T = reinterpret_cast<double*>(smraw);  // [TS_BS][TS_LD] diagonal block
-  double* ys = T + TS_BS * TS_LD;                // [TS_BS] this block's right-hand side / solution
-  double* Linv = ys + 2 * TS_BS;                 // [4][32][TS_LI] inverted diagonal sub-blocks (forward solve)
+  double* T = reinterpret_cast<double*>(smraw);  // [TS_BS][TS_LD] inverse of this block's diagonal block
+  double* ys = T + TS_BS * TS_LD;                // [TS_BS] this block's right-hand side
   __shared__ int ticket;
+  __shared__ int seenSh;      // published count as read by thread 0
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nblk = (n + TS_BS - 1) / TS_BS;
   constexpr int RPW = TS_BS / 8;   // rows per warp
@@ -1149,21 +1240,16 @@ __global__ void __launch_bounds__(256, 1) lu_trisolve_wave_kernel(const double* 
     const int blk = UPPER ? nblk - 1 - q : q;
     const int kb = blk * TS_BS;
     const int bs = min(TS_BS, n - kb);
-    {  // diagonal block -> shared memory, asynchronously (static data: no dependency)
-      const int c = tid & (TS_BS - 1);
-      for (int i = tid >> 7; i < bs; i += 2)
-        cp_async8(&T[i * TS_LD + c], LU + (long long)(kb + i) * lda + kb + c, c < bs);
+    {  // inverse diagonal block -> shared memory, asynchronously (static data: no dependency)
+      const double* src = dinv + ((long long)blk * 2 + (UPPER ? 1 : 0)) * TS_BS * TS_BS;
+      for (int e = tid; e < TS_BS * TS_BS; e += 256) cp_async8(&T[(e >> 7) * TS_LD + (e & (TS_BS - 1))], src + e, true);
       cp_async_commit();
     }
     double acc[RPW];
 #pragma unroll
     for (int rr = 0; rr < RPW; ++rr) acc[rr] = b[kb + min(warp * RPW + rr, bs - 1)];
-    if (!UPPER) {   // invert the diagonal sub-blocks now, long before this block is due
-      cp_async_wait<0>();
-      __syncthreads();
-      trisolve_prepare_lower(T, Linv, bs, lane, warp);
-    }
-    for (int k = 0; k < q; ++k) {          // earlier blocks in solve order
+    if (ablate & 2) seen = INT_MAX;
+    for (int k = 0; k < ((ablate & 8) ? 0 : q); ++k) {          // earlier blocks in solve order
       const int pblk = UPPER ? nblk - 1 - k : k;
       const int kp = pblk * TS_BS;
       const int bsp = min(TS_BS, n - kp);
@@ -1176,16 +1262,24 @@ __global__ void __launch_bounds__(256, 1) lu_trisolve_wave_kernel(const double* 
         for (int u = 0; u < CPL; ++u) v[rr][u] = __ldcs(row + min(lane + 32 * u, bsp - 1));
       }
       if (k >= seen) {
-        if (lane == 0) {
+        // ONE thread per CTA polls the published count and backs off by the number of blocks still ahead of the
+        // one it needs; only the CTA that is next in line spins without a pause.  CTA-uniform branch: `seen` is
+        // the same in every warp.
+        if (tid == 0) {
           int d = ld_acquire_gpu(&sync[1]);
           while (d <= k) {
-            if (k + 1 < q) __nanosleep(40);   // the block right before this one is polled without a pause
+            const int gap = k - d;                       // whole block steps before block k is even started
+            if (gap > 0)
+              __nanosleep(gap >= 16 ? 8000 : 500 * gap);
+            else if (k + 1 < q)
+              __nanosleep(100);
             d = ld_acquire_gpu(&sync[1]);
           }
-          seen = d;
+          seenSh = d;
         }
-        seen = __shfl_sync(0xffffffffu, seen, 0);
-        __syncwarp();   // orders the other lanes' loads of the solution behind lane 0's acquire
+        __syncthreads();
+        seen = seenSh;
+        __syncthreads();   // everybody has read it before thread 0 can write the next one
       }
       double xv[CPL];
 #pragma unroll
@@ -1206,8 +1300,25 @@ __global__ void __launch_bounds__(256, 1) lu_trisolve_wave_kernel(const double* 
     }
     cp_async_wait<0>();
     __syncthreads();
-    trisolve_diag_block<UPPER>(T, Linv, ys, bs, tid, lane, warp);
-    if (tid < bs) b[kb + tid] = ys[tid];
+    // ---- diagonal step: y = Dinv * (right-hand side), rows as in the streaming products
+    if (!(ablate & 1)) {
+      double rv[CPL];
+#pragma unroll
+      for (int u = 0; u < CPL; ++u) rv[u] = (lane + 32 * u < bs) ? ys[lane + 32 * u] : 0.0;
+      double yo = 0.0;
+#pragma unroll
+      for (int rr = 0; rr < RPW; ++rr) {
+        const double* trow = T + (warp * RPW + rr) * TS_LD;
+        double sacc = 0.0;
+#pragma unroll
+        for (int u = 0; u < CPL; ++u) sacc = fma(trow[lane + 32 * u], rv[u], sacc);
+        sacc = warp_sum(sacc);
+        if (lane == rr) yo = sacc;
+      }
+      if (lane < RPW && warp * RPW + lane < bs) b[kb + warp * RPW + lane] = yo;
+    } else if (tid < bs) {
+      b[kb + tid] = ys[tid];
+    }
     __syncthreads();               // every thread's store precedes thread 0's release (cumulative at gpu scope)
     if (tid == 0) st_release_gpu(&sync[1], q + 1);
   }
@@ -1228,6 +1339,8 @@ struct LuPlan {
   int *permSrcTop = nullptr, *permBDst = nullptr, *permBSrc = nullptr, *permNBot = nullptr;
   int* posContent = nullptr;
   int* solveSync = nullptr;                // [batch][4] ticket / published counters of the wavefront solves
+  double* dinv = nullptr;                  // [batch][nblk][2][128][128] inverses of the diagonal blocks of L and U
+  long long sDinv = 0;                     // doubles per system in dinv
   int numSMs = 148;
   double *S = nullptr, *S2 = nullptr;      // row staging of the bulk permutation (256 x n each)
   double *Sc = nullptr, *Sc2 = nullptr;    // row staging of the chain permutation (256 x 256 each)
@@ -1335,6 +1448,8 @@ static int lu_plan_fill(LuPlan* p, int n, int batch) {
   WG_CUDA(cudaMalloc(&p->posContent, sizeof(int) * n * B));
   WG_CUDA(cudaMemset(p->posContent, 0xff, sizeof(int) * n * B));
   WG_CUDA(cudaMalloc(&p->solveSync, sizeof(int) * 4 * B));
+  p->sDinv = (long long)wg_cdiv(n, TS_BS) * 2 * TS_BS * TS_BS;
+  WG_CUDA(cudaMalloc(&p->dinv, sizeof(double) * (size_t)p->sDinv * B));
   {
     int dev = 0;
     WG_CUDA(cudaGetDevice(&dev));
@@ -1403,6 +1518,7 @@ void lu_plan_destroy(LuPlan* p) {
   cudaFree(p->permNBot);
   cudaFree(p->posContent);
   cudaFree(p->solveSync);
+  cudaFree(p->dinv);
   cudaFree(p->S);
   cudaFree(p->S2);
   cudaFree(p->Sc);
@@ -1825,6 +1941,14 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
     WG_CUDA(cudaEventRecord(p->evPhase, bs));
     WG_CUDA(cudaStreamWaitEvent(st, p->evPhase, 0));
   }
+  // inverses of the 128 x 128 diagonal blocks of L and U for the wavefront triangular solves
+  {
+    const size_t smemInv = (size_t)(TS_BS * TS_LD + 4 * TS_BS) * sizeof(double);
+    if (wg_func_configured(reinterpret_cast<const void*>(lu_diag_invert_kernel), smemInv) < (long long)smemInv)
+      WG_CUDA(cudaFuncSetAttribute(lu_diag_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemInv));
+    lu_diag_invert_kernel<<<dim3(wg_cdiv(n, TS_BS), bt.count), 256, smemInv, st>>>(A, lda, n, p->dinv, bt.sA, p->sDinv);
+    WG_LAUNCH_CHECK();
+  }
   return WG_OK;
 }
 
@@ -1945,10 +2069,12 @@ static int solve_enqueue(LuPlan* p, const double* LU, long long lda, double* b, 
     WG_CUDA(cudaMemsetAsync(p->solveSync, 0, sizeof(int) * 4 * p->bt.count, st));
     const dim3 grid(nblk < p->numSMs ? nblk : p->numSMs, p->bt.count);
     if (!backwardOnly) {
-      lu_trisolve_wave_kernel<false><<<grid, 256, smem, st>>>(LU, lda, b, n, p->solveSync, p->bt.sA, p->bt.sV);
+      lu_trisolve_wave_kernel<false><<<grid, 256, smem, st>>>(LU, lda, b, n, p->solveSync, p->dinv, p->bt.sA, p->bt.sV,
+                                                              p->sDinv, p->t.waveSolve >> 4);
       WG_LAUNCH_CHECK();
     }
-    lu_trisolve_wave_kernel<true><<<grid, 256, smem, st>>>(LU, lda, b, n, p->solveSync, p->bt.sA, p->bt.sV);
+    lu_trisolve_wave_kernel<true><<<grid, 256, smem, st>>>(LU, lda, b, n, p->solveSync, p->dinv, p->bt.sA, p->bt.sV,
+                                                           p->sDinv, p->t.waveSolve >> 4);
     WG_LAUNCH_CHECK();
     return WG_OK;
   }

@@ -43,6 +43,16 @@ def _row(out, nSolves):
                            d.Delta20.coefficients.ravel(), d.Delta11.coefficients.ravel()])
 
 
+def unpackRow(row, nFields: int, P: int, M: int):
+    """One row of the scan table -> dict(pressure, widths, offsets, solves, Deltas [4, P, M-1]); NaN rows are
+    points that were not started within the budget."""
+    row = np.asarray(row)
+    assert row.size == rowWidth(nFields, P, M)
+    o = 1 + 2 * nFields
+    return dict(pressure=float(row[0]), widths=row[1:1 + nFields].copy(), offsets=row[1 + nFields:o].copy(),
+                solves=row[o], Deltas=row[o + 1:].reshape(4, P, M - 1).copy())
+
+
 def _initialWallParams(WallGo, ws):
     eom = ws.eom
     eom.pressAbsErrTol = 1e-8          # EOM.solveWall sets this before its first wallPressure (:474)
@@ -180,14 +190,16 @@ class HostWorkers:
 
 def defaultWorkers(worldSize: int = 1) -> int:
     """Host processes per rank: the node's cores are divided evenly among its GPUs (so the per-GPU host budget
-    does not depend on how many ranks a run uses), one core stays with the rank process, at most 8."""
+    does not depend on how many ranks a run uses), one core stays with the rank process, at most 14 (beyond
+    that the solve server of one GPU, not the host loop, bounds the scan: ~0.05 s of GPU per solve against ~0.5 s
+    of host Python per solve per worker)."""
     try:
         import torch  # pylint: disable=import-outside-toplevel
         gpus = max(1, torch.cuda.device_count())
     except Exception:  # pylint: disable=broad-except
         gpus = 1
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    return max(1, min(8, cores // max(gpus, worldSize) - 1))
+    return max(1, min(14, cores // max(gpus, worldSize) - 1))
 
 
 def _serverWallSolver(manager, settings):
