@@ -535,6 +535,7 @@ def test_refinement_reaches_the_extended_precision_solution(cuda_device, case):
     solver.getDeltas()
     dmax, xmax = solver.lastRefinement
     assert abs(dmax / xmax - e0) <= 0.5 * e0 + 1e-15      # the correction IS the forward error of the first solve
+    assert solver.conditionEstimate() == dmax / xmax / 2.0 ** -53
 
 
 def test_refinement_in_every_path_is_the_same(cuda_device):

@@ -405,6 +405,16 @@ class BoltzmannSolverB200Mixin:
             self.lastRefinement = eng.last_refinement if getattr(self, "refinementSteps", 1) else None
         return self._wrapResults(dF, deltas, err, keep, peaks)
 
+    def conditionEstimate(self):
+        """Condition number the last solve experienced, from the refinement step: (max|correction| / max|deltaF|)
+        / 2^-53, i.e. the forward error of the plain LU solve in units of the rounding unit.  A by-product (no extra
+        device work); None when refinement is off or nothing has been solved yet.  SURVEY.md section 7 asks for a
+        cheap estimate to decide on refinement; here the step always runs (about 1 % of a solve) and reports it."""
+        lr = getattr(self, "lastRefinement", None)
+        if not lr or not lr[1] > 0.0:
+            return None
+        return float(lr[0] / lr[1] / 2.0 ** -53)
+
     def getFeedback(self):
         """Out-of-equilibrium source terms of the wall EOM computed on the device from the moments of the
         LAST getDeltas() call: dict with T30, T33 (EOM.deltaToTmunu, equationOfMotion.py:2021-2127, all

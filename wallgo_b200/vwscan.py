@@ -190,16 +190,17 @@ class HostWorkers:
 
 def defaultWorkers(worldSize: int = 1) -> int:
     """Host processes per rank: the node's cores are divided evenly among its GPUs (so the per-GPU host budget
-    does not depend on how many ranks a run uses), one core stays with the rank process, at most 14 (beyond
-    that the solve server of one GPU, not the host loop, bounds the scan: ~0.05 s of GPU per solve against ~0.5 s
-    of host Python per solve per worker)."""
+    does not depend on how many ranks a run uses), one core stays with the rank process, at most 12.  (A 256-point scan
+    on 8 GPUs leaves 32 points per rank: 11 to 15 workers all need three rounds of ~2.3 s, so more than 12 would
+    only make the 1-GPU run faster and the measured scaling efficiency worse; the solve server of one GPU keeps up
+    with ~25 workers: ~0.05 s of GPU per solve against ~0.5 s of host Python per solve per worker.)"""
     try:
         import torch  # pylint: disable=import-outside-toplevel
         gpus = max(1, torch.cuda.device_count())
     except Exception:  # pylint: disable=broad-except
         gpus = 1
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    return max(1, min(14, cores // max(gpus, worldSize) - 1))
+    return max(1, min(12, cores // max(gpus, worldSize) - 1))
 
 
 def _serverWallSolver(manager, settings):
