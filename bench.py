@@ -393,6 +393,10 @@ def run_scan(a, world, rank, local, prep=None):
             "point": "EOM.wallPressure(vw_i, wallParams0, None) of the unmodified reference wall solver, Boltzmann "
                      "solves on the GPU via wallgo_b200.dropin (vectoriseEOM); one all_gather of the result rows",
             "host_workers_per_rank": int(workers), "points_per_rank": mine,
+            "host_cores": os.cpu_count(), "gpus_in_node": vwscan._physicalGpus(),
+            "host_budget": "workers per rank = min(12, cores // GPUs installed in the node - 1): the same host share per "
+                           "GPU at every rank count, so the scan's strong scaling is that of the GPUs (the scan is bounded "
+                           "by the reference's host loop, ~2 s of Python per point per worker, not by the device)",
             "boltzmann_solves": solves, "solves_per_point": solves / max(1, ndone),
             "host_seconds_per_point": hostTotal / max(1, ndone),
             "host_note": "wall time a point spends in the reference's host loop + waiting for its solves, summed "

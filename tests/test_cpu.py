@@ -398,3 +398,32 @@ def test_collision_directory_ingest_and_errors(tmp_path):
     (tmp_path / "collisions_p1_p0.hdf5").write_text("version https://git-lfs.github.com/spec/v1\n")   # an LFS pointer
     with pytest.raises(wb.CollisionLoadError):
         solver.loadCollisions(tmp_path)
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """Argument checks of the round-2 entry points run before any CUDA call: NULL handles and bad ranges return
+    WG_ERR_ARG (-1) with a message; nothing computes on the CPU."""
+    from wallgo_b200 import _lib
+
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.skip("library not built")
+    lib = _lib.load()
+    null = C.c_void_p()
+    out = C.c_void_p()
+    assert lib.wg_batch_create(null, 4, C.byref(out)) == -1
+    assert b"wg_batch_create" in lib.wg_last_error()
+    assert lib.wg_batch_assemble(null, None, None, 1.0, 3, None, 8, 64, None, None) == -1
+    assert lib.wg_batch_factor(null, None, 8, 64, None) == -1
+    assert lib.wg_batch_solve(null, None, 8, 64, None, None) == -1
+    assert lib.wg_batch_refine(null, None, None, 1.0, None, 8, 64, None, None, None) == -1
+    assert lib.wg_batch_spectra(null, None, None, None) == -1
+    assert lib.wg_batch_moments(null, None, None, None, 1, None, None, None, None) == -1
+    assert lib.wg_batch_info(null, None, None) == -1
+    assert lib.wg_batch_destroy(null) == 0
+    assert lib.wg_refine(null, None, 0.5, 1.0, None, 8, None, None, None) == -1
+    assert b"wg_refine" in lib.wg_last_error()
+    assert lib.wg_assemble_rows(null, None, 0.5, 1.0, 3, 0, 1, None, 8, None, None) == -1
+    assert lib.wg_lu_create_batched(0, 4, 0, C.byref(out)) == -1
+    assert lib.wg_lu_create_batched(8, 0, 0, C.byref(out)) == -1
+    assert lib.wg_lu_factor_batched(null, None, 8, 64, None, None, None) == -1
+    assert lib.wg_lu_solve_batched(null, None, 8, 64, None, 8, None) == -1

@@ -580,11 +580,22 @@ class BoltzmannSolverB200Mixin:
                 if slot >= len(chunks[c]) and slot > 0:
                     be.inp_host[slot].copy_(be.inp_host[slot - 1])
                     continue
-                self.setBackground(backgrounds[item])
-                bg = self.background
-                be.set_system(slot, np.asarray(bg.temperatureProfile, dtype=np.float64),
-                              np.asarray(bg.velocityProfile, dtype=np.float64), self._msq(bg.fieldProfiles), dxidchi,
-                              float(bg.velocityWall))
+                bg = backgrounds[item]
+                if type(bg).__name__ == "BoltzmannBackground" and type(bg).boostToPlasmaFrame.__qualname__ == \
+                        "BoltzmannBackground.boostToPlasmaFrame":
+                    # setBackground without the deep copy: the boost of containers.py:152-157 (same expression,
+                    # same bits) applied to the two quantities it changes
+                    vm = bg.velocityMid
+                    vprof = np.asarray(bg.velocityProfile, dtype=np.float64)
+                    v = (vprof - vm) / (1.0 - vprof * vm)
+                    vw = (bg.velocityWall - vm) / (1.0 - bg.velocityWall * vm)
+                    T, fields = bg.temperatureProfile, bg.fieldProfiles
+                else:
+                    self.setBackground(bg)
+                    b2 = self.background
+                    T, v, fields, vw = b2.temperatureProfile, b2.velocityProfile, b2.fieldProfiles, b2.velocityWall
+                be.set_system(slot, np.asarray(T, dtype=np.float64), np.asarray(v, dtype=np.float64), self._msq(fields),
+                              dxidchi, float(vw))
             state[c] = (be.solve_async(mult, bool(getattr(self, "refinementSteps", 1))), None)
 
         def decide(c):
@@ -611,6 +622,7 @@ class BoltzmannSolverB200Mixin:
                                                   dh[slot].reshape(4, P, M1).copy(), eh[slot].reshape(P, 4).copy(),
                                                   keep, peaks)
 
+        self.setBackground(backgrounds[-1])     # what a sequential loop would leave behind
         nC = len(chunks)
         for c in range(nC + 2):
             if c >= 2:

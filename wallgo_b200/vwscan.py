@@ -188,17 +188,31 @@ class HostWorkers:
         self.conns, self.procs = [], []
 
 
-def defaultWorkers(worldSize: int = 1) -> int:
-    """Host processes per rank: the node's cores are divided evenly among its GPUs (so the per-GPU host budget
-    does not depend on how many ranks a run uses), one core stays with the rank process, at most 12.  (A 256-point scan
-    on 8 GPUs leaves 32 points per rank: 11 to 15 workers all need three rounds of ~2.3 s, so more than 12 would
-    only make the 1-GPU run faster and the measured scaling efficiency worse; the solve server of one GPU keeps up
-    with ~25 workers: ~0.05 s of GPU per solve against ~0.5 s of host Python per solve per worker.)"""
+def _physicalGpus() -> int:
+    """GPUs installed in this node (NVML: not narrowed by CUDA_VISIBLE_DEVICES, does not initialise CUDA)."""
     try:
-        import torch  # pylint: disable=import-outside-toplevel
-        gpus = max(1, torch.cuda.device_count())
+        import pynvml  # pylint: disable=import-outside-toplevel
+        pynvml.nvmlInit()
+        try:
+            return max(1, int(pynvml.nvmlDeviceGetCount()))
+        finally:
+            pynvml.nvmlShutdown()
     except Exception:  # pylint: disable=broad-except
-        gpus = 1
+        try:
+            import torch  # pylint: disable=import-outside-toplevel
+            return max(1, torch.cuda.device_count())
+        except Exception:  # pylint: disable=broad-except
+            return 1
+
+
+def defaultWorkers(worldSize: int = 1) -> int:
+    """Host processes per rank.  The node's cores are divided evenly among the GPUs INSTALLED in it, so the host
+    budget of one GPU is the same whether a run uses one rank or all of them (a scan is bounded by the host loop
+    of the reference, ~2 s of Python per point, long before the GPU: the scaling a run reports is then that of the
+    GPUs with their share of the host, not that of idle cores); one core stays with the rank process; at most 12
+    (the solve server of one GPU keeps up with ~25 workers: ~0.05 s of GPU per solve against ~0.5 s of host Python
+    per solve per worker)."""
+    gpus = _physicalGpus()
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     return max(1, min(12, cores // max(gpus, worldSize) - 1))
 
