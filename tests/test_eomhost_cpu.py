@@ -85,6 +85,9 @@ def test_findPlasmaProfile_matches_reference_inside_solveWall():
     origFind = WallGo.EOM.findPlasmaProfile
     worst = {"T": 0.0, "v": 0.0, "calls": 0}
 
+    origViol = WallGo.EOM.violationOfEMConservation
+    worst.update(viol=0.0, violCalls=0)
+
     def both(self, *args):
         Tr, vr = origFind(self, *args)
         flagR = self.successTemperatureProfile
@@ -95,20 +98,81 @@ def test_findPlasmaProfile_matches_reference_inside_solveWall():
         worst["calls"] += 1
         return Tr, vr
 
+    def bothViol(self, *args):
+        r = origViol(self, *args)
+        g = eomhost.violationOfEMConservation(self, *args)
+        worst["viol"] = max(worst["viol"], abs(g[0] - r[0]) / abs(r[0]), abs(g[1] - r[1]) / abs(r[1]))
+        worst["violCalls"] += 1
+        return r
+
     ref.loadCollisions = lambda self, path: self.setCollisionArray(make_trace.rta_collisions(self))
     try:
         WallGo.EOM.findPlasmaProfile = both
+        WallGo.EOM.violationOfEMConservation = bothViol
         manager, settings = make_trace.build_manager(8, 5)
         resRef = manager.solveWall(settings)
-        assert worst["calls"] > 20
+        assert worst["calls"] > 20 and worst["violCalls"] > 5
         assert worst["T"] < 1e-8 and worst["v"] < 1e-8, worst
+        assert worst["viol"] < 1e-10, worst            # the energy-momentum residuals on all points at once
         WallGo.EOM.findPlasmaProfile = origFind
+        WallGo.EOM.violationOfEMConservation = origViol
         eomhost.install(WallGo.EOM)
         manager, settings = make_trace.build_manager(8, 5)
         resVec = manager.solveWall(settings)
     finally:
+        eomhost.uninstall(WallGo.EOM)
         WallGo.EOM.findPlasmaProfile = origFind
+        WallGo.EOM.violationOfEMConservation = origViol
         ref.loadCollisions = origLoad
     assert resVec.success == resRef.success
     assert abs(resVec.wallVelocity - resRef.wallVelocity) <= 1e-6 * abs(resRef.wallVelocity)
     assert np.allclose(resVec.wallWidths, resRef.wallWidths, rtol=1e-6, atol=0)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference not present on this machine")
+def test_flattened_temperature_derivative_for_point_wise_potentials():
+    """A user potential written for ONE field point at a time (the InertDoublet example: its resummed masses only
+    broadcast a scalar temperature, inertDoubletModel.py:583-585) cannot take the (stencil, points) temperature
+    array of EffectivePotential.derivT.  The vector plasma-profile solve then evaluates the same finite-difference
+    formula on flattened arrays: it must equal the reference's derivT called point by point, bit for bit, including
+    the one-sided stencils next to T = 0."""
+    sys.modules.setdefault("h5py", types.ModuleType("h5py"))
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import WallGo
+
+    class PointWisePotential(WallGo.EffectivePotential):
+        fieldCount = 1
+        effectivePotentialError = 1e-12
+
+        def evaluate(self, fields, temperature):
+            fields = WallGo.Fields(fields)
+            v = fields.getField(0)
+            T = np.asarray(temperature, dtype=float)
+            thermal = 0.1 * T ** 2 * v ** 2 - 0.3 * T ** 4 + np.log1p(T) * v
+            tree = -50.0 * v ** 2 + 0.02 * v ** 4
+            if tree.shape != thermal.shape:                      # the same "HACK" as the InertDoublet example
+                tree = tree * np.ones(thermal.shape[0])
+            return np.array(tree + thermal)
+
+    veff = PointWisePotential()
+    veff.configureDerivatives(WallGo.VeffDerivativeSettings(temperatureVariationScale=1.0, fieldValueVariationScale=[10.0]))
+    npts = 9
+    fields = WallGo.Fields(np.linspace(0.0, 60.0, npts)[:, None])
+    T = np.array([80.0, 75.0, 1e-3, 3e-3, 60.0, 55.0, 50.0, 45.0, 2e-4])      # some next to the lower bound
+    with pytest.raises(ValueError):
+        veff.derivT(fields, T)                                   # the (4, 9) temperature array does not broadcast
+
+    class FakeEOM:
+        pass
+    eom = FakeEOM()
+    eom.__class__.__module__ = "WallGo.equationOfMotion"
+    eom.thermo = types.SimpleNamespace(effectivePotential=veff)
+    eomhost._ProfileProblem._flatPotentials.discard(PointWisePotential)
+    pb = eomhost._ProfileProblem(eom, fields, np.zeros((npts, 1)), np.ones(npts), np.ones(npts))
+    got = pb._derivT(T)
+    want = np.array([float(veff.derivT(fields.getFieldPoint(i), T[i])) for i in range(npts)])
+    assert np.array_equal(got, want)
+    assert PointWisePotential in eomhost._ProfileProblem._flatPotentials     # remembered: no second failed attempt
+    lhs = pb.lhs(T)
+    assert lhs.shape == (npts,) and np.all(np.isfinite(lhs))

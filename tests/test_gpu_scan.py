@@ -104,8 +104,7 @@ def test_vectorised_profile_uses_device_feedback(cuda_device, rd, yukawa):
         try:
             vec = eom.wallPressure(0.3, wp0, boltzmannResultsInput=None)
         finally:
-            WallGo.EOM.findPlasmaProfile = WallGo.EOM._findPlasmaProfileReference
-            del WallGo.EOM._findPlasmaProfileReference
+            eomhost.uninstall(WallGo.EOM)
         assert abs(vec[0] - plain[0]) <= 1e-6 * abs(plain[0])
         assert np.allclose(vec[1].widths, plain[1].widths, rtol=1e-6)
         assert np.allclose(vec[3].temperatureProfile, plain[3].temperatureProfile, rtol=1e-7)

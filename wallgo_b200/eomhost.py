@@ -23,6 +23,8 @@ Opt-in: `wallgo_b200.dropin.install(vectoriseEOM=True)` rebinds `WallGo.EOM.find
 """
 from __future__ import annotations
 
+import sys
+
 import numpy as np
 
 
@@ -183,15 +185,48 @@ class _ProfileProblem:
     """Left-hand side of Eq. (20) of arXiv:2204.13120 on all grid points at once (the vector form of
     EOM.temperatureProfileEqLHS, equationOfMotion.py:1968-2019)."""
 
+    _flatPotentials: set = set()     # potential classes known to need the flattened temperature derivative
+
     def __init__(self, eom, fields, dPhidz, s1, s2):
         self.veff = eom.thermo.effectivePotential
+        self._flatDerivT = type(self.veff) in self._flatPotentials
+        self.helpers = sys.modules[type(eom).__module__.split(".")[0]].helpers     # WallGo.helpers of this EOM
         self.fields = fields
         self.kinetic = 0.5 * np.sum(np.asarray(dPhidz) ** 2, axis=1)
         self.s1 = np.asarray(s1, dtype=np.float64)
         self.s2 = np.asarray(s2, dtype=np.float64)
 
     def enthalpy(self, T):
-        return -T * np.asarray(self.veff.derivT(self.fields, T)).reshape(T.shape)
+        return -T * self._derivT(T)
+
+    def _derivT(self, T):
+        """dV/dT on all points.  EffectivePotential.derivT (effectivePotential.py:193-221) hands the potential a
+        (stencil, points) temperature array; user potentials written for one field point at a time cannot always
+        broadcast that against (points,) fields (InertDoublet example: inertDoubletModel.py:583-585).  For those
+        the same finite-difference formula (helpers.derivative, helpers.py:74-185: same step, stencil, one-sided
+        offsets and coefficients) is evaluated on FLATTENED (stencil*points,) arrays, which every potential that
+        works element-wise accepts."""
+        if not self._flatDerivT:
+            try:
+                return np.asarray(self.veff.derivT(self.fields, T), dtype=np.float64).reshape(T.shape)
+            except (ValueError, TypeError, IndexError):
+                self._flatDerivT = True
+                type(self)._flatPotentials.add(type(self.veff))
+        H = self.helpers
+        eps = self.veff.effectivePotentialError
+        scale = self.veff.derivativeSettings.temperatureVariationScale
+        x = np.asarray(T, dtype=np.float64)
+        dx = scale * eps ** (1.0 / 5.0)
+        dx = (x + dx) - x                                   # exactly representable steps, per point
+        offset = np.zeros(x.shape, dtype=int)
+        offset += x - dx < 0.0
+        offset += x - 2 * dx < 0.0                          # (the upper bound is +inf: no offsets on that side)
+        pos = x[None, :] + H.FIRST_DERIV_POS["4"].T[:, offset.tolist()] * dx
+        coeff = H.FIRST_DERIV_COEFF["4"].T[:, offset.tolist()] / dx
+        S = pos.shape[0]
+        fieldsRep = np.tile(np.asarray(self.fields), (S, 1)).view(type(self.fields))
+        fx = np.asarray(self.veff.evaluate(fieldsRep, pos.reshape(-1)), dtype=np.float64).reshape(S, -1)
+        return np.sum(coeff * fx, axis=0)
 
     def lhs(self, T):
         T = np.asarray(T, dtype=np.float64)
@@ -301,12 +336,46 @@ def findPlasmaProfile(eom, c1, c2, velocityMid, fields, dPhidz, offEquilDeltas, 
     return temperatureProfile, velocityProfile
 
 
+def violationOfEMConservation(eom, c1, c2, velocityMid, fields, dPhidz, offEquilDeltas, temperatureProfile,
+                              velocityProfile, wallThickness):
+    """Vector form of EOM.violationOfEMConservation (equationOfMotion.py:2145-2228) and of the violationEMPoint
+    (:2230-2293) it calls once per grid point: the residuals of the energy-momentum equations on all points at
+    once (same expressions), then the reference's own Polynomial quadrature."""
+    WallGo = sys.modules[type(eom).__module__.split(".")[0]]
+    t30, t33 = _tmunuOut(eom, fields, velocityMid, offEquilDeltas)
+    T = np.asarray(temperatureProfile, dtype=np.float64)
+    v = np.asarray(velocityProfile, dtype=np.float64)
+    pb = _ProfileProblem(eom, fields, dPhidz, np.zeros(T.shape), np.zeros(T.shape))
+    enthalpy = pb.enthalpy(T)
+    veff = np.asarray(pb.veff.evaluate(fields, T), dtype=np.float64).reshape(T.shape)
+    violationEM30 = (enthalpy * v / (1 - v**2) + t30 - c1) / c1
+    violationEM33 = (pb.kinetic - veff + enthalpy * v**2 / (1 - v**2) + t33 - c2) / c2
+    T30Poly = WallGo.Polynomial(violationEM30**2, eom.grid)
+    T33Poly = WallGo.Polynomial(violationEM33**2, eom.grid)
+    dzdchi, _, _ = eom.grid.getCompactificationDerivatives()
+    return (np.sqrt(T30Poly.integrate(weight=dzdchi)) / wallThickness,
+            np.sqrt(T33Poly.integrate(weight=dzdchi)) / wallThickness)
+
+
 def install(eomClass):
-    """Rebind `findPlasmaProfile` of the given EOM class (WallGo.EOM) to the vector form."""
+    """Rebind `findPlasmaProfile` and `violationOfEMConservation` of the given EOM class (WallGo.EOM) to their
+    vector forms."""
+    def _violationVec(self, *args):
+        if not getattr(self, "_profileVectorUnsupported", False):
+            try:
+                return violationOfEMConservation(self, *args)
+            except (ValueError, TypeError, IndexError):
+                pass
+        return eomClass._violationOfEMConservationReference(self, *args)
+    _violationVec.__doc__ = violationOfEMConservation.__doc__
+    eomClass._violationOfEMConservationReference = eomClass.violationOfEMConservation
+    eomClass.violationOfEMConservation = _violationVec
+
     def _vectorised(self, c1, c2, velocityMid, fields, dPhidz, offEquilDeltas, Tplus, Tminus):
-        # The lock-step form needs an effective potential that accepts one temperature PER field point.  Some
-        # user potentials do not (the InertDoublet example's daisy-resummed masses broadcast a scalar
-        # temperature only, inertDoubletModel.py:583-585): for those the reference's own per-point routine runs.
+        # The lock-step form needs an effective potential that accepts one temperature PER field point (element-wise
+        # (points,) arrays; potentials that cannot take the (stencil, points) array of derivT are served by the
+        # flattened derivative of _ProfileProblem._derivT).  If a user potential cannot even do that, the
+        # reference's own per-point routine runs.
         if not getattr(self, "_profileVectorUnsupported", False):
             try:
                 return findPlasmaProfile(self, c1, c2, velocityMid, fields, dPhidz, offEquilDeltas, Tplus, Tminus)
@@ -318,3 +387,13 @@ def install(eomClass):
     eomClass._findPlasmaProfileReference = eomClass.findPlasmaProfile
     eomClass.findPlasmaProfile = _vectorised
     return eomClass
+
+
+def uninstall(eomClass):
+    """Undo install(): the reference's own routines are bound again."""
+    if hasattr(eomClass, "_findPlasmaProfileReference"):
+        eomClass.findPlasmaProfile = eomClass._findPlasmaProfileReference
+        del eomClass._findPlasmaProfileReference
+    if hasattr(eomClass, "_violationOfEMConservationReference"):
+        eomClass.violationOfEMConservation = eomClass._violationOfEMConservationReference
+        del eomClass._violationOfEMConservationReference
