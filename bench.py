@@ -395,12 +395,13 @@ def run_scan(a, world, rank, local, prep=None):
             "host_workers_per_rank": int(workers), "points_per_rank": mine,
             "host_cores": os.cpu_count(), "gpus_in_node": vwscan._physicalGpus(),
             "host_budget": "workers per rank = min(12, cores // GPUs installed in the node - 1): the same host share per "
-                           "GPU at every rank count, so the scan's strong scaling is that of the GPUs (the scan is bounded "
-                           "by the reference's host loop, ~2 s of Python per point per worker, not by the device)",
+                           "GPU at every rank count, so the scan's strong scaling is that of the GPUs with their share of "
+                           "the host.  A point costs ~0.7 s of the reference's host Python per worker and ~0.15 s of GPU "
+                           "(3.7 solves): ~5 workers saturate one GPU's solve server, fewer leave the scan host-bound",
             "boltzmann_solves": solves, "solves_per_point": solves / max(1, ndone),
             "host_seconds_per_point": hostTotal / max(1, ndone),
-            "host_note": "wall time a point spends in the reference's host loop + waiting for its solves, summed "
-                         "over the host workers; the GPU time of one solve at this size is ~0.05 s",
+            "host_note": "wall time a point spends in the reference's host loop + waiting for its solves (queueing "
+                         "included), summed over the host workers; the GPU time of one solve at this size is ~0.04 s",
             "gpu_launches": launches,
             "checksum_first64": (float(np.sum(table[:head, 0])) if bool(np.all(finished[:head])) else None),
             "checksum_moments_first64": (float(np.sum(table[:head, 2 + 2 * nF:])) if bool(np.all(finished[:head])) else None),
@@ -1050,6 +1051,15 @@ def run_b200(a):
                                   "traffic": profile_traffic("assemble")[0] if (P, M, N) == (1, 40, 21) else None,
                                   "traffic_source": profile_traffic("assemble")[1], "peak_source": hbm_src,
                                   "algorithmic": "8n^2+8n bytes written per solve / mean CUDA-event time of wg_assemble"},
+            "roofline_trisolve": {"kernel": "lu_trisolve_wave_kernel (forward + backward launch)", "bound": "hbm",
+                                  "achieved": 8.0 * n * n / (unfused[2] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                  "frac": 8.0 * n * n / (unfused[2] * 1e-3) / 1e9 / hbm_peak,
+                                  "traffic": (2.0 * profile_traffic("trisolve_wave")[0]
+                                              if (P, M, N) == (1, 40, 21) and profile_traffic("trisolve_wave")[0] else None),
+                                  "traffic_source": profile_traffic("trisolve_wave")[1], "peak_source": hbm_src,
+                                  "algorithmic": "8 n^2 bytes (every factor entry read once over the two launches) / "
+                                                 "CUDA-event time of wg_solve, one system alone; traffic = 2 x the "
+                                                 "per-launch dram bytes of the ncu summary"},
             "e2e": {"value": e2e, "unit": "solves/s", "h2d_bytes_per_step": int(nprof * 8),
                     "d2h_bytes_per_step": int((eng.nspec + eng.nout) * 8 + 4)},
             "gpu_launches": int(launches), "clocks": clocks,
