@@ -622,7 +622,6 @@ class BoltzmannSolverB200Mixin:
                                                   dh[slot].reshape(4, P, M1).copy(), eh[slot].reshape(P, 4).copy(),
                                                   keep, peaks)
 
-        self.setBackground(backgrounds[-1])     # what a sequential loop would leave behind
         nC = len(chunks)
         for c in range(nC + 2):
             if c >= 2:
@@ -631,6 +630,7 @@ class BoltzmannSolverB200Mixin:
                 start(c)
             if 1 <= c <= nC:
                 decide(c - 1)
+        self.setBackground(backgrounds[-1])     # what a sequential loop would leave behind
         return results
 
     def _wrapResults(self, dF, deltas, err, keep, peaks):
