@@ -601,3 +601,28 @@ def test_assemble_rows_equals_full_assembly(cuda_device, P, M, N, G):
     h = C.c_void_p(eng.h.value)
     assert eng.lib.wg_assemble_rows(h, eng.prof.data_ptr(), vw, 1.0, 3, groups, 1, panel.data_ptr(), n,
                                     eng.S.data_ptr(), eng._stream()) == -1
+
+
+def test_strided_batches_survive_an_engine_change(cuda_device):
+    """Batch contexts borrow the solver's engine handle: when the engine is rebuilt (another species count) they
+    are released first, and the next batch builds new ones; empty input returns an empty list."""
+    import gc
+    import wallgo_b200 as wb
+    from wallgo_b200 import synthetic
+
+    M, N = 10, 7
+    grid = synthetic.makeGrid(M, N)
+    solver = wb.BoltzmannSolver(grid)
+    assert solver.getDeltasStrided([]) == []
+    for P in (1, 3, 2):
+        parts = synthetic.makeParticles(P)
+        solver.updateParticleList(parts)
+        solver.setCollisionArray(synthetic.makeCollision(grid, parts))
+        bgs = [synthetic.makeBackground(grid, velocityMid=-0.3 - 0.05 * i) for i in range(5)]
+        out = solver.getDeltasStrided(bgs, batch=4)
+        solver.setBackground(bgs[2])
+        one = solver.getDeltas()
+        assert np.array_equal(out[2].deltaF, one.deltaF)
+        assert out[2].deltaF.shape == (P, M - 1, N - 1, N - 1)
+    del solver
+    gc.collect()

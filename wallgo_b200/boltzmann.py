@@ -219,6 +219,11 @@ class BoltzmannSolverB200Mixin:
         g = self.grid
         if self._engine is None or (self._engine.P, self._engine.M, self._engine.N) != (P, g.M, g.N):
             if self._engine is not None:
+                cur = getattr(self, "_batchEng", None)
+                if cur is not None:                 # batch contexts borrow the engine's handle: they go first
+                    for b in cur[2]:
+                        b.close()
+                    self._batchEng = None
                 self._engine.close()
             self._engine = BoltzmannEngine(P, g.M, g.N, self.device)
             self._staticKey = None

@@ -87,6 +87,7 @@ struct wg_solver {
 // (the system index is a grid dimension): shares the solver's static tables, owns the per-system scratch.
 struct wg_batch {
   wg_solver* s = nullptr;
+  int device = 0;      // (kept here too: wg_batch_destroy must not look into a solver that may already be gone)
   int count = 0;
   std::vector<void*> allocs;
   double *derivs = nullptr, *w1 = nullptr, *w2 = nullptr, *cT2 = nullptr;
@@ -614,6 +615,7 @@ int wg_batch_create(wg_solver* s, int count, wg_batch** out) {
   WG_ON_DEVICE(s->device);
   wg_batch* b = new wg_batch();
   b->s = s;
+  b->device = s->device;
   b->count = count;
   const wg::BzDims& d = s->d;
   const size_t B = (size_t)count, n = d.n;
@@ -649,7 +651,7 @@ int wg_batch_create(wg_solver* s, int count, wg_batch** out) {
 
 int wg_batch_destroy(wg_batch* b) {
   if (!b) return WG_OK;
-  WG_ON_DEVICE(b->s->device);
+  WG_ON_DEVICE(b->device);
   for (void* p : b->allocs) cudaFree(p);
   wg::lu_plan_destroy(b->plan);
   delete b;
