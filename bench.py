@@ -394,7 +394,7 @@ def run_scan(a, world, rank, local, prep=None):
                      "solves on the GPU via wallgo_b200.dropin (vectoriseEOM); one all_gather of the result rows",
             "host_workers_per_rank": int(workers), "points_per_rank": mine,
             "host_cores": os.cpu_count(), "gpus_in_node": vwscan._physicalGpus(),
-            "host_budget": "workers per rank = min(12, cores // GPUs installed in the node - 1): the same host share per "
+            "host_budget": "workers per rank = min(12, share - 1 if share >= 6 else share), share = cores // GPUs installed in the node: the same host share per "
                            "GPU at every rank count, so the scan's strong scaling is that of the GPUs with their share of "
                            "the host.  A point costs ~0.7 s of the reference's host Python per worker and ~0.15 s of GPU "
                            "(3.7 solves): ~5 workers saturate one GPU's solve server, fewer leave the scan host-bound",

@@ -209,12 +209,15 @@ def defaultWorkers(worldSize: int = 1) -> int:
     """Host processes per rank.  The node's cores are divided evenly among the GPUs INSTALLED in it, so the host
     budget of one GPU is the same whether a run uses one rank or all of them (a scan is bounded by the host loop
     of the reference, ~2 s of Python per point, long before the GPU: the scaling a run reports is then that of the
-    GPUs with their share of the host, not that of idle cores); one core stays with the rank process; at most 12
+    GPUs with their share of the host, not that of idle cores); one core stays with the rank process when the share is at least six cores; at most 12
     (the solve server of one GPU keeps up with ~25 workers: ~0.05 s of GPU per solve against ~0.5 s of host Python
     per solve per worker)."""
     gpus = _physicalGpus()
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    return max(1, min(12, cores // max(gpus, worldSize) - 1))
+    share = cores // max(gpus, worldSize)
+    # the rank process (solve server) sleeps in select() most of the time: with a small share it does not get a core
+    # of its own (an 8-GPU node with 32 cores: 4 workers per rank, not 3)
+    return max(1, min(12, share - 1 if share >= 6 else share))
 
 
 def _serverWallSolver(manager, settings):
