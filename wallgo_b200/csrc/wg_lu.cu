@@ -1131,11 +1131,12 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
 // adds is of the order cond(block) * eps and is removed, with the LU's own cond(A) * eps, by the refinement step
 // that follows every solve (wg_refine).  dinv: [system][block][triangle (0 = L, 1 = U)][128][128], rows and columns
 // beyond a short last block are those of the identity.
-__global__ void __launch_bounds__(256) lu_diag_invert_kernel(const double* __restrict__ LU, long long lda, int n,
+__global__ void __launch_bounds__(512) lu_diag_invert_kernel(const double* __restrict__ LU, long long lda, int n,
                                                              double* __restrict__ dinv, long long sA, long long sD) {
   // One CTA per diagonal block, both triangles at once and in place in shared memory (LAPACK dtrti2 order):
-  // threads 0..127 own the rows of L^-1 (columns right to left), threads 128..255 the rows of U^-1 (columns left
-  // to right).  In step s a thread reads only its own row and the original column, which is parked in `col`.
+  // threads 0..255 own the rows of L^-1 (columns right to left), threads 256..511 the rows of U^-1 (columns left
+  // to right), TWO threads per row (even / odd terms of the row's dot product, combined with one shuffle).  In
+  // step s a thread pair reads only its own row and the original column, which is parked in `col`.
   extern __shared__ __align__(16) unsigned char smraw[];
   double* T = reinterpret_cast<double*>(smraw);   // [TS_BS][TS_LD]
   double* col = T + TS_BS * TS_LD;                // [2 parities][2 triangles][TS_BS]
@@ -1145,64 +1146,43 @@ __global__ void __launch_bounds__(256) lu_diag_invert_kernel(const double* __res
   const int kb = blk * TS_BS;
   const int bs = min(TS_BS, n - kb);
   const int tid = threadIdx.x;
-  for (int e = tid; e < TS_BS * TS_BS; e += 256) {
+  for (int e = tid; e < TS_BS * TS_BS; e += 512) {
     const int r = e >> 7, c = e & (TS_BS - 1);
     T[r * TS_LD + c] = (r < bs && c < bs) ? LU[(long long)(kb + r) * lda + kb + c] : (r == c ? 1.0 : 0.0);
   }
   __syncthreads();
-  const bool up = tid >= TS_BS;
-  const int i = tid & (TS_BS - 1);
+  const bool up = tid >= 2 * TS_BS;
+  const int i = (tid & (2 * TS_BS - 1)) >> 1, half = tid & 1;
   double* row = T + i * TS_LD;
-  if (up) row[i] = 1.0 / row[i];      // X_ii of the upper triangle (own row, read by nobody else before the barrier)
+  if (up && half == 0) row[i] = 1.0 / row[i];      // X_ii of the upper triangle (own row, read by nobody else before the barrier)
   __syncthreads();
   for (int s = 0; s < TS_BS - 1; ++s) {
     double* cl = col + (s & 1) * 2 * TS_BS + (up ? TS_BS : 0);
     const int j = up ? 1 + s : TS_BS - 2 - s;
-    if (up ? (i < j) : (i > j)) cl[i] = row[j];
+    const bool act = up ? (i < j) : (i > j);
+    if (act && half == 0) cl[i] = row[j];
     __syncthreads();
-    if (!up) {
-      if (i > j) {   // x_i = -( l_i + sum_{j < c < i} X[i][c] l_c )
-        double a0 = cl[i], a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int c = j + 1;
-        for (; c + 7 < i; c += 8) {      // loads of eight terms in flight, four FMA chains
-          const double r0 = row[c], r1 = row[c + 1], r2 = row[c + 2], r3 = row[c + 3];
-          const double r4 = row[c + 4], r5 = row[c + 5], r6 = row[c + 6], r7 = row[c + 7];
-          a0 = fma(r0, cl[c], a0);
-          a1 = fma(r1, cl[c + 1], a1);
-          a2 = fma(r2, cl[c + 2], a2);
-          a3 = fma(r3, cl[c + 3], a3);
-          a0 = fma(r4, cl[c + 4], a0);
-          a1 = fma(r5, cl[c + 5], a1);
-          a2 = fma(r6, cl[c + 6], a2);
-          a3 = fma(r7, cl[c + 7], a3);
-        }
-        for (; c < i; ++c) a0 = fma(row[c], cl[c], a0);
-        row[j] = -((a0 + a1) + (a2 + a3));
+    // lower: x_i = -( l_i + sum_{j < c < i} X[i][c] l_c );  upper: x_i = -( sum_{i <= c < j} X[i][c] u_c ) * X_jj
+    const int c0 = up ? i : j + 1, c1 = up ? j : i;      // terms c0 <= c < c1, this thread takes c0 + half, + 2, ...
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (act) {
+      int c = c0 + half;
+      for (; c + 6 < c1; c += 8) {      // four terms of this thread in flight
+        const double r0 = row[c], r1 = row[c + 2], r2 = row[c + 4], r3 = row[c + 6];
+        a0 = fma(r0, cl[c], a0);
+        a1 = fma(r1, cl[c + 2], a1);
+        a2 = fma(r2, cl[c + 4], a2);
+        a3 = fma(r3, cl[c + 6], a3);
       }
-    } else {
-      if (i < j) {   // x_i = -( sum_{i <= c < j} X[i][c] u_c ) * X_jj
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int c = i;
-        for (; c + 7 < j; c += 8) {
-          const double r0 = row[c], r1 = row[c + 1], r2 = row[c + 2], r3 = row[c + 3];
-          const double r4 = row[c + 4], r5 = row[c + 5], r6 = row[c + 6], r7 = row[c + 7];
-          a0 = fma(r0, cl[c], a0);
-          a1 = fma(r1, cl[c + 1], a1);
-          a2 = fma(r2, cl[c + 2], a2);
-          a3 = fma(r3, cl[c + 3], a3);
-          a0 = fma(r4, cl[c + 4], a0);
-          a1 = fma(r5, cl[c + 5], a1);
-          a2 = fma(r6, cl[c + 6], a2);
-          a3 = fma(r7, cl[c + 7], a3);
-        }
-        for (; c < j; ++c) a0 = fma(row[c], cl[c], a0);
-        row[j] = -((a0 + a1) + (a2 + a3)) * T[j * TS_LD + j];
-      }
+      for (; c < c1; c += 2) a0 = fma(row[c], cl[c], a0);
     }
+    double sum = (a0 + a1) + (a2 + a3);
+    sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+    if (act && half == 0) row[j] = up ? -sum * T[j * TS_LD + j] : -(cl[i] + sum);
     // (the other parity of `col` is written next; this one is not touched again before the barrier after that)
   }
   __syncthreads();
-  for (int e = tid; e < TS_BS * TS_BS; e += 256) {
+  for (int e = tid; e < TS_BS * TS_BS; e += 512) {
     const int r = e >> 7, c = e & (TS_BS - 1);
     const double v = T[r * TS_LD + c];
     out[e] = c < r ? v : (c == r ? 1.0 : 0.0);
@@ -1946,7 +1926,7 @@ static int factor_enqueue(LuPlan* p, double* A, long long lda, int* ipiv, int* i
     const size_t smemInv = (size_t)(TS_BS * TS_LD + 4 * TS_BS) * sizeof(double);
     if (wg_func_configured(reinterpret_cast<const void*>(lu_diag_invert_kernel), smemInv) < (long long)smemInv)
       WG_CUDA(cudaFuncSetAttribute(lu_diag_invert_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemInv));
-    lu_diag_invert_kernel<<<dim3(wg_cdiv(n, TS_BS), bt.count), 256, smemInv, st>>>(A, lda, n, p->dinv, bt.sA, p->sDinv);
+    lu_diag_invert_kernel<<<dim3(wg_cdiv(n, TS_BS), bt.count), 512, smemInv, st>>>(A, lda, n, p->dinv, bt.sA, p->sDinv);
     WG_LAUNCH_CHECK();
   }
   return WG_OK;
