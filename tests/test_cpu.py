@@ -427,3 +427,24 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
     assert lib.wg_lu_create_batched(8, 0, 0, C.byref(out)) == -1
     assert lib.wg_lu_factor_batched(null, None, 8, 64, None, None, None) == -1
     assert lib.wg_lu_solve_batched(null, None, 8, 64, None, 8, None) == -1
+
+
+def test_bench_workloads_and_profile_traffic():
+    """bench.py: the workloads are BASELINE.json's configs, and the roofline `traffic` figures come out of the
+    committed ncu summaries under profiles/ (not literals): the parser must find them."""
+    import sys
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import bench
+
+    assert bench.WORKLOADS["cfg1"] == (1, 20, 11) and bench.WORKLOADS["cfg2a"] == (1, 40, 21)
+    assert bench.WORKLOADS["cfg3"] == (3, 30, 11) and bench.WORKLOADS["cfg4"] == (4, 30, 11)
+    assert bench.WORKLOADS["cfg5fit"] == (4, 32, 31) and bench.WORKLOADS["cfg5stream"] == (4, 64, 31)
+    n = 15600
+    gemm, src = bench.profile_traffic("dgemm_128x64_2cta")
+    assert src and 3.8e9 < gemm < 5.0e9                     # 3.83e9 algorithmic at the first trailing shape
+    asm, src = bench.profile_traffic("assemble")
+    assert src and 0.98 * 8 * n * n < asm < 1.05 * 8 * n * n
+    tri, src = bench.profile_traffic("trisolve_wave")
+    assert src and 0.98 * 4 * n * n < tri < 1.05 * 4 * n * n  # one direction reads half the factors once
+    assert bench.profile_traffic("no_such_kernel") == (None, None)
