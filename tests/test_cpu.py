@@ -448,3 +448,21 @@ def test_bench_workloads_and_profile_traffic():
     tri, src = bench.profile_traffic("trisolve_wave")
     assert src and 0.98 * 4 * n * n < tri < 1.05 * 4 * n * n  # one direction reads half the factors once
     assert bench.profile_traffic("no_such_kernel") == (None, None)
+
+
+def test_scan_row_packing_round_trip():
+    """vwscan rows: [pressure | widths | offsets | solves | Delta00,02,20,11]; unpackRow inverts the packing."""
+    from wallgo_b200 import vwscan
+
+    nF, P, M = 2, 3, 6
+    width = vwscan.rowWidth(nF, P, M)
+    assert width == 2 + 2 * nF + 4 * P * (M - 1)
+    rng = np.random.default_rng(0)
+    row = rng.standard_normal(width)
+    d = vwscan.unpackRow(row, nF, P, M)
+    assert d["pressure"] == row[0] and np.array_equal(d["widths"], row[1:3]) and np.array_equal(d["offsets"], row[3:5])
+    assert d["solves"] == row[5] and d["Deltas"].shape == (4, P, M - 1)
+    assert np.array_equal(d["Deltas"].ravel(), row[6:])
+    with pytest.raises(AssertionError):
+        vwscan.unpackRow(row[:-1], nF, P, M)
+    assert 1 <= vwscan.defaultWorkers(1) <= 12 and 1 <= vwscan.defaultWorkers(8) <= 12
