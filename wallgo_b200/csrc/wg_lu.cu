@@ -1225,9 +1225,12 @@ __global__ void __launch_bounds__(256, 1) lu_trisolve_wave_kernel(const double* 
       for (int e = tid; e < TS_BS * TS_BS; e += 256) cp_async8(&T[(e >> 7) * TS_LD + (e & (TS_BS - 1))], src + e, true);
       cp_async_commit();
     }
-    double acc[RPW];
+    double acc[RPW], part[RPW];
 #pragma unroll
-    for (int rr = 0; rr < RPW; ++rr) acc[rr] = b[kb + min(warp * RPW + rr, bs - 1)];
+    for (int rr = 0; rr < RPW; ++rr) {
+      acc[rr] = b[kb + min(warp * RPW + rr, bs - 1)];
+      part[rr] = 0.0;
+    }
     if (ablate & 2) seen = INT_MAX;
     for (int k = 0; k < ((ablate & 8) ? 0 : q); ++k) {          // earlier blocks in solve order
       const int pblk = UPPER ? nblk - 1 - k : k;
@@ -1264,15 +1267,16 @@ __global__ void __launch_bounds__(256, 1) lu_trisolve_wave_kernel(const double* 
       double xv[CPL];
 #pragma unroll
       for (int u = 0; u < CPL; ++u) xv[u] = (lane + 32 * u < bsp) ? __ldcg(b + kp + lane + 32 * u) : 0.0;
+      // per-lane partial sums over ALL tiles of the row: the cross-lane reduction happens once per block, not per tile
 #pragma unroll
       for (int rr = 0; rr < RPW; ++rr) {
-        double sacc = 0.0;
 #pragma unroll
         for (int u = 0; u < CPL; ++u)
-          if (lane + 32 * u < bsp) sacc = fma(v[rr][u], xv[u], sacc);
-        acc[rr] -= warp_sum(sacc);
+          if (lane + 32 * u < bsp) part[rr] = fma(v[rr][u], xv[u], part[rr]);
       }
     }
+#pragma unroll
+    for (int rr = 0; rr < RPW; ++rr) acc[rr] -= warp_sum(part[rr]);
     if (lane == 0) {
 #pragma unroll
       for (int rr = 0; rr < RPW; ++rr)
