@@ -687,3 +687,25 @@ def test_trisolve_wavefront_many_right_hand_sides(env):
                     assert np.array_equal(x0, x)
     finally:
         lib.wg_lu_destroy(plan)
+
+
+def test_solve_before_factor_is_a_state_error(env):
+    """The triangular solves need the diagonal-block inverses a factorisation of the same plan leaves behind:
+    solving first is reported (WG_ERR_STATE), not computed from uninitialised memory."""
+    torch, lib, _lib = env
+    n = 64
+    A = torch.eye(n, dtype=torch.float64, device="cuda")
+    b = torch.ones(n, dtype=torch.float64, device="cuda")
+    plan = C.c_void_p()
+    _lib.check(lib.wg_lu_create(n, 0, C.byref(plan)), "wg_lu_create")
+    try:
+        assert lib.wg_lu_solve(plan, A.data_ptr(), n, b.data_ptr(), _stream(torch)) == -3
+        assert b"no factorisation" in lib.wg_last_error()
+        ipiv = torch.zeros(n, dtype=torch.int32, device="cuda")
+        info = torch.zeros(1, dtype=torch.int32, device="cuda")
+        _lib.check(lib.wg_lu_factor(plan, A.data_ptr(), n, ipiv.data_ptr(), info.data_ptr(), _stream(torch)), "factor")
+        _lib.check(lib.wg_lu_solve(plan, A.data_ptr(), n, b.data_ptr(), _stream(torch)), "solve")
+        torch.cuda.synchronize()
+        assert torch.equal(b, torch.ones(n, dtype=torch.float64, device="cuda"))
+    finally:
+        lib.wg_lu_destroy(plan)

@@ -1323,6 +1323,7 @@ struct LuPlan {
   int *permSrcTop = nullptr, *permBDst = nullptr, *permBSrc = nullptr, *permNBot = nullptr;
   int* posContent = nullptr;
   int* solveSync = nullptr;                // [batch][4] ticket / published counters of the wavefront solves
+  bool haveInv = false;                    // a factorisation of this plan has filled dinv
   double* dinv = nullptr;                  // [batch][nblk][2][128][128] inverses of the diagonal blocks of L and U
   long long sDinv = 0;                     // doubles per system in dinv
   int numSMs = 148;
@@ -1941,6 +1942,7 @@ int lu_factor(LuPlan* p, double* A, long long lda, int* ipiv, int* info, cudaStr
   WG_REQUIRE(p && A && ipiv && info && lda >= p->n, "lu_factor: bad arguments");
   WG_REQUIRE(p->batch == 1 || strideA >= (long long)p->n * lda, "lu_factor: batch stride smaller than one operator");
   p->rhs = rhs;   // non-null: the forward solve L y = P rhs rides along (finish with lu_solve(..., backwardOnly))
+  p->haveInv = true;
   lu_sync_tuning(p);
   p->bt.sA = p->batch > 1 ? strideA : 0;
   p->bt.sV = (p->batch > 1 && rhs) ? strideRhs : 0;
@@ -1987,6 +1989,10 @@ static int solve_enqueue(LuPlan* p, const double* LU, long long lda, double* b, 
 int lu_solve(LuPlan* p, const double* LU, long long lda, double* b, cudaStream_t st, bool backwardOnly,
              long long strideA, long long strideB) {
   WG_REQUIRE(p && LU && b && lda >= p->n, "lu_solve: bad arguments");
+  if (!p->haveInv) {   // the wavefront solves use the diagonal-block inverses the factorisation of THIS plan leaves behind
+    wg_set_error("lu_solve: no factorisation has been enqueued on this plan yet");
+    return WG_ERR_STATE;
+  }
   lu_sync_tuning(p);
   p->bt.sA = p->batch > 1 ? strideA : 0;
   p->bt.sV = p->batch > 1 ? strideB : 0;
