@@ -407,7 +407,10 @@ def run_scan(a, world, rank, local, prep=None):
             "checksum_moments_first64": (float(np.sum(table[:head, 2 + 2 * nF:])) if bool(np.all(finished[:head])) else None),
             "checksum_note": "sum of the pressures / of all moments of scan points 0..63: equal for every GPU and "
                              "worker count (each point starts from the same guess; the device path is batch-invariant)",
-            "pressure_first": float(table[0, 0])}
+            "pressure_first": float(table[0, 0]),
+            "pressure_last": (float(table[-1, 0]) if bool(finished[-1]) else None),
+            "pressure_note": "compare with `pressures` of the reference arm's scan block (points 0 and 255): the "
+                             "1e-6 gate of the north star applies"}
 
 
 def run_scan_boltzmann_only(a, world, rank, local):
