@@ -466,3 +466,25 @@ def test_scan_row_packing_round_trip():
     with pytest.raises(AssertionError):
         vwscan.unpackRow(row[:-1], nF, P, M)
     assert 1 <= vwscan.defaultWorkers(1) <= 12 and 1 <= vwscan.defaultWorkers(8) <= 12
+
+
+def test_extended_precision_yardstick():
+    """oracle.solve_extended (the yardstick of the refinement tests and of tools/parity_fuzz.py): on integer systems
+    whose exact solution is known (A, x integer, b = A x exact in FP64) it is exact to the last bits while LAPACK's
+    own solve carries cond * eps."""
+    from oracle import boltzmann_oracle as bo
+
+    worstLap = 0.0
+    for seed in range(4):
+        rng = np.random.default_rng(seed)
+        n = 150
+        A = rng.integers(-3, 4, size=(n, n)).astype(float)
+        A[:, 0] = A[:, 1] + rng.integers(-1, 2, size=n) * (rng.random(n) < 0.08)      # two nearly dependent columns
+        xExact = rng.integers(-50, 51, size=n).astype(float)
+        b = A @ xExact                                           # exact: small integers
+        if np.linalg.matrix_rank(A) < n:
+            continue
+        xExt, xLap = bo.solve_extended(A, b)
+        assert relmax(xExt, xExact) < 5e-16, (seed, relmax(xExt, xExact))
+        worstLap = max(worstLap, relmax(xLap, xExact))
+    assert worstLap > 1e-15          # the plain FP64 solve is measurably off on at least one of them
