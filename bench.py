@@ -357,7 +357,8 @@ def run_scan(a, world, rank, local, prep=None):
         manager, settings, vws, setup = prep["manager"], prep["settings"], prep["vws"], prep["setup_s"]
         workers = len(prep["hostWorkers"]) if prep["hostWorkers"] is not None else 0
         # warm-up: engines, buffers and CUDA graphs of every slot (in-process, one point + one batch)
-        vwscan.warmUp(manager, settings, float(vws[rank % len(vws)]))
+        reuse = bool(a.scan_reuse)
+        vwscan.warmUp(manager, settings, float(vws[rank % len(vws)]), workers=workers, reuseFactors=reuse)
         lib = _lib.load()
         if world > 1:
             dist.barrier()
@@ -366,7 +367,8 @@ def run_scan(a, world, rank, local, prep=None):
         stats = {}
         t0 = time.perf_counter()
         table = vwscan.scanWallPressure(manager, settings, vws, workers=workers, stats=stats,
-                                        budgetSeconds=a.scan_budget_s, hostWorkers=prep["hostWorkers"])
+                                        budgetSeconds=a.scan_budget_s, hostWorkers=prep["hostWorkers"],
+                                        reuseFactors=reuse)
         torch.cuda.synchronize()
         el = time.perf_counter() - t0
         launches = lib.wg_launch_count() - l0
@@ -403,6 +405,12 @@ def run_scan(a, world, rank, local, prep=None):
             "host_note": "wall time a point spends in the reference's host loop + waiting for its solves (queueing "
                          "included), summed over the host workers; the GPU time of one solve at this size is ~0.04 s",
             "gpu_launches": launches,
+            "factor_reuse": dict(stats.get("reuse", {"enabled": False}),
+                                 note="rank 0's server: from the third Boltzmann solve of a point on, the solution is "
+                                      "reached by refinement steps (double-double residual of the regenerated operator) "
+                                      "preconditioned with the LU factors of the point's last factorisation; `fresh` "
+                                      "factorisations, `stale` solves that converged that way in `steps` refinement "
+                                      "steps, `fallbacks` to a fresh factorisation (counted in `fresh` too)"),
             "checksum_first64": (float(np.sum(table[:head, 0])) if bool(np.all(finished[:head])) else None),
             "checksum_moments_first64": (float(np.sum(table[:head, 2 + 2 * nF:])) if bool(np.all(finished[:head])) else None),
             "checksum_note": "sum of the pressures / of all moments of scan points 0..63: equal for every GPU and "
@@ -1156,6 +1164,8 @@ def main():
     ap.add_argument("--scan-workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--scan-model", default="idm", choices=sorted(SCAN_MODELS))
     ap.add_argument("--scan-workers", type=int, default=-1, help="host processes per rank for the scan (-1: auto, 0: in-process)")
+    ap.add_argument("--scan-reuse", type=int, default=1,
+                    help="scan server re-uses LU factors across the solves of a point (stale-factor refinement); 0: off")
     ap.add_argument("--scan-budget-s", type=float, default=200.0,
                     help="stop handing out scan points after this many seconds (the rate is reported over the points done)")
     ap.add_argument("--ref-scan-points", type=int, default=2, help="scan points the reference arm times (0: skip)")

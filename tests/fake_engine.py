@@ -30,6 +30,9 @@ class _NP:
     def __mul__(self, other):
         return _NP(self.arr * (other.arr if isinstance(other, _NP) else other))
 
+    def __getitem__(self, idx):
+        return _NP(self.arr[idx])
+
 
 class _FakeStream:
     cuda_stream = 0
@@ -200,14 +203,37 @@ class FakeEngine:
         return self.A
 
     def factor(self):
-        pass
+        import scipy.linalg as sla
+        self._lu = sla.lu_factor(self.A.arr)     # kept until the next factor(), like the device factors
 
     def solve(self, b=None):
+        import scipy.linalg as sla
         b = self.S if b is None else b
-        b.arr[...] = np.linalg.solve(self.A.arr, b.arr)
+        b.arr[...] = sla.lu_solve(self._lu, b.arr)
         return b
 
+    MAX_REUSE_STEPS = 64
+
+    def refine_steps(self, vw, collisionMultiplier, first, count):
+        """Richardson steps of self.S towards the solution of the CURRENT profiles' system with the factors of
+        the last factor() (BoltzmannEngine.refine_steps)."""
+        import scipy.linalg as sla
+        if getattr(self, "rstats", None) is None:
+            self.rstats = _NP(np.zeros((self.MAX_REUSE_STEPS, 2)))
+            self.rstats_host = self.rstats
+        op, src = bo.assemble(self._problem(vw, collisionMultiplier))
+        for i in range(first, first + count):
+            c = sla.lu_solve(self._lu, src - op @ self.S.arr)
+            self.S.arr += c
+            self.rstats.arr[i] = (np.max(np.abs(c)), np.max(np.abs(self.S.arr)))
+        self.refine_calls = getattr(self, "refine_calls", 0) + count
+
+    @property
+    def nout(self):
+        return self.n + 4 * self.P * self.M1 + 4 * self.P + 2
+
     def factor_solve(self, b=None):
+        self.factor()
         return self.solve(b)
 
     last_refinement = (0.0, 1.0)

@@ -325,9 +325,9 @@ def test_auto_concurrency_policy():
     import wallgo_b200 as wb
 
     ac = wb.BoltzmannSolver.autoConcurrency
-    assert ac(15600) == 3 and ac(11600) == 4 and ac(8700) == 4 and ac(3800) == 8 and ac(1900) == 32
+    assert ac(15600) == 4 and ac(11600) == 8 and ac(8700) == 8 and ac(3800) == 8 and ac(1900) == 32
     assert ac(31200, freeBytes=20 * 2**30) == 1          # one 7.8 GB operator + workspace in 60 % of 20 GB
-    assert ac(15600, freeBytes=170 * 2**30) == 3
+    assert ac(15600, freeBytes=170 * 2**30) == 4
     assert ac(1900, freeBytes=2**30) >= 1
 
 

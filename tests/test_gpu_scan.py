@@ -39,11 +39,22 @@ def test_scan_workers_equal_sequential_and_reference(cuda_device, rd, yukawa):
     origNew = rd.patch_load_collisions(cls)
     origRef = rd.patch_load_collisions(refCls)
     try:
-        st0, st1 = {}, {}
+        st0, st1, st2, st3 = {}, {}, {}, {}
         seq = vwscan.scanLocal(manager, settings, vws, range(len(vws)), workers=0, stats=st0)
-        par = vwscan.scanLocal(manager, settings, vws, range(len(vws)), workers=3, concurrency=2, stats=st1)
+        par = vwscan.scanLocal(manager, settings, vws, range(len(vws)), workers=3, concurrency=2, stats=st1,
+                               reuseFactors=False)
         assert st0["solves"] == st1["solves"] > 2 * len(vws)
         assert np.array_equal(seq, par), "solve server + host workers must reproduce the sequential loop bit for bit"
+        # factor re-use (the scan's default): from the third solve of a point on, refinement steps on the point's
+        # last factors.  Same table for any number of workers; the plain table to solver accuracy.
+        re3 = vwscan.scanLocal(manager, settings, vws, range(len(vws)), workers=3, stats=st2, reuseFactors=True)
+        re1 = vwscan.scanLocal(manager, settings, vws, range(len(vws)), workers=1, stats=st3, reuseFactors=True)
+        assert np.array_equal(re3, re1)
+        r = st2["reuse"]
+        assert r["enabled"] and r["slots"] == 3 and r["stale"] > 0, r
+        assert r["fresh"] + r["stale"] == st2["solves"] == st0["solves"]
+        assert np.allclose(re3[:, 0], seq[:, 0], rtol=1e-8, atol=0)
+        assert np.max(np.abs(re3[:, 4:] - seq[:, 4:])) <= 1e-8 * np.max(np.abs(seq[:, 4:]))
         # the reference itself on three of the points
         mgr.BoltzmannSolver = refCls
         ws = manager.setupWallSolver(settings)
@@ -114,3 +125,63 @@ def test_vectorised_profile_uses_device_feedback(cuda_device, rd, yukawa):
             del cls.loadCollisions
         else:
             cls.loadCollisions = origNew
+
+
+def _raw_of(solver, bg):
+    solver.setBackground(bg)
+    b = solver.background
+    dxidchi, _, _ = solver.grid.getCompactificationDerivatives()
+    return (np.array(b.temperatureProfile, float), np.array(b.velocityProfile, float), solver._msq(b.fieldProfiles),
+            np.array(dxidchi, float), float(b.velocityWall))
+
+
+def _run_sequence(pool, raws, slot=None, seqs=None):
+    out = {}
+    for k, raw in enumerate(raws):
+        assert pool.submit(k, raw=raw, slot=slot, seq=None if seqs is None else seqs[k])
+        while pool.busy():
+            for token, res in pool.poll():
+                out[token] = res
+    return [out[k] for k in range(len(raws))]
+
+
+@pytest.mark.parametrize("P,M,N", [(2, 16, 9), (1, 30, 11)])
+def test_slot_pool_factor_reuse_on_the_device(cuda_device, P, M, N):
+    """slotPool(reuseFactors=True) on the CUDA engine (twin of tests/test_reuse_cpu.py): a sequence of nearby
+    systems converges on the stale factors to the fresh LU + refinement answer (1e-12), positions 0 and 1 are the
+    fresh path bit for bit, a far system falls back to a factorisation, and the run is reproducible."""
+    import wallgo_b200 as wb
+    from wallgo_b200 import synthetic
+
+    grid = synthetic.makeGrid(M, N)
+    parts = synthetic.makeParticles(P)
+    s = wb.BoltzmannSolver(grid, device=cuda_device)
+    s.updateParticleList(parts)
+    s.setCollisionArray(synthetic.makeCollision(grid, parts, r=0.05))
+    raws = [_raw_of(s, synthetic.makeBackground(grid, velocityMid=-0.5, wallL=w))
+            for w in (0.05, 0.0505, 0.0508, 0.0509, 0.05095)]
+    fresh = _run_sequence(s.slotPool(1), raws)
+    pool = s.slotPool(2, reuseFactors=True)
+    got = _run_sequence(pool, raws, slot=1, seqs=range(5))
+    st = dict(pool.reuseStats)
+    assert st["fresh"] == 2 and st["stale"] == 3 and st["fallbacks"] == 0, st
+    for g, f in zip(got, fresh):
+        assert np.max(np.abs(g.deltaF - f.deltaF)) <= 1e-12 * np.max(np.abs(f.deltaF))
+        for name in ("Delta00", "Delta02", "Delta20", "Delta11"):
+            a, b = getattr(g.Deltas, name).coefficients, getattr(f.Deltas, name).coefficients
+            assert np.max(np.abs(a - b)) <= 1e-11 * np.max(np.abs(b))
+        assert tuple(g.truncatedTail) == tuple(f.truncatedTail) and tuple(g.spectralPeaks) == tuple(f.spectralPeaks)
+    assert np.array_equal(got[0].deltaF, fresh[0].deltaF) and np.array_equal(got[1].deltaF, fresh[1].deltaF)
+    again = _run_sequence(s.slotPool(2, reuseFactors=True), raws, slot=0, seqs=range(5))
+    assert all(np.array_equal(a.deltaF, g.deltaF) for a, g in zip(again, got)), "re-use must be reproducible"
+    # a far member (temperature doubled: the collision term grows fourfold) falls back to the fresh path
+    far = list(raws[:4])
+    for k in (2, 3):
+        far[k] = (2.0 * far[k][0],) + far[k][1:]
+    fresh = _run_sequence(s.slotPool(1), far)
+    pool = s.slotPool(1, reuseFactors=True)
+    got = _run_sequence(pool, far, slot=0, seqs=range(4))
+    st = dict(pool.reuseStats)
+    assert st["fallbacks"] == 1 and st["fresh"] == 3 and st["stale"] == 1, st
+    assert np.array_equal(got[2].deltaF, fresh[2].deltaF)
+    assert np.max(np.abs(got[3].deltaF - fresh[3].deltaF)) <= 1e-12 * np.max(np.abs(fresh[3].deltaF))

@@ -36,10 +36,40 @@ class _Keep(list):
         self.dev = list(sizes)
 
 
-class _SlotPool:
-    """Slots of independent systems in flight on one GPU (see BoltzmannSolverB200Mixin.slotPool)."""
+class _Slot:
+    """What one busy slot of a _SlotPool is doing."""
 
-    def __init__(self, solver, count):
+    __slots__ = ("token", "phase", "event", "keep", "peaks", "raw", "steps", "fresh")
+
+    def __init__(self, token, phase, event, raw=None, steps=0, fresh=True):
+        self.token, self.phase, self.event = token, phase, event
+        self.keep = self.peaks = None
+        self.raw, self.steps, self.fresh = raw, steps, fresh
+
+
+class _SlotPool:
+    """Slots of independent systems in flight on one GPU (see BoltzmannSolverB200Mixin.slotPool).
+
+    reuseFactors=True adds FACTOR RE-USE for sequences of nearby systems (the successive Boltzmann solves inside
+    one `EOM.wallPressure`, equationOfMotion.py:1133-1449: same wall velocity and grid mapping, slowly changing
+    profiles).  A caller that submits such a sequence to a FIXED slot with its position `seq` in the sequence
+    gets, from REUSE_FROM on, the solution of the new system by Richardson iteration preconditioned with the LU
+    factors the slot still holds from the sequence's last factorisation, started from the previous solution:
+    x <- x + (LU_old)^-1 (S_new - A_new x), the residual formed in double-double arithmetic from the operator
+    regenerated on the fly (wg_refine; A_new is never stored).  Steps are enqueued REUSE_CHUNK at a time; the
+    host looks at the history of max|correction| / max|x| behind every chunk and stops at REUSE_TOL (the answer
+    then agrees with a fresh LU + refinement step to ~1e-14), or falls back to the fresh factorisation when the
+    iteration does not contract (profiles changed too much) or REUSE_MAX_STEPS are used up.  A step costs ~1 ms
+    of mostly idle GPU against ~40-100 ms of full-GPU tensor work for a factorisation.  Everything is
+    deterministic, so a sequence gives the same bits wherever and beside whatever it runs."""
+
+    REUSE_FROM = 2          # first position in a sequence that tries the stale factors (0 and 1 always factor)
+    REUSE_CHUNK = 4         # refinement steps enqueued between two looks at the history
+    REUSE_TOL = 1e-13       # max|correction| / max|x| at which the iteration has converged
+    REUSE_MAX_STEPS = 32
+    REUSE_MIN_GAIN = 0.2    # a chunk must shrink the correction at least to this fraction (0.67 per step)
+
+    def __init__(self, solver, count, reuseFactors=False):
         import ctypes
 
         self.sibs = solver._siblings(count)
@@ -49,7 +79,10 @@ class _SlotPool:
             if getattr(s_, "_stream", None) is None:
                 s_._stream = self.torch.cuda.Stream(device=eng.dev)
             eng.stream_ptr = ctypes.c_void_p(s_._stream.cuda_stream)   # pinned while the pool is open
-        self.state = [None] * count      # per slot: (token, phase, event[, keep, peaks])
+        self.state = [None] * count      # per slot: None (free) or a _Slot
+        self.reuse = bool(reuseFactors)
+        self.maxFresh = None             # at most this many factorisations in flight (None: every slot may factor)
+        self.reuseStats = dict(fresh=0, stale=0, fallbacks=0, steps=0)
 
     def close(self):
         for s_ in self.sibs:
@@ -62,45 +95,114 @@ class _SlotPool:
     def busy(self) -> bool:
         return any(st is not None for st in self.state)
 
-    def submit(self, token, background=None, raw=None) -> bool:
-        """Enqueue one system (a BoltzmannBackground, or raw = (T, v, msq, dxidchi, vw)) on a free slot.
-        Returns False when every slot is busy."""
-        for slot, st in enumerate(self.state):
-            if st is None:
-                break
-        else:
+    def _factoring(self) -> int:
+        return sum(1 for st in self.state if st is not None and st.fresh and st.phase == 0)
+
+    @staticmethod
+    def _factorTag(raw):
+        return (float(raw[4]), np.asarray(raw[3], dtype=np.float64).tobytes())
+
+    def _finishSolve(self, s_, eng, token, raw, fresh):
+        """spectra of the solution in eng.S + their download; the slot then waits in phase 0"""
+        torch = self.torch
+        eng.spectra_async(eng.S)
+        eng.spectra_host.copy_(eng.spectra, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(s_._stream)
+        return _Slot(token, 0, ev, raw=raw, fresh=fresh)
+
+    def submit(self, token, background=None, raw=None, slot=None, seq=None) -> bool:
+        """Enqueue one system (a BoltzmannBackground, or raw = (T, v, msq, dxidchi, vw)) on a free slot (or on
+        slot `slot`).  seq: position of the system in a sequence of nearby systems submitted to this slot (see the
+        class docstring; needs reuseFactors, raw and a fixed slot).  Returns False when the slot (every slot) is
+        busy or maxFresh factorisations are already in flight."""
+        if slot is None:
+            for slot, st in enumerate(self.state):
+                if st is None:
+                    break
+            else:
+                return False
+        elif self.state[slot] is not None:
             return False
         s_ = self.sibs[slot]
         torch = self.torch
+        stale = False
+        if self.reuse and raw is not None and seq is not None and int(seq) >= self.REUSE_FROM:
+            eng = s_._engine
+            stale = eng is not None and getattr(eng, "factorTag", None) == self._factorTag(raw)
+        if not stale and self.maxFresh is not None and self._factoring() >= self.maxFresh:
+            return False
         with torch.cuda.stream(s_._stream):
+            if stale:
+                eng = s_._staleStartOnDevice(raw, 0, self.REUSE_CHUNK)
+                ev = torch.cuda.Event()
+                ev.record(s_._stream)
+                self.state[slot] = _Slot(token, "R", ev, raw=raw, steps=self.REUSE_CHUNK, fresh=False)
+                return True
             if raw is None:
                 s_.setBackground(background)
                 eng = s_._solveOnDevice()
+                eng.factorTag = None
             else:
                 eng = s_._solveRawOnDevice(*raw)
-            eng.spectra_async(eng.S)
-            eng.spectra_host.copy_(eng.spectra, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(s_._stream)
-        self.state[slot] = (token, 0, ev)
+                eng.factorTag = self._factorTag(raw) if self.reuse else None
+            self.reuseStats["fresh"] += 1
+            self.state[slot] = self._finishSolve(s_, eng, token, raw, True)
         return True
 
-    def _advance(self, slot, finished):
-        token, phase = self.state[slot][0], self.state[slot][1]
+    def _advanceReuse(self, slot):
+        """Behind a chunk of stale-factor refinement steps: converged -> spectra; contracting -> next chunk;
+        otherwise -> fresh factorisation of the same system."""
+        st = self.state[slot]
         s_ = self.sibs[slot]
         eng = s_._engine
         torch = self.torch
-        if phase == 0:
+        h = eng.rstats_host.numpy()[:st.steps]
+        with np.errstate(all="ignore"):
+            ratio = h[:, 0] / h[:, 1]
+        last = ratio[-1]
+        C = self.REUSE_CHUNK
+        with torch.cuda.stream(s_._stream):
+            if np.isfinite(last) and last <= self.REUSE_TOL:
+                eng.out[eng.nout - 2:].copy_(eng.rstats[st.steps - 1])     # lastRefinement of this solve
+                self.reuseStats["stale"] += 1
+                self.reuseStats["steps"] += st.steps
+                self.state[slot] = self._finishSolve(s_, eng, st.token, st.raw, False)
+                return
+            contracting = np.isfinite(last) and (st.steps < 2 * C or last <= self.REUSE_MIN_GAIN * ratio[-1 - C])
+            if contracting and st.steps + C <= min(self.REUSE_MAX_STEPS, eng.MAX_REUSE_STEPS):
+                s_._staleStartOnDevice(st.raw, st.steps, C)
+                ev = torch.cuda.Event()
+                ev.record(s_._stream)
+                st.event, st.steps = ev, st.steps + C
+                return
+            self.reuseStats["fallbacks"] += 1
+            self.reuseStats["steps"] += st.steps
+            self.reuseStats["fresh"] += 1
+            eng = s_._solveRawOnDevice(*st.raw)
+            eng.factorTag = self._factorTag(st.raw)
+            self.state[slot] = self._finishSolve(s_, eng, st.token, st.raw, True)
+
+    def _advance(self, slot, finished):
+        st = self.state[slot]
+        s_ = self.sibs[slot]
+        eng = s_._engine
+        torch = self.torch
+        if st.phase == "R":
+            self._advanceReuse(slot)
+            return
+        if st.phase == 0:
             keep, peaks = s_._decideTruncation(eng.spectra_host.numpy().copy())
             with torch.cuda.stream(s_._stream):
                 eng.moments_async(eng.S, keep.dev, s_.truncationOption.name != "NONE")
                 eng.out_host.copy_(eng.out, non_blocking=True)
                 ev2 = torch.cuda.Event()
                 ev2.record(s_._stream)
-            self.state[slot] = (token, 1, ev2, keep, peaks)
+            st.phase, st.event, st.keep, st.peaks = 1, ev2, keep, peaks
             return
-        _, _, _, keep, peaks = self.state[slot]
+        keep, peaks = st.keep, st.peaks
         if eng.info() != 0:
+            eng.factorTag = None
             raise np.linalg.LinAlgError("Singular matrix")
         h = eng.out_host.numpy()
         pm = 4 * eng.P * eng.M1
@@ -109,7 +211,7 @@ class _SlotPool:
         err = h[eng.n + pm:eng.n + pm + 4 * eng.P].reshape(eng.P, 4).copy()
         s_.lastRefinement = (float(h[-2]), float(h[-1])) if getattr(s_, "refinementSteps", 1) else None
         self.state[slot] = None
-        finished.append((token, (dF, deltas, err, keep, peaks) if self.rawResults else
+        finished.append((st.token, (dF, deltas, err, keep, peaks) if self.rawResults else
                          s_._wrapResults(dF, deltas, err, keep, peaks)))
 
     rawResults = False   # True: poll() returns the (dF, deltas, err, keep, peaks) tuples instead of BoltzmannResults
@@ -117,14 +219,14 @@ class _SlotPool:
     def poll(self):
         finished = []
         for slot, st in enumerate(self.state):
-            if st is not None and st[2].query():
+            if st is not None and st.event.query():
                 self._advance(slot, finished)
         return finished
 
     def waitOldest(self):
-        live = [(st[0] if isinstance(st[0], int) else k, k) for k, st in enumerate(self.state) if st is not None]
+        live = [(st.token if isinstance(st.token, int) else k, k) for k, st in enumerate(self.state) if st is not None]
         if live:
-            self.state[min(live)[1]][2].synchronize()
+            self.state[min(live)[1]].event.synchronize()
 
 
 class BoltzmannSolverB200Mixin:
@@ -278,6 +380,18 @@ class BoltzmannSolverB200Mixin:
         eng.solve()
         if getattr(self, "refinementSteps", 1):
             eng.refine(float(vw), float(self.collisionMultiplier))
+        return eng
+
+    def _staleStartOnDevice(self, raw, first, count):
+        """`count` Richardson steps towards the solution of the system `raw` = (T, v, msq, dxidchi, vw), starting
+        from whatever eng.S holds (the previous solution of the sequence) with the factors eng.A holds
+        (_SlotPool, reuseFactors).  first = 0 uploads the new profiles."""
+        eng = self._engine
+        T, v, msq, dxidchi, vw = raw
+        if first == 0:
+            eng.upload_profiles(np.asarray(T, dtype=np.float64), np.asarray(v, dtype=np.float64),
+                                np.asarray(msq, dtype=np.float64), np.asarray(dxidchi, dtype=np.float64))
+        eng.refine_steps(float(vw), float(self.collisionMultiplier), first, count)
         return eng
 
     def _solveOnDevice(self, fused: bool = False):
@@ -470,8 +584,10 @@ class BoltzmannSolverB200Mixin:
     def autoConcurrency(n: int, freeBytes: int | None = None) -> int:
         """How many independent systems of size n to keep in flight on one B200.  A single LU of this size
         cannot fill the GPU during its latency-bound panel chain (16 SMs), so a few large systems or many
-        small ones share it (measured: n=15600: 3, n=8700: 4, n=1900: 32 slots)."""
-        c = 3 if n >= 12000 else 4 if n >= 6000 else 8 if n >= 2500 else 32
+        small ones share it.  Measured with tools/knob_sweep.py (round 2, solves/s through getDeltasBatch):
+        n=15600: 2/3/4 slots 10.48/10.55/10.60; n=11600: 3/4/6/8 slots 23.7/24.0/24.2/24.3; n=8700: 4/6/8/12
+        slots 50.6/51.9/51.9/52.3 -- flat beyond the first few, so the table only has to stay clear of too few."""
+        c = 4 if n >= 12000 else 8 if n >= 2500 else 32
         if freeBytes is not None:
             perSlot = 8 * n * n + 2 * 8 * 256 * n + 64 * n + (1 << 20)
             c = max(1, min(c, int(0.6 * freeBytes) // perSlot))
@@ -486,7 +602,7 @@ class BoltzmannSolverB200Mixin:
             self._autoSlots = (eng0.n, self.autoConcurrency(eng0.n, free + have))
         return self._autoSlots[1]
 
-    def slotPool(self, concurrency: int | None = None):
+    def slotPool(self, concurrency: int | None = None, reuseFactors: bool = False):
         """Asynchronous form of getDeltas() for many independent systems: `concurrency` slots (None:
         autoConcurrency), each with its own engine, operator buffer, CUDA stream and captured graphs.
         submit() enqueues one system on a free slot without waiting; poll() advances the slots whose device
@@ -495,7 +611,7 @@ class BoltzmannSolverB200Mixin:
         (wallgo_b200.vwscan) are built on it."""
         if concurrency is None or int(concurrency) <= 0:
             concurrency = self._autoSlotCount()
-        return _SlotPool(self, max(1, int(concurrency)))
+        return _SlotPool(self, max(1, int(concurrency)), reuseFactors)
 
     def getDeltasBatch(self, backgrounds, concurrency: int | None = None):
         """getDeltas() for a list of independent backgrounds (wall-velocity scan points, parameter points),

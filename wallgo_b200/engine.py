@@ -227,6 +227,29 @@ class BoltzmannEngine:
               "wg_refine")
         return x
 
+    MAX_REUSE_STEPS = 64      # rows of the stale-factor refinement history (refine_steps)
+
+    def refine_steps(self, vw: float, collisionMultiplier: float, first: int, count: int):
+        """`count` further refinement steps of self.S against the system of the CURRENT profiles with whatever
+        factors self.A holds (wg_refine: residual of the regenerated operator in double-double, triangular solves,
+        update) -- the factors may belong to an earlier, nearby system (factor re-use across the pressure
+        iteration of one scan point, BoltzmannSolver.slotPool(reuseFactors=True)): the iteration is then a
+        Richardson iteration preconditioned by the stale factors and converges to the solution of the CURRENT
+        system.  Step first+i writes (max|correction|, max|x|) to row first+i of self.rstats; the whole history
+        is copied to pinned host memory (self.rstats_host) behind the last step."""
+        torch = self.torch
+        if getattr(self, "rstats", None) is None:
+            self.rstats = torch.zeros((self.MAX_REUSE_STEPS, 2), dtype=torch.float64, device=self.dev)
+            self.rstats_host = torch.zeros((self.MAX_REUSE_STEPS, 2), dtype=torch.float64).pin_memory()
+        assert 0 <= first and first + count <= self.MAX_REUSE_STEPS
+        A = self._ensure_A()
+        for i in range(first, first + count):
+            check(self.lib.wg_refine(self.h, self.prof.data_ptr(), float(vw), float(collisionMultiplier), A.data_ptr(),
+                                     A.stride(0), self.S.data_ptr(), self.rstats[i].data_ptr(), self._stream()),
+                  "wg_refine")
+        with self._onEngineStream():
+            self.rstats_host.copy_(self.rstats, non_blocking=True)
+
     def info(self) -> int:
         v = C.c_int(0)
         check(self.lib.wg_info(self.h, self._stream(), C.byref(v)), "wg_info")

@@ -77,6 +77,7 @@ def makeRemoteClass(conn):
     class RemoteBoltzmannSolver(BoltzmannSolverB200Mixin, _RefSolver):
         _types = _WallGoTypes
         nSolves = 0
+        pointSeq = 0      # position of the next solve within the current scan point (reset by the worker loop)
 
         def __init__(self, grid, basisM="Cardinal", basisN="Chebyshev", derivatives="Spectral",
                      collisionMultiplier=1.0, truncationOption=None, device=None):
@@ -96,7 +97,8 @@ def makeRemoteClass(conn):
             dxidchi, _, _ = self.grid.getCompactificationDerivatives()
             conn.send(("solve", np.asarray(bg.temperatureProfile, dtype=np.float64),
                        np.asarray(bg.velocityProfile, dtype=np.float64), self._msq(bg.fieldProfiles),
-                       np.asarray(dxidchi, dtype=np.float64), float(bg.velocityWall)))
+                       np.asarray(dxidchi, dtype=np.float64), float(bg.velocityWall), int(type(self).pointSeq)))
+            type(self).pointSeq += 1
             kind, payload = conn.recv()
             if kind == "error":
                 raise np.linalg.LinAlgError(payload)
@@ -135,6 +137,7 @@ def _workerMain(conn, manager, settings):
                 break
             _, idx, vw = msg
             before = cls.nSolves
+            cls.pointSeq = 0            # the solves of one wallPressure form one sequence of nearby systems
             t0 = time.perf_counter()
             out = ws.eom.wallPressure(float(vw), wp0, boltzmannResultsInput=None)
             conn.send(("done", idx, _row(out, cls.nSolves - before), time.perf_counter() - t0))
@@ -230,12 +233,30 @@ def _serverWallSolver(manager, settings):
     return cached[1]
 
 
-def warmUp(manager, settings, vw, concurrency=None):
+def reuseSlots(solver, workers: int, reuseFactors) -> int:
+    """Slots of the solve server when factors are re-used across the solves of a scan point: one per host worker
+    (a worker's sequence of systems must meet its own previous factors), or 0 when re-use is off or the operators
+    of that many slots do not fit the GPU's free memory."""
+    if not reuseFactors or workers <= 0:
+        return 0
+    eng = solver._getEngine()
+    have = sum(1 for s_ in (getattr(solver, "_sibs", None) or [solver])
+               if s_._engine is not None and s_._engine.A is not None)
+    free = eng.torch.cuda.mem_get_info(eng.dev)[0]
+    perSlot = 8 * eng.n * eng.n + 6 * 8 * 256 * eng.n + (64 << 20)
+    return int(workers) if max(0, int(workers) - have) * perSlot < 0.8 * free else 0
+
+
+REUSE_FACTORS = True      # default of scanLocal / scanWallPressure / warmUp
+
+
+def warmUp(manager, settings, vw, concurrency=None, workers=0, reuseFactors=None):
     """One point in-process, then one batch through every slot: engines, operator buffers and CUDA graphs of the
-    whole slot pool exist before a timed scan starts."""
+    whole slot pool exist before a timed scan starts (with factor re-use: one slot per host worker)."""
     rows = scanLocal(manager, settings, [vw], [0], workers=0)
     solver = _serverWallSolver(manager, settings).boltzmannSolver
-    pool = solver.slotPool(concurrency)
+    reuseFactors = REUSE_FACTORS if reuseFactors is None else reuseFactors
+    pool = solver.slotPool(reuseSlots(solver, workers, reuseFactors) or concurrency)
     count = len(pool.sibs)
     pool.close()
     import copy  # pylint: disable=import-outside-toplevel
@@ -246,13 +267,17 @@ def warmUp(manager, settings, vw, concurrency=None):
 
 
 def scanLocal(manager, settings, vws, indices, workers=None, concurrency=None, stats=None, budgetSeconds=None,
-              hostWorkers=None):
+              hostWorkers=None, reuseFactors=None):
     """The points `indices` of `vws` on this process' GPU.  Returns [len(indices), width] rows in the order
     of `indices`.  `manager` is a WallGoManager after setupThermodynamicsHydrodynamics with
     wallgo_b200.dropin installed (dropin.install()); `settings` its WallSolverSettings.
     budgetSeconds: stop handing out points after this long (points are handed out in the order of `indices`;
     rows of points that were not started stay NaN and stats["done"] counts the finished ones).
-    hostWorkers: a HostWorkers started earlier (closed by this call); None: forked here."""
+    hostWorkers: a HostWorkers started earlier (closed by this call); None: forked here.
+    reuseFactors (None: REUSE_FACTORS): from the third Boltzmann solve of a point on, the server first tries to
+    reach the solution by refinement steps preconditioned with the LU factors of the point's last factorisation
+    (BoltzmannSolver.slotPool(reuseFactors=True)); it needs one slot per host worker and is switched off when
+    those do not fit the GPU.  stats["reuse"] = dict(fresh, stale, fallbacks, steps)."""
     from multiprocessing.connection import wait as mpWait
 
     import WallGo  # pylint: disable=import-outside-toplevel
@@ -306,8 +331,22 @@ def scanLocal(manager, settings, vws, indices, workers=None, concurrency=None, s
     if hostWorkers is None:
         hostWorkers = HostWorkers(manager, settings, workers)
     conns = hostWorkers.conns
-    pool = solver.slotPool(concurrency)
+    reuseFactors = REUSE_FACTORS if reuseFactors is None else reuseFactors
+    nReuse = reuseSlots(solver, len(conns), reuseFactors)
+    if nReuse:
+        pool = solver.slotPool(nReuse, reuseFactors=True)
+        # factorisations in flight: what fills the GPU (the other slots wait their turn or iterate on stale factors)
+        pool.maxFresh = int(concurrency) if concurrency else solver._autoSlotCount()
+    else:
+        pool = solver.slotPool(concurrency)
+    slotOf = {c: k for k, c in enumerate(conns)} if nReuse else {}
     pool.rawResults = True
+
+    def submit(c, payload):
+        if nReuse:
+            return pool.submit(c, raw=payload[:5], slot=slotOf[c], seq=payload[5])
+        return pool.submit(c, raw=payload[:5])
+
     todo = list(enumerate(indices))[::-1]
     waiting = []                      # solve requests that found no free slot: (conn, raw)
     done = 0
@@ -321,7 +360,7 @@ def scanLocal(manager, settings, vws, indices, workers=None, concurrency=None, s
                 msg = c.recv()
                 kind = msg[0]
                 if kind == "solve":
-                    if not pool.submit(c, raw=msg[1:]):
+                    if not submit(c, msg[1:]):
                         waiting.append((c, msg[1:]))
                 elif kind in ("ready", "done"):
                     if kind == "done":
@@ -344,20 +383,22 @@ def scanLocal(manager, settings, vws, indices, workers=None, concurrency=None, s
                 dF, deltas, err, keep, peaks = payload
                 c.send(("result", (dF, deltas, err, list(keep), peaks)))
             while waiting and pool.freeSlots():
-                c, raw = waiting.pop(0)
-                pool.submit(c, raw=raw)
+                if not submit(*waiting[0]):
+                    break              # factorisation limit reached: the head of the queue keeps its place
+                waiting.pop(0)
             tServerBusy += time.perf_counter() - t0
     finally:
         pool.close()
         hostWorkers.close()
     stats["server_s"] = tServerBusy
     stats["done"] = done
+    stats["reuse"] = dict(pool.reuseStats, slots=len(pool.sibs), enabled=bool(nReuse))
     assert done == started
     return rows
 
 
 def scanWallPressure(manager, settings, vws, workers=None, concurrency=None, stats=None, budgetSeconds=None,
-                     hostWorkers=None):
+                     hostWorkers=None, reuseFactors=None):
     """All points of `vws`, sharded round-robin over the ranks of the default process group (one per GPU),
     gathered with ONE all_gather.  Every rank returns the full [len(vws), width] table (NaN rows: points a
     rank did not start within budgetSeconds)."""
@@ -371,5 +412,5 @@ def scanWallPressure(manager, settings, vws, workers=None, concurrency=None, sta
     if workers is None:
         workers = defaultWorkers(world)
     rows = scanLocal(manager, settings, vws, mine, workers=workers, concurrency=concurrency, stats=stats,
-                     budgetSeconds=budgetSeconds, hostWorkers=hostWorkers)
+                     budgetSeconds=budgetSeconds, hostWorkers=hostWorkers, reuseFactors=reuseFactors)
     return scan.gatherPoints(rows, len(vws), rows.shape[1])
