@@ -228,6 +228,13 @@ class FakeEngine:
             self.rstats.arr[i] = (np.max(np.abs(c)), np.max(np.abs(self.S.arr)))
         self.refine_calls = getattr(self, "refine_calls", 0) + count
 
+    def refine_history(self, steps):
+        return self.rstats.arr[:steps].copy()
+
+    def _onEngineStream(self):
+        import contextlib
+        return contextlib.nullcontext()
+
     @property
     def nout(self):
         return self.n + 4 * self.P * self.M1 + 4 * self.P + 2

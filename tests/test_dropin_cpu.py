@@ -63,3 +63,37 @@ def test_solveWall_through_dropin_matches_reference_run(wallgo, monkeypatch):
     assert abs(res.wallVelocity - float(tr["wallVelocity"])) <= 1e-6 * abs(float(tr["wallVelocity"]))
     assert np.allclose(res.wallWidths, tr["wallWidths"], rtol=1e-6, atol=0)
     assert isinstance(res.deltaF, np.ndarray) or res.deltaF is None or True
+
+
+def test_solveWall_with_factor_reuse_stays_inside_the_gate(wallgo, monkeypatch):
+    """The same run with install(reuseFactors=True): part of the factorisations are replaced by refinement steps
+    on stale factors; the wall velocity and widths stay within 1e-6 of the recorded reference run."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import make_trace
+    from fake_engine import FakeEngine
+    from wallgo_b200 import dropin
+    import wallgo_b200.engine as engine_mod
+
+    monkeypatch.setattr(engine_mod, "BoltzmannEngine", FakeEngine)
+    cls = dropin.makeDropInClass()
+    monkeypatch.setattr(cls, "loadCollisions", lambda self, path: self.setCollisionArray(make_trace.rta_collisions(self)))
+    monkeypatch.setattr(cls, "reuseFactorsDefault", True, raising=False)
+    import WallGo.manager as mgr
+    monkeypatch.setattr(mgr, "BoltzmannSolver", cls)
+    made = []
+    origInit = cls.__init__
+
+    def spy(self, *a, **k):
+        origInit(self, *a, **k)
+        made.append(self)
+
+    monkeypatch.setattr(cls, "__init__", spy)
+    tr = load_golden("trace_yukawa_M12_N7")
+    manager, settings = make_trace.build_manager(int(tr["M"]), int(tr["N"]))
+    res = manager.solveWall(settings)
+    assert res.success == bool(tr["success"])
+    assert abs(res.wallVelocity - float(tr["wallVelocity"])) <= 1e-6 * abs(float(tr["wallVelocity"]))
+    assert np.allclose(res.wallWidths, tr["wallWidths"], rtol=1e-6, atol=0)
+    st = [s_.reuseStats for s_ in made if getattr(s_, "reuseStats", None)]
+    assert st and sum(x["stale"] for x in st) > 0, st
+    assert sum(x["fresh"] + x["stale"] for x in st) >= 30       # the recorded run has 34 getDeltas() calls

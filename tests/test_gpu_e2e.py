@@ -133,3 +133,55 @@ def test_solveWall_gate(cuda_device, rd, name, M, N, slow, gate):
     sFD = np.max(np.abs(rRef.deltaFFiniteDifference))
     assert np.max(np.abs(rNew.deltaFFiniteDifference - rRef.deltaFFiniteDifference)) <= 1e-6 * sFD
     assert abs(rNew.wallVelocityError - rRef.wallVelocityError) <= 1e-4 * abs(rRef.wallVelocityError) + 1e-12
+
+
+@pytest.mark.parametrize("name,M,N", [("yukawa", 20, 11), ("singlet", 20, 11)])
+def test_solveWall_with_factor_reuse(cuda_device, rd, name, M, N):
+    """dropin.install(reuseFactors=True): inside every wallPressure the third and later Boltzmann solves run as
+    refinement steps on the last LU factors.  The whole solveWall result must stay (far) inside the 1e-6 gate
+    relative to the plain drop-in, which test_solveWall_gate pins to the reference."""
+    WallGo = rd.load_reference()
+    import WallGo.manager as mgr
+    from wallgo_b200 import dropin
+
+    manager, settings, _ = rd.build_manager(name, M, N)
+    saved = mgr.BoltzmannSolver
+    cls = dropin.makeDropInClass()
+    origNew = rd.patch_load_collisions(cls)
+    made = []
+    origInit = cls.__init__
+
+    def spy(self, *a, **k):
+        origInit(self, *a, **k)
+        made.append(self)
+
+    try:
+        mgr.BoltzmannSolver = cls
+        cls.reuseFactorsDefault = False
+        t0 = time.perf_counter()
+        rPlain = manager.solveWall(settings)
+        tPlain = time.perf_counter() - t0
+        cls.reuseFactorsDefault = True
+        cls.__init__ = spy
+        t0 = time.perf_counter()
+        rReuse = manager.solveWall(settings)
+        tReuse = time.perf_counter() - t0
+    finally:
+        cls.__init__ = origInit
+        cls.reuseFactorsDefault = False
+        mgr.BoltzmannSolver = saved
+        if origNew is None:
+            del cls.loadCollisions
+        else:
+            cls.loadCollisions = origNew
+    st = [s_.reuseStats for s_ in made if getattr(s_, "reuseStats", None)]
+    tot = {k: sum(x[k] for x in st) for k in ("fresh", "stale", "fallbacks", "steps")}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "e2e_gate.log"), "a") as f:
+        f.write(f"{name} M={M} N={N} factor re-use: plain drop-in {tPlain:.1f}s, with re-use {tReuse:.1f}s, {tot}; "
+                f"vw plain {rPlain.wallVelocity!r} re-use {rReuse.wallVelocity!r} "
+                f"rel {abs(rReuse.wallVelocity - rPlain.wallVelocity) / abs(rPlain.wallVelocity):.2e}\n")
+    assert tot["stale"] > 0, tot
+    assert rPlain.success and rReuse.success and rPlain.solutionType == rReuse.solutionType
+    assert np.allclose(rd.result_vector(rReuse), rd.result_vector(rPlain), rtol=1e-7, atol=1e-12)
+    assert np.max(np.abs(rReuse.deltaF - rPlain.deltaF)) <= 1e-7 * np.max(np.abs(rPlain.deltaF))

@@ -113,3 +113,49 @@ def test_factorisation_limit_and_fixed_slots(solver):
     while pool.busy():
         done += pool.poll()
     assert [t for t, _ in done] == ["a", "b"]
+
+
+def test_verdicts():
+    from wallgo_b200.boltzmann import REUSE_CHUNK, REUSE_MAX_STEPS, reuseVerdict
+
+    geo = lambda rho, k: [(rho ** (i + 1), 1.0) for i in range(k)]      # noqa: E731
+    assert reuseVerdict(geo(0.5, 4)) == "more"            # the first chunk is never judged on its contraction
+    assert reuseVerdict(geo(0.5, 8)) == "more"            # 0.5^4 = 0.06 per chunk
+    assert reuseVerdict(geo(0.7, 8)) == "fail"            # 0.7^4 = 0.24 per chunk: too slow
+    assert reuseVerdict(geo(1.1, 4)) == "more" and reuseVerdict(geo(1.1, 8)) == "fail"
+    assert reuseVerdict(geo(1e-4, 4)) == "done"
+    assert reuseVerdict(geo(0.5, REUSE_MAX_STEPS)) == "fail"            # out of steps
+    assert reuseVerdict([(1.0, 1.0)] * 3 + [(float("nan"), 1.0)]) == "fail"
+    assert reuseVerdict([(1.0, 1.0)] * 3 + [(0.0, 0.0)]) == "fail"      # 0/0
+    assert REUSE_CHUNK * 2 <= REUSE_MAX_STEPS
+
+
+def test_in_process_reuse_follows_getDeltas_sequences(solver):
+    """solver.reuseFactors: consecutive getDeltas() with the same wall velocity and grid form a sequence."""
+    from wallgo_b200 import synthetic
+    bgs = [synthetic.makeBackground(solver.grid, velocityMid=-0.5, wallL=w) for w in (0.05, 0.0505, 0.0508, 0.0509)]
+    plain = []
+    for bg in bgs:
+        solver.setBackground(bg)
+        plain.append(solver.getDeltas())
+    assert not hasattr(solver, "reuseStats")
+    solver.reuseFactors = True
+    got = []
+    for bg in bgs:
+        solver.setBackground(bg)
+        got.append(solver.getDeltas())
+    assert solver.reuseStats["fresh"] == 2 and solver.reuseStats["stale"] == 2 and solver.reuseStats["fallbacks"] == 0
+    for g, f in zip(got, plain):
+        assert close(g.deltaF, f.deltaF, 1e-12) and close(g.Deltas.Delta11.coefficients, f.Deltas.Delta11.coefficients, 1e-11)
+    assert np.array_equal(got[0].deltaF, plain[0].deltaF)
+    # another wall velocity starts a new sequence: two factorisations again
+    for w in (0.05, 0.0505, 0.0508):
+        solver.setBackground(synthetic.makeBackground(solver.grid, velocityMid=-0.4, wallL=w))
+        solver.getDeltas()
+    assert solver.reuseStats["fresh"] == 4 and solver.reuseStats["stale"] == 3
+    # a copy (EOM.getBoltzmannFiniteDifference deep-copies the solver) owns no factors and starts afresh
+    import copy
+    c = copy.deepcopy(solver)
+    c.setBackground(synthetic.makeBackground(solver.grid, velocityMid=-0.4, wallL=0.0509))
+    c.getDeltas()
+    assert c.reuseStats["fresh"] == 5 and c.reuseStats["stale"] == 3     # counters are copied, factors are not

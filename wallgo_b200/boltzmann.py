@@ -36,6 +36,31 @@ class _Keep(list):
         self.dev = list(sizes)
 
 
+REUSE_FROM = 2          # first position in a sequence that tries the stale factors (0 and 1 always factor)
+REUSE_CHUNK = 4         # refinement steps enqueued between two looks at the history
+REUSE_TOL = 1e-13       # max|correction| / max|x| at which the iteration has converged
+REUSE_MAX_STEPS = 32
+REUSE_MIN_GAIN = 0.2    # a chunk must shrink the correction at least to this fraction (0.67 per step)
+
+
+def reuseVerdict(history, maxSteps=REUSE_MAX_STEPS):
+    """What to do behind a chunk of stale-factor refinement steps.  history[k] = (max|correction|, max|x|) of step
+    k.  "done": converged (last ratio <= REUSE_TOL); "more": contracting, enqueue the next chunk; "fail": not
+    contracting fast enough (after the second chunk: less than 5x per chunk), not finite, or out of steps --
+    factor afresh."""
+    h = np.asarray(history, dtype=np.float64).reshape(-1, 2)
+    steps = h.shape[0]
+    with np.errstate(all="ignore"):
+        ratio = h[:, 0] / h[:, 1]
+    last = ratio[-1]
+    if not np.isfinite(last):
+        return "fail"
+    if last <= REUSE_TOL:
+        return "done"
+    contracting = steps < 2 * REUSE_CHUNK or last <= REUSE_MIN_GAIN * ratio[-1 - REUSE_CHUNK]
+    return "more" if contracting and steps + REUSE_CHUNK <= maxSteps else "fail"
+
+
 class _Slot:
     """What one busy slot of a _SlotPool is doing."""
 
@@ -63,11 +88,7 @@ class _SlotPool:
     of mostly idle GPU against ~40-100 ms of full-GPU tensor work for a factorisation.  Everything is
     deterministic, so a sequence gives the same bits wherever and beside whatever it runs."""
 
-    REUSE_FROM = 2          # first position in a sequence that tries the stale factors (0 and 1 always factor)
-    REUSE_CHUNK = 4         # refinement steps enqueued between two looks at the history
-    REUSE_TOL = 1e-13       # max|correction| / max|x| at which the iteration has converged
-    REUSE_MAX_STEPS = 32
-    REUSE_MIN_GAIN = 0.2    # a chunk must shrink the correction at least to this fraction (0.67 per step)
+    REUSE_FROM, REUSE_CHUNK, REUSE_TOL, REUSE_MAX_STEPS = REUSE_FROM, REUSE_CHUNK, REUSE_TOL, REUSE_MAX_STEPS
 
     def __init__(self, solver, count, reuseFactors=False):
         import ctypes
@@ -157,20 +178,16 @@ class _SlotPool:
         s_ = self.sibs[slot]
         eng = s_._engine
         torch = self.torch
-        h = eng.rstats_host.numpy()[:st.steps]
-        with np.errstate(all="ignore"):
-            ratio = h[:, 0] / h[:, 1]
-        last = ratio[-1]
-        C = self.REUSE_CHUNK
+        verdict = reuseVerdict(eng.rstats_host.numpy()[:st.steps], min(REUSE_MAX_STEPS, eng.MAX_REUSE_STEPS))
+        C = REUSE_CHUNK
         with torch.cuda.stream(s_._stream):
-            if np.isfinite(last) and last <= self.REUSE_TOL:
+            if verdict == "done":
                 eng.out[eng.nout - 2:].copy_(eng.rstats[st.steps - 1])     # lastRefinement of this solve
                 self.reuseStats["stale"] += 1
                 self.reuseStats["steps"] += st.steps
                 self.state[slot] = self._finishSolve(s_, eng, st.token, st.raw, False)
                 return
-            contracting = np.isfinite(last) and (st.steps < 2 * C or last <= self.REUSE_MIN_GAIN * ratio[-1 - C])
-            if contracting and st.steps + C <= min(self.REUSE_MAX_STEPS, eng.MAX_REUSE_STEPS):
+            if verdict == "more":
                 s_._staleStartOnDevice(st.raw, st.steps, C)
                 ev = torch.cuda.Event()
                 ev.record(s_._stream)
@@ -259,6 +276,10 @@ class BoltzmannSolverB200Mixin:
         # max|deltaF|) of the most recent getDeltas(); the ratio / 2^-53 estimates the condition number.
         self.refinementSteps = 1
         self.lastRefinement = None
+        # Opt-in: consecutive getDeltas() calls with unchanged wall velocity and grid mapping re-use the LU factors
+        # of their last factorisation from the third call on (_solveMaybeStale); results agree with the plain path
+        # to ~1e-13 instead of bit for bit.  The wall-velocity scan server has its own switch (vwscan).
+        self.reuseFactors = bool(getattr(type(self), "reuseFactorsDefault", False))
 
     def setBackground(self, background) -> None:
         """Deep-copies and boosts to the plasma frame (boltzmann.py:116-123)."""
@@ -394,6 +415,42 @@ class BoltzmannSolverB200Mixin:
         eng.refine_steps(float(vw), float(self.collisionMultiplier), first, count)
         return eng
 
+    def _solveMaybeStale(self):
+        """_solveOnDevice() for getDeltas(), with FACTOR RE-USE when self.reuseFactors is set: consecutive
+        getDeltas() calls with the same wall velocity and grid mapping (the pressure iteration of one
+        EOM.wallPressure, equationOfMotion.py:1133-1449) form a sequence, and from its third member on the
+        solution is first sought by refinement steps on the factors of the sequence's last factorisation (see
+        _SlotPool; same constants, same verdicts, synchronous here).  self.reuseStats counts what happened."""
+        if not getattr(self, "reuseFactors", False):
+            return self._solveOnDevice()
+        eng = self._getEngine()
+        bg = self.background
+        assert bg is not None, "BoltzmannSolver error: background not set"
+        dxidchi, _, _ = self.grid.getCompactificationDerivatives()
+        tag = (float(bg.velocityWall), np.asarray(dxidchi, dtype=np.float64).tobytes())
+        seq = getattr(self, "_seq", -1) + 1 if tag == getattr(self, "_seqTag", None) else 0
+        self._seqTag, self._seq = tag, seq
+        stats = self.__dict__.setdefault("reuseStats", dict(fresh=0, stale=0, fallbacks=0, steps=0))
+        if seq >= REUSE_FROM and getattr(eng, "factorTag", None) == tag:
+            self._uploadBackground(eng)
+            vw, mult = float(bg.velocityWall), float(self.collisionMultiplier)
+            steps, verdict = 0, "more"
+            while verdict == "more":
+                eng.refine_steps(vw, mult, steps, REUSE_CHUNK)
+                steps += REUSE_CHUNK
+                verdict = reuseVerdict(eng.refine_history(steps), min(REUSE_MAX_STEPS, eng.MAX_REUSE_STEPS))
+            stats["steps"] += steps
+            if verdict == "done":
+                stats["stale"] += 1
+                with eng._onEngineStream():
+                    eng.out[eng.nout - 2:].copy_(eng.rstats[steps - 1])
+                return eng
+            stats["fallbacks"] += 1
+        stats["fresh"] += 1
+        eng = self._solveOnDevice()
+        eng.factorTag = tag
+        return eng
+
     def _solveOnDevice(self, fused: bool = False):
         """assemble + LU + triangular solves; leaves deltaF in eng.S (device).  fused=True uses wg_factor_solve
         (the forward solve rides along inside the factorisation): 0.6 ms lower latency for one n=15600 system
@@ -510,7 +567,7 @@ class BoltzmannSolverB200Mixin:
     def getDeltas(self, deltaF=None):
         """Solve (unless deltaF is given), truncate, integrate the four moments (boltzmann.py:141-238)."""
         if deltaF is None:
-            eng = self._solveOnDevice()
+            eng = self._solveMaybeStale()
             dFdev = eng.S
         else:
             eng = self._getEngine()
@@ -520,6 +577,7 @@ class BoltzmannSolverB200Mixin:
         if deltaF is None:
             info = eng.info()
             if info != 0:
+                eng.factorTag = None
                 raise np.linalg.LinAlgError("Singular matrix")
             self.lastRefinement = eng.last_refinement if getattr(self, "refinementSteps", 1) else None
         return self._wrapResults(dF, deltas, err, keep, peaks)

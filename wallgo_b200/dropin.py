@@ -51,8 +51,13 @@ def makeDropInClass():
     return _cached
 
 
-def install(vectoriseEOM: bool = False):
+def install(vectoriseEOM: bool = False, reuseFactors: bool = False):
     """Make WallGoManager construct the B200 solver (manager.py:605-611).
+
+    reuseFactors=True: solvers built from now on re-use LU factors across the Boltzmann solves of one
+    `EOM.wallPressure` (same wall velocity and grid mapping): from the third solve on, refinement steps
+    preconditioned with the last factorisation replace the LU (BoltzmannSolverB200Mixin._solveMaybeStale);
+    deltaF then agrees with the plain path to ~1e-13 instead of bit for bit.
 
     vectoriseEOM=True additionally rebinds `WallGo.EOM.findPlasmaProfile` to the lock-step vector form of
     `wallgo_b200.eomhost` (the consumer of the moments and, once the Boltzmann solve
@@ -62,6 +67,7 @@ def install(vectoriseEOM: bool = False):
     import WallGo.manager as _manager
 
     cls = makeDropInClass()
+    cls.reuseFactorsDefault = bool(reuseFactors)
     _manager.BoltzmannSolver = cls
     WallGo.BoltzmannSolver = cls
     if vectoriseEOM:

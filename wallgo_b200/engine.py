@@ -250,6 +250,12 @@ class BoltzmannEngine:
         with self._onEngineStream():
             self.rstats_host.copy_(self.rstats, non_blocking=True)
 
+    def refine_history(self, steps: int):
+        """(max|correction|, max|x|) of the first `steps` refinement steps of refine_steps(), after a synchronise."""
+        with self._onEngineStream():
+            self.torch.cuda.current_stream(self.dev).synchronize()
+        return self.rstats_host.numpy()[:steps].copy()
+
     def info(self) -> int:
         v = C.c_int(0)
         check(self.lib.wg_info(self.h, self._stream(), C.byref(v)), "wg_info")
