@@ -589,7 +589,8 @@ def run_small(a, rank, world, local, lib, fp64_peak_fn):
     eng = solver._getEngine()
     n, nprof, dev = eng.n, eng.nprof, eng.dev
     fp64_peak = fp64_peak_fn(dev)
-    bes = [BatchEngine(eng, B), BatchEngine(eng, B)]
+    F = max(1, int(a.inflight))
+    bes = [BatchEngine(eng, B) for _ in range(F)]
     inp = np.empty((K + W, B, nprof + 1))
     L = M + 1
     for i, bg in enumerate(bgs):
@@ -637,8 +638,8 @@ def run_small(a, rank, world, local, lib, fp64_peak_fn):
         if world > 1:
             dist.barrier()
 
-    for i in range(W):
-        step(bes[i % 2], i)
+    for i in range(max(W, F)):
+        step(bes[i % F], i % W)
     torch.cuda.synchronize()
     rec = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
     step(bes[0], 0, rec)
@@ -656,7 +657,7 @@ def run_small(a, rank, world, local, lib, fp64_peak_fn):
     for be in bes:
         be.stream.wait_event(start)
     for i in range(K):
-        step(bes[i % 2], W + i)
+        step(bes[i % F], W + i)
     for be in bes:
         done = torch.cuda.Event()
         done.record(be.stream)
@@ -1157,6 +1158,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--batch", type=int, default=64,
                     help="small systems (cfg1): systems per lock-step strided batch (0: the slot-pool path instead)")
+    ap.add_argument("--inflight", type=int, default=2,
+                    help="developer knob (small systems): strided batches in flight for the device-resident value")
     ap.add_argument("--panel-groups", type=int, default=6,
                     help="cfg5stream: (species, position) row groups per panel (6 x 900 rows x 226800 columns = 9.8 GB)")
     ap.add_argument("--scan-points", type=int, default=None,
