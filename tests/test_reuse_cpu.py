@@ -159,3 +159,21 @@ def test_in_process_reuse_follows_getDeltas_sequences(solver):
     c.setBackground(synthetic.makeBackground(solver.grid, velocityMid=-0.4, wallL=0.0509))
     c.getDeltas()
     assert c.reuseStats["fresh"] == 5 and c.reuseStats["stale"] == 3     # counters are copied, factors are not
+
+
+def test_new_static_data_drops_the_stale_factors(solver):
+    """A new collision tensor between two members of a sequence: the next member factors afresh."""
+    from wallgo_b200 import synthetic
+    raws = sequence(solver, [0.05, 0.0505, 0.0508, 0.0509])
+    pool = solver.slotPool(1, reuseFactors=True)
+    run(pool, raws[:3], slot=0, seqs=range(3))
+    assert pool.reuseStats["stale"] == 1
+    for s_ in pool.sibs:
+        s_.setCollisionArray(synthetic.makeCollision(solver.grid, solver.offEqParticles, r=0.4))
+    out = {}
+    assert pool.submit(3, raw=raws[3], slot=0, seq=3)
+    while pool.busy():
+        out.update(dict(pool.poll()))
+    assert pool.reuseStats["stale"] == 1 and pool.reuseStats["fresh"] == 3
+    fresh = run(solver.slotPool(1), raws[3:])
+    assert np.array_equal(out[3].deltaF, fresh[0].deltaF)

@@ -149,8 +149,8 @@ class _SlotPool:
         torch = self.torch
         stale = False
         if self.reuse and raw is not None and seq is not None and int(seq) >= self.REUSE_FROM:
-            eng = s_._engine
-            stale = eng is not None and getattr(eng, "factorTag", None) == self._factorTag(raw)
+            eng = s_._getEngine()      # (a change of the static data re-uploads it and drops the factor tag)
+            stale = getattr(eng, "factorTag", None) == self._factorTag(raw)
         if not stale and self.maxFresh is not None and self._factoring() >= self.maxFresh:
             return False
         with torch.cuda.stream(s_._stream):
@@ -376,6 +376,7 @@ class BoltzmannSolverB200Mixin:
             assert coll.shape == (P, g.N - 1, g.N - 1, P, g.N - 1, g.N - 1), "collision tensor has the wrong shape"
             eng.set_collision(coll)
             self._staticKey = key
+            eng.factorTag = None       # factors of an operator built from other static data are not re-used
         return eng
 
     def _msq(self, fields):
