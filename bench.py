@@ -393,13 +393,15 @@ def run_scan(a, world, rank, local, prep=None):
             "workload": f"{a.scan_model}: P={P} M={M} N={N} n={n}, vw in [{vws[0]:.3f}, {vws[-1]:.3f}], "
                         "relaxation-time collision tensor",
             "point": "EOM.wallPressure(vw_i, wallParams0, None) of the unmodified reference wall solver, Boltzmann "
-                     "solves on the GPU via wallgo_b200.dropin (vectoriseEOM); one all_gather of the result rows",
+                     "solves on the GPU via wallgo_b200.dropin (vectoriseEOM), LU factors re-used across the solves of a "
+                     "point unless --scan-reuse 0 (factor_reuse below); one all_gather of the result rows",
             "host_workers_per_rank": int(workers), "points_per_rank": mine,
             "host_cores": os.cpu_count(), "gpus_in_node": vwscan._physicalGpus(),
             "host_budget": "workers per rank = min(12, share - 1 if share >= 6 else share), share = cores // GPUs installed in the node: the same host share per "
                            "GPU at every rank count, so the scan's strong scaling is that of the GPUs with their share of "
                            "the host.  A point costs ~0.7 s of the reference's host Python per worker and ~0.15 s of GPU "
-                           "(3.7 solves): ~5 workers saturate one GPU's solve server, fewer leave the scan host-bound",
+                           "(3.7 factorisations; ~0.09 s with factor re-use: 2 factorisations + 1.7 stale-factor solves): "
+                           "5-8 workers saturate one GPU's solve server, fewer leave the scan host-bound",
             "boltzmann_solves": solves, "solves_per_point": solves / max(1, ndone),
             "host_seconds_per_point": hostTotal / max(1, ndone),
             "host_note": "wall time a point spends in the reference's host loop + waiting for its solves (queueing "

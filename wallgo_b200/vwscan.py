@@ -16,8 +16,15 @@ cannot keep a B200 busy.  Layout per rank (one process per GPU, as everywhere in
   * points are handed out dynamically (the iteration count varies per vw); ranks take points round-robin
     and one all_gather of the per-point rows ends the scan (wallgo_b200.scan.gatherPoints).
 
-Every point starts from the same (wallParams0, deltaF = 0), and the device path is batch-invariant, so the
-table is identical for any number of workers and GPUs (checked by a checksum in bench.py and by the tests).
+  * FACTOR RE-USE (default, `reuseFactors`): the ~4 solves of a point share wall velocity and grid mapping, so the
+    server gives every worker its own slot and, from the third solve of a point on, reaches the solution by
+    refinement steps preconditioned with the LU factors of the point's last factorisation instead of factoring
+    again (BoltzmannSolver.slotPool(reuseFactors=True)); workers send the position of each solve within its point.
+
+Every point starts from the same (wallParams0, deltaF = 0), the device path is batch-invariant and the re-use
+decisions depend only on the point's own sequence, so the table is identical for any number of workers and GPUs
+(checked by a checksum in bench.py and by the tests); without re-use it is also bit-identical to the sequential
+in-process loop, with re-use it agrees with it to ~1e-9 (deltaF to ~1e-13).
 `workers=0` runs the points sequentially in the rank process through the plain drop-in class.
 
 Needs WallGo (the reference) importable, like wallgo_b200.dropin.
