@@ -24,20 +24,19 @@ small = n <= wb.BoltzmannSolver.STRIDED_MAX_N
 ref = None
 import itertools
 for nb, l32, sp in itertools.product(nbs, leafs, splits):
-    if True:
-        for c in slots:
-            lib.wg_set_tuning(nb, 1); lib.wg_debug_leaf32(l32); lib.wg_set_bulk_split(sp)
-            cc = None if (small or c <= 0) else c
-            nsys = 256 if small else max(2, (c if c > 0 else 4) * per)
-            bgs = [synthetic.makeBackground(grid, velocityMid=-0.3 - 0.001 * i) for i in range(nsys)]
-            s.getDeltasBatch(bgs[:max(2, (128 if small else (c if c > 0 else 4)))], concurrency=cc)   # graphs captured
-            torch.cuda.synchronize(); t0 = time.perf_counter()
-            res = s.getDeltasBatch(bgs, concurrency=cc)
-            torch.cuda.synchronize(); dt = time.perf_counter() - t0
-            d = np.concatenate([r.Deltas.Delta00.coefficients.ravel() for r in res])
-            same = "" if ref is None else f"  Delta00 == first run: {bool(np.array_equal(d[:ref.size], ref[:d.size]))}"
-            if ref is None: ref = d
-            print(f"P={P} M={M} N={N} n={n} nb={nb} leaf32={l32} split={sp} slots={'auto' if cc is None else c}: "
-                  f"{nsys / dt:.2f} solves/s ({1e3 * dt / nsys:.2f} ms/solve, "
-                  f"{nsys * 2 / 3 * n ** 3 / dt / 1e12:.2f} TFLOP/s){same}", flush=True)
+    for c in slots:
+        lib.wg_set_tuning(nb, 1); lib.wg_debug_leaf32(l32); lib.wg_set_bulk_split(sp)
+        cc = None if (small or c <= 0) else c
+        nsys = 256 if small else max(2, (c if c > 0 else 4) * per)
+        bgs = [synthetic.makeBackground(grid, velocityMid=-0.3 - 0.001 * i) for i in range(nsys)]
+        s.getDeltasBatch(bgs[:max(2, (128 if small else (c if c > 0 else 4)))], concurrency=cc)   # graphs captured
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        res = s.getDeltasBatch(bgs, concurrency=cc)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        d = np.concatenate([r.Deltas.Delta00.coefficients.ravel() for r in res])
+        same = "" if ref is None else f"  Delta00 == first run: {bool(np.array_equal(d[:ref.size], ref[:d.size]))}"
+        if ref is None: ref = d
+        print(f"P={P} M={M} N={N} n={n} nb={nb} leaf32={l32} split={sp} slots={'auto' if cc is None else c}: "
+              f"{nsys / dt:.2f} solves/s ({1e3 * dt / nsys:.2f} ms/solve, "
+              f"{nsys * 2 / 3 * n ** 3 / dt / 1e12:.2f} TFLOP/s){same}", flush=True)
 lib.wg_debug_leaf32(0); lib.wg_set_tuning(256, 1); lib.wg_set_bulk_split(1)
