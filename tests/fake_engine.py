@@ -196,7 +196,10 @@ class FakeEngine:
         return bo.Problem(tab=self.tab, xi_dxidchi=dxidchi, pz=pz, pp=pp, dpzdrz=dpzdrz, dppdrp=dppdrp, T=T, v=v,
                           msq=msq, vw=vw, statistics=self.stat, collision=self.coll, collisionMultiplier=mult)
 
+    factorTag = None
+
     def assemble(self, vw, collisionMultiplier=1.0, parts=3, A=None):
+        self.factorTag = None
         self.pb = self._problem(vw, collisionMultiplier)
         op, src = bo.assemble(self.pb)
         self.A, self.S = _NP(op), _NP(src.copy())

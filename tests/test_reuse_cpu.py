@@ -177,3 +177,23 @@ def test_new_static_data_drops_the_stale_factors(solver):
     assert pool.reuseStats["stale"] == 1 and pool.reuseStats["fresh"] == 3
     fresh = run(solver.slotPool(1), raws[3:])
     assert np.array_equal(out[3].deltaF, fresh[0].deltaF)
+
+
+def test_other_uses_of_the_operator_buffer_drop_the_tag(solver):
+    """buildLinearEquations() between two members of a getDeltas() sequence re-assembles into the operator buffer:
+    the next member must not take it for factors."""
+    from wallgo_b200 import synthetic
+    solver.reuseFactors = True
+    bgs = [synthetic.makeBackground(solver.grid, velocityMid=-0.5, wallL=w) for w in (0.05, 0.0505, 0.0508, 0.0509)]
+    for bg in bgs[:3]:
+        solver.setBackground(bg)
+        solver.getDeltas()
+    assert solver.reuseStats["stale"] == 1 and solver._engine.factorTag is not None
+    solver.buildLinearEquations()
+    assert solver._engine.factorTag is None
+    solver.setBackground(bgs[3])
+    res = solver.getDeltas()
+    assert solver.reuseStats["stale"] == 1 and solver.reuseStats["fresh"] == 3
+    solver.reuseFactors = False
+    solver.setBackground(bgs[3])
+    assert np.array_equal(res.deltaF, solver.getDeltas().deltaF)

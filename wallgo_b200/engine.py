@@ -57,6 +57,9 @@ class BoltzmannEngine:
         self.dF_in = torch.empty(self.n, dtype=f64, device=self.dev)
         self.launches = 0  # kernels launched through this engine (rough, for bench accounting)
         self.stream_ptr = None
+        # Factor re-use (BoltzmannSolver.slotPool(reuseFactors=True)): what the LU factors in self.A belong to, as set
+        # by the caller that enqueued the factorisation; every assemble() / factor() of this engine clears it.
+        self.factorTag = None
 
     # ------------------------------------------------------------------ lifecycle
     def close(self):
@@ -193,6 +196,8 @@ class BoltzmannEngine:
             self.prof.copy_(self.prof_host, non_blocking=True)
 
     def assemble(self, vw: float, collisionMultiplier: float = 1.0, parts: int = 3, A=None):
+        if A is None:
+            self.factorTag = None      # the operator buffer no longer holds the factors of an earlier system
         A = self._ensure_A() if A is None else A
         check(self.lib.wg_assemble(self.h, self.prof.data_ptr(), float(vw), float(collisionMultiplier),
                                    int(parts), A.data_ptr(), A.stride(0), self.S.data_ptr(), self._stream()),
@@ -201,12 +206,14 @@ class BoltzmannEngine:
 
     def factor(self):
         A = self._ensure_A()
+        self.factorTag = None
         check(self.lib.wg_factor(self.h, A.data_ptr(), A.stride(0), self._stream()), "wg_factor")
 
     def factor_solve(self, b=None):
         """np.linalg.solve in one call: LU with the forward solve of b riding along, then the backward solve."""
         b = self.S if b is None else b
         A = self._ensure_A()
+        self.factorTag = None
         check(self.lib.wg_factor_solve(self.h, A.data_ptr(), A.stride(0), b.data_ptr(), self._stream()), "wg_factor_solve")
         return b
 
