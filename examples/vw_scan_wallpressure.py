@@ -11,7 +11,9 @@ model (the bench and the tests use oracle/ref_drivers.py for the four shipped ex
 
 Structure (wallgo_b200/vwscan.py): each rank builds its own manager, forks its host workers BEFORE it touches CUDA,
 then runs a solve server on its GPU; workers execute the reference's pressure iteration and send every getDeltas()
-to the server; one all_gather returns the table to every rank.
+to the server; one all_gather returns the table to every rank.  By default the server re-uses the LU factors across
+the solves of a point (third solve on: refinement steps on the last factors instead of a new LU; --no-reuse for the
+plain path, bit-identical to the sequential drop-in).
 """
 import argparse
 import importlib.util
@@ -35,6 +37,7 @@ def main():
     ap.add_argument("--model", required=True, help="model file below Models/")
     ap.add_argument("--points", type=int, default=256)
     ap.add_argument("--vmax", type=float, default=0.53)
+    ap.add_argument("--no-reuse", action="store_true", help="factor every system afresh")
     a = ap.parse_args()
     sys.path.insert(0, os.path.join(a.wallgo, "src"))
     sys.path.insert(0, os.path.join(a.wallgo, "Models"))
@@ -59,8 +62,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stats = {}
-    table = vwscan.scanWallPressure(manager, settings, vws, stats=stats, hostWorkers=workers)
+    table = vwscan.scanWallPressure(manager, settings, vws, stats=stats, hostWorkers=workers,
+                                    reuseFactors=not a.no_reuse)
     if rank == 0:
+        print("factor re-use on rank 0:", stats.get("reuse"))
         ws = manager.setupWallSolver(settings)
         nF, P, M = ws.eom.nbrFields, len(ws.boltzmannSolver.offEqParticles), ws.boltzmannSolver.grid.M
         for i in (0, len(vws) // 2, len(vws) - 1):
